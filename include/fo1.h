@@ -1,0 +1,125 @@
+/*
+ * fo1.h -- C ABI of libfo1.so, the B200 (sm_100a) engine for the VLM-FO1 inference hot path.
+ *
+ * Plain C types only: device pointers, sizes, a cudaStream_t passed as void*.  Every entry point
+ * returns 0 on success or a negative fo1_status; fo1_last_error() returns a message for the calling
+ * thread.  Nothing here allocates on the hot path: callers own inputs/outputs and hand the library a
+ * workspace; the model-level handle owns its weights and one arena sized when the model is created.
+ * All entry points enqueue on the given stream and return (asynchronous) unless stated otherwise.
+ *
+ * Each declaration cites the reference interface (om-ai-lab/VLM-FO1 @ e6bef8d) it replaces.
+ * The reference has no FFI of its own (pure PyTorch); INTEGRATION.md shows the ctypes binding a
+ * maintainer adds under vlm_fo1/model/.
+ */
+#ifndef FO1_H_
+#define FO1_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FO1_ABI_VERSION 1
+
+typedef enum {
+  FO1_OK = 0,
+  FO1_ERR_INVALID_ARG = -1,
+  FO1_ERR_CUDA = -2,
+  FO1_ERR_UNSUPPORTED = -3,
+  FO1_ERR_WORKSPACE = -4,
+  FO1_ERR_NOT_FOUND = -5,
+  FO1_ERR_STATE = -6
+} fo1_status;
+
+typedef enum { FO1_BF16 = 0, FO1_F32 = 1, FO1_I32 = 2, FO1_I64 = 3, FO1_U8 = 4, FO1_F16 = 5 } fo1_dtype;
+
+int fo1_abi_version(void);
+/* Message describing the last failure on this thread ("" if none). */
+const char* fo1_last_error(void);
+/* Number of kernels this library has launched since load / since the last reset (all threads). */
+uint64_t fo1_launch_count(void);
+void fo1_launch_count_reset(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * HFRE -- Hybrid Fine-grained Region Encoder.
+ * Replaces HFREModule.__call__ (vlm_fo1/model/multimodal_visual_prompt_encoder/
+ * hybrid_finegrained_region_encoder.py:275-468) as called from encode_regions
+ * (vlm_fo1/model/language_model/omchat_qwen2_5_vl.py:101-106): ROIAlign(7x7, adaptive sampling,
+ * aligned=False) + mean over bins on every pyramid level of both towers, channel concat, and the
+ * sinusoidal box embedding -- WITHOUT materialising the up-sampled/concatenated map (:338-350).
+ * ---------------------------------------------------------------------------------------------- */
+
+/* One feature level: bf16, channels-last [H][W][C] in device memory, C % 8 == 0, 16-byte aligned. */
+typedef struct {
+  const void* data;
+  int32_t H, W, C;
+  int32_t up_H, up_W;     /* grid the reference bilinearly up-samples this level to before ROIAlign
+                             (F.interpolate align_corners=False, :341-346); == H, W when it does not */
+  float spatial_scale;    /* ROIAlign spatial_scale on that (up-sampled) grid: 0.25 aux (:357),
+                             1/14 taps (:267), 1/3.5 .. 1/28 FPN (:245-253) */
+  int32_t box_set;        /* 0: aux boxes, 1: primary-tower ("vt") boxes */
+  int32_t out_offset;     /* first output channel written by this level */
+} fo1_hfre_level;
+
+#define FO1_HFRE_MAX_LEVELS 8
+
+/* One image's work. */
+typedef struct {
+  fo1_hfre_level levels[FO1_HFRE_MAX_LEVELS];
+  int32_t n_levels;
+  int32_t n_boxes;
+  const float* boxes_aux;  /* [n_boxes][4] xyxy, aux-tensor pixels (device) */
+  const float* boxes_vt;   /* [n_boxes][4] xyxy, primary-tower pixels (device); may equal boxes_aux */
+  float* out;              /* [n_boxes][out_dim] fp32 (device) */
+  void* out_bf16;          /* optional [n_boxes][out_dim] bf16 copy for the projector GEMM, or NULL */
+  float pos_img_w, pos_img_h; /* normaliser of the box embedding (:447-448): grid * 14 */
+  int32_t pos_box_set;     /* which boxes feed the embedding (:442-452): 1 = vt */
+} fo1_hfre_image;
+
+typedef struct {
+  int32_t out_dim;          /* D = mm_region_hidden_size (5888 variant B, 8960 variant A) */
+  int32_t roi_size;         /* 7 (omchat_arch.py:18) */
+  int32_t apply_pos_embed;  /* mm_apply_position_embedding, bbox_based */
+  int32_t algo;             /* 0 = auto, 1 = per-box gather, 2 = map sweep */
+} fo1_hfre_params;
+
+/* Bytes of device workspace fo1_hfre_forward needs for these images (host-side arithmetic only). */
+size_t fo1_hfre_workspace_bytes(const fo1_hfre_image* images, int32_t n_images, const fo1_hfre_params* p);
+/* Enqueue HFRE for n_images images.  `images` is a HOST array (device pointers inside). */
+int fo1_hfre_forward(const fo1_hfre_image* images, int32_t n_images, const fo1_hfre_params* p,
+                     void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Dense contraction: D[M,N] = epilogue(A[M,K] . W[N,K]^T) -- bf16 operands, fp32 accumulate in TMEM
+ * (tcgen05.mma, operands staged by TMA).  Replaces every nn.Linear / 1x1 conv / patch-embed on the
+ * path (modeling_qwen2_5_vl.py:88-111, 176-177, 151-155, 731-734, 633-635; modeling_davit.py:62-66,
+ * 157-158, 235-236; simple_fpn.py:143-175; multimodal_projector/builder.py:100-106).
+ * ---------------------------------------------------------------------------------------------- */
+typedef enum {
+  FO1_EPI_NONE = 0,
+  FO1_EPI_GELU = 1,          /* exact erf GELU (nn.GELU default) */
+  FO1_EPI_SILU = 2
+} fo1_epilogue_act;
+
+typedef struct {
+  int32_t M, N, K;
+  const void* A; int64_t lda;      /* bf16 [M][K], row stride lda elements (lda*2 % 16 == 0) */
+  const void* W; int64_t ldw;      /* bf16 [N][K] (nn.Linear weight layout) */
+  void* D; int64_t ldd;            /* output [M][N], bf16 or fp32 */
+  int32_t d_dtype;                 /* FO1_BF16 or FO1_F32 */
+  const void* bias;                /* optional [N], bias_dtype */
+  int32_t bias_dtype;              /* FO1_BF16 or FO1_F32 */
+  int32_t act;                     /* fo1_epilogue_act, applied after bias */
+  const void* residual; int64_t ldr; /* optional bf16 [M][N] added after act */
+  int32_t gated;                   /* 1: W rows interleave [32 gate | 32 up] blocks -> D[M][N/2] =
+                                      act(gate)*up  (Qwen2MLP, modeling_qwen2_5_vl.py:84-85,638-640) */
+} fo1_gemm_desc;
+
+int fo1_gemm_bf16(const fo1_gemm_desc* d, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FO1_H_ */

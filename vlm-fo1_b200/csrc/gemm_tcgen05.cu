@@ -1,0 +1,368 @@
+// gemm_tcgen05.cu -- D[M,N] = epilogue(A[M,K] . W[N,K]^T): the one dense-contraction kernel of the
+// engine (every nn.Linear / 1x1 conv / patch-embed / projector / LM head on the FO1 path).
+//
+// Blackwell-native structure (no wgmma, no mma.sync):
+//   * persistent CTAs, one per SM, static round-robin over 128 x BN output tiles;
+//   * warp 0  : TMA producer  -- cp.async.bulk.tensor 2-D tiles (128B swizzle) of A and W into a
+//               STAGES-deep shared-memory ring, completion on mbarriers (expect_tx);
+//   * warp 1  : MMA issuer    -- one elected thread issues tcgen05.mma (kind::f16, bf16 x bf16 -> fp32,
+//               UMMA 128 x BN x 16) straight from shared-memory descriptors into TMEM; tcgen05.commit
+//               releases ring slots and publishes finished accumulators;
+//   * warps 2-5: epilogue     -- tcgen05.ld TMEM -> registers, bias / GELU / SiLU / gated-SiLU /
+//               residual fused, bf16 or fp32 stores.  Two TMEM accumulator stages (2 x BN columns) let
+//               the epilogue of tile i overlap the main loop of tile i+1.
+// Out-of-bounds rows/cols/K are zero-filled by TMA on load and predicated on store, so M, N, K need no
+// padding beyond 16-byte row pitches.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace fo1 {
+
+constexpr int BM = 128;
+constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle atom row
+constexpr int UMMA_K = 16;
+constexpr int kGemmThreads = 192;
+constexpr int kEpiWarp0 = 2;
+
+struct GemmArgs {
+  int M, N, K;
+  void* D; long long ldd; int d_dtype;
+  const void* bias; int bias_dtype;
+  int act;
+  const __nv_bfloat16* residual; long long ldr;
+  int gated;
+  int tiles_m, tiles_n;
+};
+
+template <int BN>
+struct GemmCfg {
+  static constexpr int kStageBytes = (BM * BK + BN * BK) * 2;
+  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int kTmemCols = 2 * BN;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+__device__ __forceinline__ float load_bias(const void* bias, int dtype, int n) {
+  return dtype == FO1_F32 ? __ldg(static_cast<const float*>(bias) + n)
+                          : __bfloat162float(__ldg(static_cast<const __nv_bfloat16*>(bias) + n));
+}
+__device__ __forceinline__ float apply_act(float x, int act) {
+  if (act == FO1_EPI_GELU) return gelu_erf(x);
+  if (act == FO1_EPI_SILU) return silu(x);
+  return x;
+}
+
+// residual add + store of 32 consecutive output columns of one row
+__device__ __forceinline__ void store_row32(const GemmArgs& g, float (&v)[32], int m, int n, int n_limit) {
+  const bool full = (n + 32 <= n_limit);
+  if (g.residual != nullptr) {
+    const __nv_bfloat16* rp = g.residual + (long long)m * g.ldr + n;
+    if (full && ((g.ldr & 7) == 0)) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint4 rv = __ldg(reinterpret_cast<const uint4*>(rp) + q);
+        v[q * 8 + 0] += bf16_lo(rv.x); v[q * 8 + 1] += bf16_hi(rv.x);
+        v[q * 8 + 2] += bf16_lo(rv.y); v[q * 8 + 3] += bf16_hi(rv.y);
+        v[q * 8 + 4] += bf16_lo(rv.z); v[q * 8 + 5] += bf16_hi(rv.z);
+        v[q * 8 + 6] += bf16_lo(rv.w); v[q * 8 + 7] += bf16_hi(rv.w);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (n + j < n_limit) v[j] += __bfloat162float(rp[j]);
+    }
+  }
+  if (g.d_dtype == FO1_BF16) {
+    __nv_bfloat16* dp = static_cast<__nv_bfloat16*>(g.D) + (long long)m * g.ldd + n;
+    if (full && ((g.ldd & 7) == 0)) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        uint4 o;
+        o.x = pack_bf16(v[q * 8 + 0], v[q * 8 + 1]);
+        o.y = pack_bf16(v[q * 8 + 2], v[q * 8 + 3]);
+        o.z = pack_bf16(v[q * 8 + 4], v[q * 8 + 5]);
+        o.w = pack_bf16(v[q * 8 + 6], v[q * 8 + 7]);
+        reinterpret_cast<uint4*>(dp)[q] = o;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (n + j < n_limit) dp[j] = __float2bfloat16_rn(v[j]);
+    }
+  } else {
+    float* dp = static_cast<float*>(g.D) + (long long)m * g.ldd + n;
+    if (full && ((g.ldd & 3) == 0)) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q)
+        reinterpret_cast<float4*>(dp)[q] = make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (n + j < n_limit) dp[j] = v[j];
+    }
+  }
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kGemmThreads, 1)
+gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const GemmArgs g) {
+  using Cfg = GemmCfg<BN>;
+  constexpr int S = Cfg::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-byte alignment: required by the 128B swizzle atoms the UMMA descriptors assume
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + S * (BM * BK * 2);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * Cfg::kStageBytes);
+  uint64_t* full_bar = bars;                 // [S]
+  uint64_t* empty_bar = bars + S;            // [S]
+  uint64_t* tmem_full = bars + 2 * S;        // [2]
+  uint64_t* tmem_empty = bars + 2 * S + 2;   // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * S + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = g.tiles_m * g.tiles_n;
+  const int num_kb = (g.K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmA);
+    ptx::prefetch_tmap(&tmW);
+    for (int s = 0; s < S; ++s) {
+      ptx::mbar_init(ptx::smem_u32(full_bar + s), 1);
+      ptx::mbar_init(ptx::smem_u32(empty_bar + s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(ptx::smem_u32(tmem_full + a), 1);
+      ptx::mbar_init(ptx::smem_u32(tmem_empty + a), 4);  // one arrive per epilogue warp
+    }
+    ptx::mbar_fence_init();
+  }
+  if (warp == 1) ptx::tmem_alloc(ptx::smem_u32(tmem_ptr), Cfg::kTmemCols);
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ===================================== TMA producer =====================================
+    if (ptx::elect_one()) {
+      uint32_t it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m0 = (tile / g.tiles_n) * BM;
+        const int n0 = (tile % g.tiles_n) * BN;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const uint32_t s = it % S, ph = (it / S) & 1;
+          ptx::mbar_wait(ptx::smem_u32(empty_bar + s), ph ^ 1);
+          const uint32_t fb = ptx::smem_u32(full_bar + s);
+          ptx::mbar_expect_tx(fb, Cfg::kStageBytes);
+          ptx::tma_load_2d(ptx::smem_u32(smem_a + s * (BM * BK * 2)), &tmA, fb, kb * BK, m0);
+          ptx::tma_load_2d(ptx::smem_u32(smem_b + s * (BN * BK * 2)), &tmW, fb, kb * BK, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ====================================== MMA issuer ======================================
+    constexpr uint32_t idesc = ptx::umma_idesc_bf16(BM, BN);
+    uint32_t it = 0, tcount = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
+      const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
+      ptx::mbar_wait(ptx::smem_u32(tmem_empty + acc), aph ^ 1);  // epilogue has drained this accumulator
+      ptx::tc_fence_after();
+      const uint32_t tmem_d = tmem_base + acc * BN;
+      for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        const uint32_t s = it % S, ph = (it / S) & 1;
+        ptx::mbar_wait(ptx::smem_u32(full_bar + s), ph);
+        ptx::tc_fence_after();
+        if (ptx::elect_one()) {
+          const uint32_t a_addr = ptx::smem_u32(smem_a + s * (BM * BK * 2));
+          const uint32_t b_addr = ptx::smem_u32(smem_b + s * (BN * BK * 2));
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint64_t da = ptx::umma_desc_k_sw128(a_addr + k * UMMA_K * 2);
+            const uint64_t db = ptx::umma_desc_k_sw128(b_addr + k * UMMA_K * 2);
+            ptx::tc_mma_bf16(tmem_d, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          ptx::tc_commit(ptx::smem_u32(empty_bar + s));                    // slot free when these MMAs retire
+          if (kb == num_kb - 1) ptx::tc_commit(ptx::smem_u32(tmem_full + acc));  // accumulator complete
+        }
+        __syncwarp();
+      }
+    }
+  } else {
+    // ======================================= epilogue ========================================
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may read
+    uint32_t tcount = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
+      const int m0 = (tile / g.tiles_n) * BM;
+      const int n0 = (tile % g.tiles_n) * BN;
+      const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
+      ptx::mbar_wait(ptx::smem_u32(tmem_full + acc), aph);
+      ptx::tc_fence_after();
+      const int m = m0 + quarter * 32 + lane;
+      const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(quarter * 32) << 16);
+      if (!g.gated) {
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 32) {
+          if (n0 + c >= g.N) break;  // warp-uniform
+          uint32_t r[32];
+          ptx::tmem_ld_32x32(taddr + c, r);
+          ptx::tmem_ld_wait();
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+          if (g.bias != nullptr) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (n0 + c + j < g.N) v[j] += load_bias(g.bias, g.bias_dtype, n0 + c + j);
+          }
+          if (g.act != FO1_EPI_NONE) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], g.act);
+          }
+          if (m < g.M) store_row32(g, v, m, n0 + c, g.N);
+        }
+      } else {
+        // W rows interleave [32 gate | 32 up] blocks: out[:, (n0+c)/2 + j] = act(gate_j) * up_j
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 64) {
+          if (n0 + c >= g.N) break;
+          uint32_t rg[32], ru[32];
+          ptx::tmem_ld_32x32(taddr + c, rg);
+          ptx::tmem_ld_32x32(taddr + c + 32, ru);
+          ptx::tmem_ld_wait();
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float gt = __uint_as_float(rg[j]), up = __uint_as_float(ru[j]);
+            if (g.bias != nullptr && n0 + c + 32 + j < g.N) {
+              gt += load_bias(g.bias, g.bias_dtype, n0 + c + j);
+              up += load_bias(g.bias, g.bias_dtype, n0 + c + 32 + j);
+            }
+            v[j] = apply_act(gt, g.act) * up;
+          }
+          if (m < g.M) store_row32(g, v, m, (n0 + c) >> 1, g.N >> 1);
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(tmem_empty + acc));
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc(tmem_base, Cfg::kTmemCols);
+}
+
+// ---------------------------------------------------------------------------------------------- host
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                        const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                        CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_tmapEncodeTiled get_encode_fn() {
+  static PFN_tmapEncodeTiled fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_tmapEncodeTiled>(p);
+  }
+  return fn;
+}
+
+// 2-D bf16 tensor map over a row-major [outer][inner] matrix with row pitch ld (elements), 128B swizzle.
+int make_tmap_2d_bf16(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_t outer, uint64_t ld,
+                      uint32_t box_inner, uint32_t box_outer) {
+  PFN_tmapEncodeTiled fn = get_encode_fn();
+  if (fn == nullptr) {
+    set_error("cuTensorMapEncodeTiled is not available from the driver");
+    return FO1_ERR_CUDA;
+  }
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d): ptr=%p inner=%llu outer=%llu ld=%llu box=%ux%u", (int)r, ptr,
+              (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)ld, box_inner, box_outer);
+    return FO1_ERR_CUDA;
+  }
+  return FO1_OK;
+}
+
+int device_sm_count() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+      sms = 148;
+  }
+  return sms;
+}
+
+template <int BN>
+static int launch_gemm(const fo1_gemm_desc* d, cudaStream_t stream) {
+  using Cfg = GemmCfg<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    FO1_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    attr_set = true;
+  }
+  CUtensorMap tmA, tmW;
+  FO1_TRY(make_tmap_2d_bf16(&tmA, d->A, (uint64_t)d->K, (uint64_t)d->M, (uint64_t)d->lda, BK, BM));
+  FO1_TRY(make_tmap_2d_bf16(&tmW, d->W, (uint64_t)d->K, (uint64_t)d->N, (uint64_t)d->ldw, BK, BN));
+  GemmArgs g;
+  g.M = d->M; g.N = d->N; g.K = d->K;
+  g.D = d->D; g.ldd = d->ldd; g.d_dtype = d->d_dtype;
+  g.bias = d->bias; g.bias_dtype = d->bias_dtype;
+  g.act = d->act;
+  g.residual = static_cast<const __nv_bfloat16*>(d->residual); g.ldr = d->ldr;
+  g.gated = d->gated;
+  g.tiles_m = ceil_div(d->M, BM);
+  g.tiles_n = ceil_div(d->N, BN);
+  const int tiles = g.tiles_m * g.tiles_n;
+  const int grid = tiles < device_sm_count() ? tiles : device_sm_count();
+  gemm_bf16_tcgen05_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(tmA, tmW, g);
+  FO1_LAUNCH_CHECK();
+  return FO1_OK;
+}
+
+int gemm_bf16(const fo1_gemm_desc* d, cudaStream_t stream) {
+  FO1_CHECK_ARG(d != nullptr, "fo1_gemm_bf16: null descriptor");
+  FO1_CHECK_ARG(d->M >= 0 && d->N > 0 && d->K > 0, "fo1_gemm_bf16: bad shape M=%d N=%d K=%d", d->M, d->N, d->K);
+  if (d->M == 0) return FO1_OK;
+  FO1_CHECK_ARG(d->A && d->W && d->D, "fo1_gemm_bf16: null operand");
+  FO1_CHECK_ARG((reinterpret_cast<uintptr_t>(d->A) & 15) == 0 && (reinterpret_cast<uintptr_t>(d->W) & 15) == 0,
+                "fo1_gemm_bf16: A and W must be 16-byte aligned");
+  FO1_CHECK_ARG(d->lda >= d->K && d->ldw >= d->K && (d->lda % 8) == 0 && (d->ldw % 8) == 0,
+                "fo1_gemm_bf16: lda=%lld / ldw=%lld must be >= K and multiples of 8 elements (TMA 16-byte pitch)",
+                (long long)d->lda, (long long)d->ldw);
+  FO1_CHECK_ARG(d->d_dtype == FO1_BF16 || d->d_dtype == FO1_F32, "fo1_gemm_bf16: d_dtype %d unsupported", d->d_dtype);
+  FO1_CHECK_ARG(d->bias == nullptr || d->bias_dtype == FO1_BF16 || d->bias_dtype == FO1_F32, "fo1_gemm_bf16: bias_dtype %d unsupported", d->bias_dtype);
+  FO1_CHECK_ARG(d->act >= FO1_EPI_NONE && d->act <= FO1_EPI_SILU, "fo1_gemm_bf16: act %d unsupported", d->act);
+  const int n_out = d->gated ? d->N / 2 : d->N;
+  FO1_CHECK_ARG(!d->gated || d->N % 64 == 0, "fo1_gemm_bf16: gated N=%d must be a multiple of 64", d->N);
+  FO1_CHECK_ARG(d->ldd >= n_out, "fo1_gemm_bf16: ldd=%lld < %d", (long long)d->ldd, n_out);
+  FO1_CHECK_ARG(d->residual == nullptr || d->ldr >= n_out, "fo1_gemm_bf16: ldr too small");
+  // tile-width choice: widest tile that still yields >= 1 wave of CTAs, else narrower for occupancy
+  const int sms = device_sm_count();
+  const long long tm = ceil_div(d->M, BM);
+  if (d->N >= 256 && tm * ceil_div(d->N, 256) >= sms) return launch_gemm<256>(d, stream);
+  if (d->N >= 128 && tm * ceil_div(d->N, 128) >= sms / 2) return launch_gemm<128>(d, stream);
+  return launch_gemm<64>(d, stream);
+}
+
+}  // namespace fo1
+
+extern "C" int fo1_gemm_bf16(const fo1_gemm_desc* d, void* stream) {
+  return fo1::gemm_bf16(d, static_cast<cudaStream_t>(stream));
+}

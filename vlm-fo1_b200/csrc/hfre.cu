@@ -1,0 +1,405 @@
+// hfre.cu -- Hybrid Fine-grained Region Encoder on sm_100a: separable-window region pooling.
+//
+// What the reference does (hybrid_finegrained_region_encoder.py:319-363, 230-273): up-sample aux
+// levels 1..3 to level 0's grid (F.interpolate bilinear, align_corners=False), concatenate to a
+// [1,3840,H/4,W/4] fp32 map (771 MB at 896^2), torchvision roi_align(7x7, sampling_ratio=-1,
+// aligned=False), mean over the 49 bins; same for the primary tower's maps; concat; add a sinusoidal
+// box embedding (:436-467, :55-103).
+//
+// What this file does instead: because every bin of a box holds the same number of samples,
+// mean_{7x7}(roi_align(U))[c] = a^T U[c] b with 1-D weight vectors that depend only on the box, and
+// because the up-sampling is linear and separable too, U[c] = Mh L[c] Mw^T, the whole thing is
+//        out[c] = (Mh^T a)^T L[c] (Mw^T b)
+// over the NATIVE-resolution bf16 level L (channels-last).  Kernel 1 builds the two weight vectors
+// per (box, level, axis) with torchvision's exact per-sample rules; kernel 3 is a pure memory-bound
+// weighted window sum: coalesced 16-byte channel-vector loads, fp32 accumulation, shared-memory
+// cross-warp reduction.  No tensor cores: 2 FLOP per loaded bf16 element.
+#include "common.cuh"
+
+namespace fo1 {
+
+constexpr int kMaxBatch = 8;           // images per launch (kernel-parameter budget: < 4 KB)
+constexpr int kGatherThreads = 256;
+constexpr int kChunk = 256;            // channels per gather block: 32 lanes x 8 bf16 (16 B) each
+
+struct LevelDev {
+  const __nv_bfloat16* data;
+  int H, W, C, upH, upW;
+  float scale;
+  int box_set;
+  int out_off;
+  int wofs;      // float offset of this level's weight records inside the image's workspace slice
+  int wstride;   // floats per box record: 4 header words + H + W, rounded up to 4
+};
+struct ImageDev {
+  LevelDev lv[FO1_HFRE_MAX_LEVELS];
+  const float* boxes[2];
+  float* out;
+  __nv_bfloat16* out_bf16;
+  long long ws_ofs;  // float offset of this image's workspace slice
+  float pos_w, pos_h;
+  int pos_box_set;
+  int n_levels;
+  int n_boxes;
+  int n_chunks;  // sum over levels of ceil(C / kChunk)
+};
+struct BatchDev {
+  ImageDev img[kMaxBatch];
+  int n_images;
+  int out_dim;
+  int roi;
+  int pos;
+};
+
+// ------------------------------------------------------------------------------------------------
+// Kernel 1: per (image, box, level, axis) weight vector on the native grid.
+// Sample coordinates and tap rules follow torchvision roi_align_forward_kernel_impl /
+// bilinear_interpolate (aligned=False, sampling_ratio=-1): roi extent max(end-start,1); adaptive grid
+// g = ceil(extent/P); sample y = start + p*bin + (i+.5)*bin/g; a sample with y < -1 or y > size
+// contributes nothing; y <= 0 -> 0; y_low >= size-1 -> both taps on size-1.  Up-sampling taps follow
+// ATen upsample_bilinear2d (align_corners=False): src = (in/out)*(dst+.5)-.5 clamped at 0.
+// Arithmetic is written with explicit round-to-nearest ops so ptxas cannot contract it into FMAs and
+// the discrete decisions (floor/ceil/skip) match the CPU kernels bit for bit.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float roi_sample_coord(float start, float bin, int p, int i, int g) {
+  float t0 = __fadd_rn(start, __fmul_rn((float)p, bin));
+  float t1 = __fdiv_rn(__fmul_rn(__fadd_rn((float)i, 0.5f), bin), (float)g);
+  return __fadd_rn(t0, t1);
+}
+
+__global__ void __launch_bounds__(128) hfre_axis_weights_kernel(const BatchDev B, float* __restrict__ ws) {
+  const ImageDev& im = B.img[blockIdx.z];
+  const int box = blockIdx.x;
+  const int lvl = blockIdx.y >> 1;
+  const int axis = blockIdx.y & 1;  // 0: rows (y), 1: cols (x)
+  if (box >= im.n_boxes || lvl >= im.n_levels) return;
+  const LevelDev& L = im.lv[lvl];
+  const int n_nat = axis ? L.W : L.H;
+  const int n_up = axis ? L.upW : L.upH;
+  const float* bx = im.boxes[L.box_set] + 4 * box;
+  const float lo = axis ? bx[0] : bx[1];
+  const float hi = axis ? bx[2] : bx[3];
+  const int P = B.roi;
+
+  const float start = __fmul_rn(lo, L.scale);
+  const float end = __fmul_rn(hi, L.scale);
+  const float extent = fmaxf(__fsub_rn(end, start), 1.0f);
+  const float bin = __fdiv_rn(extent, (float)P);
+  const int g = (int)ceilf(__fdiv_rn(extent, (float)P));
+  const int ns = P * g;
+
+  extern __shared__ float sm[];
+  float* A = sm;            // [n_up] weights on the up-sampled axis
+  // support on the up-sampled axis (samples are monotone in their index)
+  const float y_first = roi_sample_coord(start, bin, 0, 0, g);
+  const float y_last = roi_sample_coord(start, bin, P - 1, g - 1, g);
+  int i_min = (int)floorf(fmaxf(y_first, 0.0f));
+  int i_max = (int)floorf(fmaxf(y_last, 0.0f)) + 1;
+  i_min = min(max(i_min, 0), n_up - 1);
+  i_max = min(max(i_max, 0), n_up - 1);
+
+  for (int r = i_min + threadIdx.x; r <= i_max; r += blockDim.x) {
+    float acc = 0.0f;
+    for (int p = 0; p < P; ++p) {
+      for (int i = 0; i < g; ++i) {
+        float y = roi_sample_coord(start, bin, p, i, g);
+        const bool ok = !(y < -1.0f || y > (float)n_up);
+        if (y <= 0.0f) y = 0.0f;
+        int yl = (int)y, yh;
+        if (yl >= n_up - 1) {
+          yh = yl = n_up - 1;
+          y = (float)yl;
+        } else {
+          yh = yl + 1;
+        }
+        const float ly = __fsub_rn(y, (float)yl);
+        const float hy = __fsub_rn(1.0f, ly);
+        if (ok) {
+          if (yl == r) acc = __fadd_rn(acc, hy);
+          if (yh == r) acc = __fadd_rn(acc, ly);
+        }
+      }
+    }
+    A[r] = acc;
+  }
+  __syncthreads();
+
+  float* rec = ws + im.ws_ofs + L.wofs + (long long)box * L.wstride;
+  int* hdr = reinterpret_cast<int*>(rec);
+  float* wout = rec + 4 + (axis ? L.H : 0);
+  const float norm = (float)ns;  // P * g samples per axis: mean over bins and over the bin's grid
+
+  if (n_up == n_nat) {
+    for (int r = i_min + threadIdx.x; r <= i_max; r += blockDim.x) wout[r - i_min] = __fdiv_rn(A[r], norm);
+    if (threadIdx.x == 0) {
+      hdr[axis * 2 + 0] = i_min;
+      hdr[axis * 2 + 1] = i_max - i_min + 1;
+    }
+    return;
+  }
+  // compose with the bilinear up-sampling: native tap weights of every touched up-sampled row
+  const float us = __fdiv_rn((float)n_nat, (float)n_up);
+  auto src_of = [&](int i) {
+    float s = __fsub_rn(__fmul_rn(us, __fadd_rn((float)i, 0.5f)), 0.5f);
+    return s < 0.0f ? 0.0f : s;
+  };
+  const int r_min = (int)src_of(i_min);
+  int r_max = (int)src_of(i_max);
+  r_max = r_max + (r_max < n_nat - 1 ? 1 : 0);
+  for (int r = r_min + threadIdx.x; r <= r_max; r += blockDim.x) {
+    float acc = 0.0f;
+    for (int i = i_min; i <= i_max; ++i) {
+      const float s = src_of(i);
+      const int i0 = (int)s;
+      const int i1 = i0 + (i0 < n_nat - 1 ? 1 : 0);
+      const float l1 = __fsub_rn(s, (float)i0);
+      const float l0 = __fsub_rn(1.0f, l1);
+      if (i0 == r) acc = __fadd_rn(acc, __fmul_rn(l0, A[i]));
+      if (i1 == r) acc = __fadd_rn(acc, __fmul_rn(l1, A[i]));
+    }
+    wout[r - r_min] = __fdiv_rn(acc, norm);
+  }
+  if (threadIdx.x == 0) {
+    hdr[axis * 2 + 0] = r_min;
+    hdr[axis * 2 + 1] = r_max - r_min + 1;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Kernel 2: out[n][d] = sinusoidal box embedding (or 0): order (cy, cx, w, h), D/4 channels each,
+// interleaved sin/cos, dim_t = 10000^(2*floor(i/2)/(D/4))  (gen_sineembed_for_position :55-103).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) hfre_pos_init_kernel(const BatchDev B) {
+  const ImageDev& im = B.img[blockIdx.z];
+  const int box = blockIdx.y;
+  if (box >= im.n_boxes) return;
+  const int D = B.out_dim;
+  const int q = D / 4;
+  float v[4] = {0.f, 0.f, 0.f, 0.f};
+  if (B.pos) {
+    const float* bx = im.boxes[im.pos_box_set] + 4 * box;
+    const float x1 = __fdiv_rn(bx[0], im.pos_w), y1 = __fdiv_rn(bx[1], im.pos_h);
+    const float x2 = __fdiv_rn(bx[2], im.pos_w), y2 = __fdiv_rn(bx[3], im.pos_h);
+    const float w = __fsub_rn(x2, x1), h = __fsub_rn(y2, y1);
+    v[0] = __fadd_rn(y1, __fdiv_rn(h, 2.0f));  // cy
+    v[1] = __fadd_rn(x1, __fdiv_rn(w, 2.0f));  // cx
+    v[2] = w;
+    v[3] = h;
+  }
+  float* out = im.out + (long long)box * D;
+  for (int d = blockIdx.x * blockDim.x + threadIdx.x; d < D; d += gridDim.x * blockDim.x) {
+    float val = 0.0f;
+    if (B.pos && d < 4 * q) {
+      const int part = d / q, i = d - part * q;
+      const float expo = __fdiv_rn((float)(2 * (i / 2)), (float)q);
+      const float dim_t = powf(10000.0f, expo);
+      const float ph = __fdiv_rn(__fmul_rn(v[part], 6.283185307179586f), dim_t);
+      val = (i & 1) ? cosf(ph) : sinf(ph);
+    }
+    out[d] = val;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Kernel 3 (algo 1, per-box gather): one block per (image, box, level, 256-channel chunk).
+// 8 warps stride over the window's rows; each lane owns 8 consecutive channels (one 16-byte load per
+// cell, a warp reads 512 contiguous bytes per cell); fp32 accumulate; cross-warp reduce in smem.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kGatherThreads) hfre_gather_kernel(const BatchDev B, const float* __restrict__ ws) {
+  const ImageDev& im = B.img[blockIdx.z];
+  const int box = blockIdx.y;
+  if (box >= im.n_boxes || (int)blockIdx.x >= im.n_chunks) return;
+  // (level, chunk) of this block
+  int lvl = 0, chunk = blockIdx.x;
+  for (; lvl < im.n_levels; ++lvl) {
+    const int nc = (im.lv[lvl].C + kChunk - 1) / kChunk;
+    if (chunk < nc) break;
+    chunk -= nc;
+  }
+  const LevelDev& L = im.lv[lvl];
+  const float* rec = ws + im.ws_ofs + L.wofs + (long long)box * L.wstride;
+  const int* hdr = reinterpret_cast<const int*>(rec);
+  const int r0 = hdr[0], rl = hdr[1], c0 = hdr[2], cl = hdr[3];
+
+  extern __shared__ float sm[];
+  float* red = sm;                                  // [8][kChunk] (16-byte aligned for float4)
+  float* wa = sm + (kGatherThreads / 32) * kChunk;  // [rl]
+  float* wb = wa + L.H;                             // [cl]
+  for (int i = threadIdx.x; i < rl; i += blockDim.x) wa[i] = rec[4 + i];
+  for (int i = threadIdx.x; i < cl; i += blockDim.x) wb[i] = rec[4 + L.H + i];
+  __syncthreads();
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cbase = chunk * kChunk + lane * 8;
+  const bool active = cbase < L.C;
+  float acc[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) acc[j] = 0.0f;
+
+  if (active) {
+    const long long rowpitch = (long long)L.W * L.C;
+    for (int r = warp; r < rl; r += kGatherThreads / 32) {
+      const float ar = wa[r];
+      const __nv_bfloat16* p = L.data + (long long)(r0 + r) * rowpitch + (long long)c0 * L.C + cbase;
+      int k = 0;
+      for (; k + 4 <= cl; k += 4) {
+        uint4 v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = ldg_nc_v4(p + (long long)(k + u) * L.C);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const float w = ar * wb[k + u];
+          acc[0] = fmaf(w, bf16_lo(v[u].x), acc[0]); acc[1] = fmaf(w, bf16_hi(v[u].x), acc[1]);
+          acc[2] = fmaf(w, bf16_lo(v[u].y), acc[2]); acc[3] = fmaf(w, bf16_hi(v[u].y), acc[3]);
+          acc[4] = fmaf(w, bf16_lo(v[u].z), acc[4]); acc[5] = fmaf(w, bf16_hi(v[u].z), acc[5]);
+          acc[6] = fmaf(w, bf16_lo(v[u].w), acc[6]); acc[7] = fmaf(w, bf16_hi(v[u].w), acc[7]);
+        }
+      }
+      for (; k < cl; ++k) {
+        const uint4 v = ldg_nc_v4(p + (long long)k * L.C);
+        const float w = ar * wb[k];
+        acc[0] = fmaf(w, bf16_lo(v.x), acc[0]); acc[1] = fmaf(w, bf16_hi(v.x), acc[1]);
+        acc[2] = fmaf(w, bf16_lo(v.y), acc[2]); acc[3] = fmaf(w, bf16_hi(v.y), acc[3]);
+        acc[4] = fmaf(w, bf16_lo(v.z), acc[4]); acc[5] = fmaf(w, bf16_hi(v.z), acc[5]);
+        acc[6] = fmaf(w, bf16_lo(v.w), acc[6]); acc[7] = fmaf(w, bf16_hi(v.w), acc[7]);
+      }
+    }
+  }
+  float4* rv = reinterpret_cast<float4*>(red + warp * kChunk + lane * 8);
+  rv[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+  rv[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+  __syncthreads();
+  const int c = chunk * kChunk + threadIdx.x;
+  if (c < L.C) {
+    float s = 0.0f;
+#pragma unroll
+    for (int w = 0; w < kGatherThreads / 32; ++w) s += red[w * kChunk + threadIdx.x];
+    float* o = im.out + (long long)box * B.out_dim + L.out_off + c;
+    *o += s;  // exclusive owner of this output element (kernel 2 initialised it)
+  }
+}
+
+// Kernel 4: optional bf16 copy of the region features (the reference casts to the tower dtype
+// before mm_projector_aux, omchat_qwen2_5_vl.py:106).
+__global__ void __launch_bounds__(256) hfre_to_bf16_kernel(const BatchDev B) {
+  const ImageDev& im = B.img[blockIdx.z];
+  if (im.out_bf16 == nullptr) return;
+  const long long n = (long long)im.n_boxes * B.out_dim;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    im.out_bf16[i] = __float2bfloat16_rn(im.out[i]);
+}
+
+// ---------------------------------------------------------------------------------------------- host
+static int level_wstride(const fo1_hfre_level& l) { return (4 + l.H + l.W + 3) & ~3; }
+
+static size_t image_ws_floats(const fo1_hfre_image& im) {
+  size_t f = 0;
+  for (int l = 0; l < im.n_levels; ++l) f += (size_t)im.n_boxes * level_wstride(im.levels[l]);
+  return f;
+}
+
+}  // namespace fo1
+
+using namespace fo1;
+
+extern "C" size_t fo1_hfre_workspace_bytes(const fo1_hfre_image* images, int32_t n_images, const fo1_hfre_params*) {
+  size_t f = 0;
+  for (int i = 0; i < n_images; ++i) f += image_ws_floats(images[i]);
+  return f * sizeof(float) + 256;
+}
+
+extern "C" int fo1_hfre_forward(const fo1_hfre_image* images, int32_t n_images, const fo1_hfre_params* p,
+                                void* workspace, size_t workspace_bytes, void* stream_) {
+  FO1_CHECK_ARG(images && p && n_images >= 0, "fo1_hfre_forward: null argument");
+  if (n_images == 0) return FO1_OK;
+  FO1_CHECK_ARG(p->roi_size >= 1 && p->roi_size <= 32, "fo1_hfre_forward: roi_size %d unsupported", p->roi_size);
+  FO1_CHECK_ARG(p->out_dim > 0 && p->out_dim % 4 == 0, "fo1_hfre_forward: out_dim %d must be a positive multiple of 4", p->out_dim);
+  FO1_CHECK_ARG(p->algo == 0 || p->algo == 1, "fo1_hfre_forward: algo %d not available", p->algo);
+  const size_t need = fo1_hfre_workspace_bytes(images, n_images, p);
+  if (workspace == nullptr || workspace_bytes < need) {
+    set_error("fo1_hfre_forward: workspace %zu B < required %zu B", workspace_bytes, need);
+    return FO1_ERR_WORKSPACE;
+  }
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  float* ws = static_cast<float*>(workspace);
+
+  size_t ws_ofs = 0;
+  for (int base = 0; base < n_images; base += kMaxBatch) {
+    BatchDev B;
+    memset(&B, 0, sizeof(B));
+    B.n_images = (n_images - base < kMaxBatch) ? n_images - base : kMaxBatch;
+    B.out_dim = p->out_dim;
+    B.roi = p->roi_size;
+    B.pos = p->apply_pos_embed ? 1 : 0;
+    int max_boxes = 0, max_levels = 0, max_chunks = 0, max_up = 0, max_hw = 0;
+    for (int i = 0; i < B.n_images; ++i) {
+      const fo1_hfre_image& src = images[base + i];
+      ImageDev& d = B.img[i];
+      FO1_CHECK_ARG(src.n_levels >= 1 && src.n_levels <= FO1_HFRE_MAX_LEVELS, "image %d: n_levels %d out of range", base + i, src.n_levels);
+      FO1_CHECK_ARG(src.n_boxes >= 0, "image %d: negative n_boxes", base + i);
+      FO1_CHECK_ARG(src.n_boxes == 0 || (src.boxes_aux && src.boxes_vt && src.out), "image %d: null boxes/out", base + i);
+      d.n_levels = src.n_levels;
+      d.n_boxes = src.n_boxes;
+      d.boxes[0] = src.boxes_aux;
+      d.boxes[1] = src.boxes_vt;
+      d.out = src.out;
+      d.out_bf16 = static_cast<__nv_bfloat16*>(src.out_bf16);
+      d.pos_w = src.pos_img_w;
+      d.pos_h = src.pos_img_h;
+      d.pos_box_set = src.pos_box_set ? 1 : 0;
+      d.ws_ofs = (long long)ws_ofs;
+      int wofs = 0, chunks = 0;
+      for (int l = 0; l < src.n_levels; ++l) {
+        const fo1_hfre_level& sl = src.levels[l];
+        FO1_CHECK_ARG(sl.data != nullptr && sl.H > 0 && sl.W > 0 && sl.C > 0, "image %d level %d: bad shape", base + i, l);
+        FO1_CHECK_ARG(sl.C % 8 == 0, "image %d level %d: C=%d must be a multiple of 8", base + i, l, sl.C);
+        FO1_CHECK_ARG((reinterpret_cast<uintptr_t>(sl.data) & 15) == 0, "image %d level %d: data not 16-byte aligned", base + i, l);
+        FO1_CHECK_ARG(sl.up_H >= sl.H && sl.up_W >= sl.W, "image %d level %d: up-sampled grid smaller than native", base + i, l);
+        FO1_CHECK_ARG(sl.out_offset >= 0 && sl.out_offset + sl.C <= p->out_dim, "image %d level %d: channels [%d,%d) exceed out_dim %d", base + i, l, sl.out_offset, sl.out_offset + sl.C, p->out_dim);
+        LevelDev& dl = d.lv[l];
+        dl.data = static_cast<const __nv_bfloat16*>(sl.data);
+        dl.H = sl.H; dl.W = sl.W; dl.C = sl.C; dl.upH = sl.up_H; dl.upW = sl.up_W;
+        dl.scale = sl.spatial_scale;
+        dl.box_set = sl.box_set ? 1 : 0;
+        dl.out_off = sl.out_offset;
+        dl.wofs = wofs;
+        dl.wstride = level_wstride(sl);
+        wofs += src.n_boxes * dl.wstride;
+        chunks += ceil_div(sl.C, kChunk);
+        max_up = max_up > sl.up_H ? max_up : sl.up_H;
+        max_up = max_up > sl.up_W ? max_up : sl.up_W;
+        max_hw = max_hw > sl.H + sl.W ? max_hw : sl.H + sl.W;
+      }
+      d.n_chunks = chunks;
+      ws_ofs += (size_t)wofs;
+      max_boxes = max_boxes > src.n_boxes ? max_boxes : src.n_boxes;
+      max_levels = max_levels > src.n_levels ? max_levels : src.n_levels;
+      max_chunks = max_chunks > chunks ? max_chunks : chunks;
+    }
+    if (max_boxes == 0) continue;
+    {
+      dim3 grid(max_boxes, max_levels * 2, B.n_images);
+      hfre_axis_weights_kernel<<<grid, 128, (size_t)max_up * sizeof(float), stream>>>(B, ws);
+      FO1_LAUNCH_CHECK();
+    }
+    {
+      dim3 grid(ceil_div(p->out_dim, 256 * 4), max_boxes, B.n_images);
+      hfre_pos_init_kernel<<<grid, 256, 0, stream>>>(B);
+      FO1_LAUNCH_CHECK();
+    }
+    {
+      dim3 grid(max_chunks, max_boxes, B.n_images);
+      const size_t smem = ((size_t)max_hw + (kGatherThreads / 32) * kChunk) * sizeof(float);
+      hfre_gather_kernel<<<grid, kGatherThreads, smem, stream>>>(B, ws);
+      FO1_LAUNCH_CHECK();
+    }
+    bool any_bf16 = false;
+    for (int i = 0; i < B.n_images; ++i) any_bf16 |= (B.img[i].out_bf16 != nullptr);
+    if (any_bf16) {
+      dim3 grid(ceil_div(max_boxes * p->out_dim, 256 * 8), 1, B.n_images);
+      hfre_to_bf16_kernel<<<grid, 256, 0, stream>>>(B);
+      FO1_LAUNCH_CHECK();
+    }
+  }
+  return FO1_OK;
+}

@@ -1,0 +1,68 @@
+"""Stateless operator wrappers over the C ABI (device pointers in, device pointers out).
+torch tensors are only the memory handles; every computation happens inside libfo1.so."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import GemmDesc, check, lib
+
+_ACT = {None: _lib.EPI_NONE, "none": _lib.EPI_NONE, "gelu": _lib.EPI_GELU, "silu": _lib.EPI_SILU}
+_DT = {torch.bfloat16: _lib.FO1_BF16, torch.float32: _lib.FO1_F32}
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _require_cuda(*ts) -> None:
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise _lib.Fo1Error("libfo1 operators take CUDA tensors only (no CPU fallback)")
+
+
+def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, act: Optional[str] = None,
+         residual: Optional[torch.Tensor] = None, out_dtype: torch.dtype = torch.bfloat16, gated: bool = False,
+         out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[M, N] = act(a[M, K] @ w[N, K]^T + bias) + residual   (nn.Linear semantics).
+    ``gated``: w/bias rows interleave [32 gate | 32 up] blocks -> out[M, N/2] = act(gate) * up."""
+    _require_cuda(a, w, bias, residual)
+    assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and a.dim() == 2 and w.dim() == 2
+    assert a.stride(1) == 1 and w.stride(1) == 1 and a.shape[1] == w.shape[1]
+    M, K = a.shape
+    N = w.shape[0]
+    n_out = N // 2 if gated else N
+    if out is None:
+        out = torch.empty((M, n_out), dtype=out_dtype, device=a.device)
+    assert out.shape == (M, n_out) and out.stride(1) == 1
+    d = GemmDesc()
+    d.M, d.N, d.K = M, N, K
+    d.A, d.lda = a.data_ptr(), a.stride(0)
+    d.W, d.ldw = w.data_ptr(), w.stride(0)
+    d.D, d.ldd, d.d_dtype = out.data_ptr(), out.stride(0), _DT[out.dtype]
+    if bias is not None:
+        assert bias.shape == (N,) and bias.is_contiguous()
+        d.bias, d.bias_dtype = bias.data_ptr(), _DT[bias.dtype]
+    d.act = _ACT[act]
+    if residual is not None:
+        assert residual.dtype == torch.bfloat16 and residual.shape == (M, n_out) and residual.stride(1) == 1
+        d.residual, d.ldr = residual.data_ptr(), residual.stride(0)
+    d.gated = 1 if gated else 0
+    check(lib().fo1_gemm_bf16(C.byref(d), C.c_void_p(_stream())), "fo1_gemm_bf16")
+    return out
+
+
+def interleave_gate_up(gate: torch.Tensor, up: torch.Tensor, block: int = 32) -> torch.Tensor:
+    """Host-side weight prep for the gated epilogue: rows (or bias entries) of gate/up interleaved in
+    blocks of ``block``; the row count is zero-padded to a multiple of ``block`` first."""
+    n = gate.shape[0]
+    pad = (-n) % block
+    if pad:
+        z = torch.zeros((pad,) + tuple(gate.shape[1:]), dtype=gate.dtype, device=gate.device)
+        gate = torch.cat([gate, z]); up = torch.cat([up, z])
+    g = gate.reshape(-1, block, *gate.shape[1:])
+    u = up.reshape(-1, block, *up.shape[1:])
+    return torch.stack([g, u], dim=1).reshape(-1, *gate.shape[1:]).contiguous()

@@ -79,7 +79,7 @@ def test_hfre_empty_and_errors():
     empty = torch.zeros(0, 4, device="cuda")
     out = H.hfre_forward([aux], [pyr], [empty], [empty], H.HfreConfig(region_dim=64), [(2, 2)])[0]
     assert out.shape == (0, 64)
-    with pytest.raises(L.Fo1Error):   # region_dim smaller than the channels provided -> rejected on the host side
+    with pytest.raises(ValueError):   # region_dim smaller than the channels provided -> rejected on the host side
         H.hfre_forward([aux], [pyr], [empty], [empty], H.HfreConfig(region_dim=16), [(2, 2)])
     bad = [torch.zeros(8, 8, 12, dtype=torch.bfloat16, device="cuda")] + aux[1:]  # C % 8 != 0
     one = torch.tensor([[0.0, 0.0, 4.0, 4.0]], device="cuda")

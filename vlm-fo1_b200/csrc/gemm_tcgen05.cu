@@ -15,7 +15,7 @@
 // padding beyond 16-byte row pitches.
 #include <cuda.h>
 
-#include "common.cuh"
+#include "kernels.cuh"
 #include "ptx.cuh"
 
 namespace fo1 {
@@ -24,7 +24,6 @@ constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle atom row
 constexpr int UMMA_K = 16;
 constexpr int kGemmThreads = 192;
-constexpr int kEpiWarp0 = 2;
 
 struct GemmArgs {
   int M, N, K;
@@ -366,3 +365,16 @@ int gemm_bf16(const fo1_gemm_desc* d, cudaStream_t stream) {
 extern "C" int fo1_gemm_bf16(const fo1_gemm_desc* d, void* stream) {
   return fo1::gemm_bf16(d, static_cast<cudaStream_t>(stream));
 }
+
+namespace fo1 {
+int linear(const bf16* A, long long lda, const bf16* W, long long ldw, void* D, long long ldd, int d_dtype, int M, int N,
+           int K, const void* bias, int bias_dtype, int act, const bf16* residual, long long ldr, int gated,
+           cudaStream_t stream) {
+  fo1_gemm_desc d;
+  memset(&d, 0, sizeof(d));
+  d.M = M; d.N = N; d.K = K;
+  d.A = A; d.lda = lda; d.W = W; d.ldw = ldw; d.D = D; d.ldd = ldd; d.d_dtype = d_dtype;
+  d.bias = bias; d.bias_dtype = bias_dtype; d.act = act; d.residual = residual; d.ldr = ldr; d.gated = gated;
+  return gemm_bf16(&d, stream);
+}
+}  // namespace fo1

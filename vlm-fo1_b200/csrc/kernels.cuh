@@ -1,0 +1,57 @@
+// kernels.cuh -- internal launcher declarations shared by the engine (host side of every .cu file).
+#pragma once
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace fo1 {
+
+typedef __nv_bfloat16 bf16;
+
+// ---- gemm_tcgen05.cu ----
+int gemm_bf16(const fo1_gemm_desc* d, cudaStream_t stream);
+int device_sm_count();
+// convenience: D = act(A.W^T + bias) + residual, all row-major contiguous unless ld given
+int linear(const bf16* A, long long lda, const bf16* W, long long ldw, void* D, long long ldd, int d_dtype, int M, int N,
+           int K, const void* bias, int bias_dtype, int act, const bf16* residual, long long ldr, int gated,
+           cudaStream_t stream);
+
+// ---- norm.cu ----
+// Qwen2RMSNorm (modeling_qwen2_5_vl.py:126-140): y = w * bf16(x * rsqrt(mean(x^2) + eps))
+int rmsnorm(const bf16* x, long long ldx, const bf16* w, bf16* y, long long ldy, int rows, int cols, float eps, cudaStream_t s);
+// nn.LayerNorm over the last dim (fp32 statistics), optional gamma/beta
+int layernorm(const bf16* x, long long ldx, const bf16* gamma, const bf16* beta, bf16* y, long long ldy, int rows, int cols,
+              float eps, cudaStream_t s);
+
+// ---- rope.cu ----
+// ViT 2-D RoPE (modeling_qwen2_5_vl.py:162-169, 436-463): table[t][j] = pos_{h|w}[t] * inv_freq[j mod half]
+int vit_rope_table(const int* pos_hw /*[T][2]*/, float* cos_sin /*[T][rot_dim] cos then [T][rot_dim] sin*/, int T, int head_dim,
+                   float theta, cudaStream_t s);
+// rotate q and k inside a packed qkv buffer [T][3*heads*head_dim] (non-interleaved halves)
+int vit_rope_apply(bf16* qkv, const float* cos_sin, int T, int heads, int head_dim, cudaStream_t s);
+// LLM M-RoPE (modeling_qwen2_5_vl.py:603-624, 643-685): q [T][q_heads*hd], k [T][kv_heads*hd] in a packed row of pitch ld
+int mrope_apply(bf16* q, bf16* k, long long ld, const int* pos3 /*[3][T]*/, int T, int q_heads, int kv_heads, int head_dim,
+                int sec_t, int sec_h, int sec_w, float theta, cudaStream_t s);
+
+// ---- attention.cu ----
+// varlen flash attention over packed rows; q/k/v may live in one packed buffer (pitches in elements)
+struct AttnArgs {
+  const bf16* q; const bf16* k; const bf16* v; bf16* o;
+  long long ldq, ldk, ldv, ldo;     // row pitches (elements)
+  const int* cu_seqlens;            // [n_seqs + 1] token offsets (device); q and kv share them
+  int n_seqs;
+  int max_seqlen;                   // longest segment (host knowledge, sizes the grid)
+  int q_heads, kv_heads, head_dim;
+  float scale;
+  int causal;
+};
+int attention_varlen(const AttnArgs& a, cudaStream_t s);
+
+// ---- misc.cu ----
+int cast_gather_rows_f32_bf16(const float* src, long long lds, const int* row_idx, bf16* dst, long long ldd, int rows, int cols, cudaStream_t s);
+int gather_rows_bf16(const bf16* src, long long lds, const int* row_idx, bf16* dst, long long ldd, int rows, int cols, cudaStream_t s);
+int scatter_rows_bf16(const bf16* src, long long lds, const int* row_idx, bf16* dst, long long ldd, int rows, int cols, cudaStream_t s);
+int add_bf16(const bf16* a, const bf16* b, bf16* out, long long n, cudaStream_t s);
+int gelu_bf16(const bf16* x, bf16* y, long long n, cudaStream_t s);
+
+}  // namespace fo1

@@ -1,0 +1,111 @@
+// norm.cu -- row normalisations (memory-bound: one pass, fp32 statistics, 16-byte vector I/O).
+#include "kernels.cuh"
+
+namespace fo1 {
+
+// one warp per row; each lane walks the row in 8-element (16 B) vectors, keeping them in registers
+template <int MAXV, bool RMS>
+__global__ void __launch_bounds__(256) rownorm_kernel(const bf16* __restrict__ x, long long ldx, const bf16* __restrict__ gamma,
+                                                      const bf16* __restrict__ beta, bf16* __restrict__ y, long long ldy,
+                                                      int rows, int cols, float eps) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const bf16* xr = x + (long long)row * ldx;
+  bf16* yr = y + (long long)row * ldy;
+  const int nvec = cols >> 3;
+  uint4 v[MAXV];
+  float sum = 0.f, sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int vi = lane + i * 32;
+    if (vi < nvec) {
+      v[i] = *reinterpret_cast<const uint4*>(xr + vi * 8);
+      const uint32_t u[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float a = bf16_lo(u[j]), b = bf16_hi(u[j]);
+        sum += a + b;
+        sq += a * a + b * b;
+      }
+    }
+  }
+  sum = warp_sum(sum);
+  sq = warp_sum(sq);
+  const float inv_n = 1.0f / (float)cols;
+  float mean = 0.f, rstd;
+  if (RMS) {
+    rstd = rsqrtf(sq * inv_n + eps);
+  } else {
+    mean = sum * inv_n;
+    float var = 0.f;  // two-pass variance on the register copy (no cancellation)
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      const int vi = lane + i * 32;
+      if (vi < nvec) {
+        const uint32_t u[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float a = bf16_lo(u[j]) - mean, b = bf16_hi(u[j]) - mean;
+          var += a * a + b * b;
+        }
+      }
+    }
+    var = warp_sum(var);
+    rstd = rsqrtf(var * inv_n + eps);
+  }
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int vi = lane + i * 32;
+    if (vi < nvec) {
+      const uint32_t u[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+      uint4 g = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u), bt = make_uint4(0, 0, 0, 0);
+      if (gamma) g = *reinterpret_cast<const uint4*>(gamma + vi * 8);
+      if (beta) bt = *reinterpret_cast<const uint4*>(beta + vi * 8);
+      const uint32_t gu[4] = {g.x, g.y, g.z, g.w}, bu[4] = {bt.x, bt.y, bt.z, bt.w};
+      uint32_t o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float a = (bf16_lo(u[j]) - mean) * rstd, b = (bf16_hi(u[j]) - mean) * rstd;
+        if (RMS) {  // Qwen2RMSNorm rounds the normalised value to bf16 before the gain (:139-140)
+          a = __bfloat162float(__float2bfloat16_rn(a));
+          b = __bfloat162float(__float2bfloat16_rn(b));
+        }
+        a = a * bf16_lo(gu[j]) + bf16_lo(bu[j]);
+        b = b * bf16_hi(gu[j]) + bf16_hi(bu[j]);
+        o[j] = pack_bf16(a, b);
+      }
+      *reinterpret_cast<uint4*>(yr + vi * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+  }
+}
+
+template <bool RMS>
+static int launch_rownorm(const bf16* x, long long ldx, const bf16* g, const bf16* b, bf16* y, long long ldy, int rows, int cols,
+                          float eps, cudaStream_t s) {
+  FO1_CHECK_ARG(cols % 8 == 0 && ldx % 8 == 0 && ldy % 8 == 0, "rownorm: cols/pitches must be multiples of 8 (cols=%d)", cols);
+  FO1_CHECK_ARG(cols <= 8 * 32 * 32, "rownorm: cols=%d too large", cols);
+  if (rows == 0) return FO1_OK;
+  const int nvec = cols / 8;
+  const int maxv = ceil_div(nvec, 32);
+  dim3 grid(ceil_div(rows, 8));
+#define FO1_RN(MV)                                                                              \
+  if (maxv <= MV) {                                                                             \
+    rownorm_kernel<MV, RMS><<<grid, 256, 0, s>>>(x, ldx, g, b, y, ldy, rows, cols, eps);        \
+    FO1_LAUNCH_CHECK();                                                                         \
+    return FO1_OK;                                                                              \
+  }
+  FO1_RN(1) FO1_RN(2) FO1_RN(4) FO1_RN(5) FO1_RN(8) FO1_RN(16) FO1_RN(32)
+#undef FO1_RN
+  return FO1_ERR_UNSUPPORTED;
+}
+
+int rmsnorm(const bf16* x, long long ldx, const bf16* w, bf16* y, long long ldy, int rows, int cols, float eps, cudaStream_t s) {
+  return launch_rownorm<true>(x, ldx, w, nullptr, y, ldy, rows, cols, eps, s);
+}
+int layernorm(const bf16* x, long long ldx, const bf16* gamma, const bf16* beta, bf16* y, long long ldy, int rows, int cols,
+              float eps, cudaStream_t s) {
+  return launch_rownorm<false>(x, ldx, gamma, beta, y, ldy, rows, cols, eps, s);
+}
+
+}  // namespace fo1

@@ -119,6 +119,91 @@ typedef struct {
 
 int fo1_gemm_bf16(const fo1_gemm_desc* d, void* stream);
 
+
+
+/* ------------------------------------------------------------------------------------------------
+ * Variable-length softmax attention over packed token rows (replaces flash_attn_varlen_func at
+ * modeling_qwen2_5_vl.py:205 and _flash_attention_forward at :895, and DaViT's window attention
+ * modeling_davit.py:261-268).  q/k/v/o: bf16 rows with the given pitches (elements); head h of a row
+ * starts at h*head_dim.  cu_seqlens: device int32 [n_seqs+1].  head_dim in {32, 80, 128}.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  const void* q; const void* k; const void* v; void* o;
+  int64_t ldq, ldk, ldv, ldo;
+  const int32_t* cu_seqlens;
+  int32_t n_seqs, max_seqlen;
+  int32_t q_heads, kv_heads, head_dim;
+  float scale;
+  int32_t causal;
+} fo1_attn_desc;
+int fo1_attention_varlen(const fo1_attn_desc* d, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Model-level engine.  One handle per GPU / rank; calls on one handle are not re-entrant.
+ * Weights are BORROWED device pointers (the caller keeps them alive): the Python loader prepares
+ * them once (layout changes listed in DESIGN.md section "weights") from the checkpoint tensors that
+ * vlm_fo1/model/builder.py:90-131 loads.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct fo1_model fo1_model;
+
+typedef struct {
+  /* primary tower: Qwen2.5-VL ViT (configuration_qwen2_5_vl.py:30-66) */
+  int32_t vit_depth, vit_hidden, vit_heads, vit_inter, vit_inter_pad, vit_out_hidden;
+  int32_t vit_patch, vit_merge, vit_temporal, vit_in_ch, vit_window;
+  int32_t vit_n_fullatt; int32_t vit_fullatt[8];   /* fullatt_block_indexes, also the tap layers */
+  /* aux tower: DaViT (davit/configs.py:70-136) */
+  int32_t davit_dims[4], davit_depths[4], davit_heads[4], davit_groups[4], davit_window;
+  /* SimpleFPN on the last tap (simple_fpn.py:100-216) */
+  int32_t fpn_out;                 /* 512; 0 = FPN absent (variant A) */
+  /* region projector / image projector (multimodal_projector/builder.py:39-115) */
+  int32_t region_dim;              /* mm_region_hidden_size */
+  int32_t proj_aux_layers;         /* mlpNx_gelu depth; 1 = linear */
+  int32_t proj_img_layers;         /* 0 = identity */
+  /* LLM: Qwen2.5 decoder (configuration_qwen2_5_vl.py:193-253) */
+  int32_t llm_layers, llm_hidden, llm_heads, llm_kv_heads, llm_head_dim, llm_inter, llm_vocab;
+  int32_t mrope_section[3];
+  float rope_theta, rms_eps;
+  int32_t tie_embeddings;
+} fo1_model_config;
+
+int fo1_model_create(const fo1_model_config* cfg, fo1_model** out);
+void fo1_model_destroy(fo1_model* m);
+/* Register one prepared weight (device pointer, borrowed).  Names: see DESIGN.md / vlm-fo1_b200/weights.py. */
+int fo1_model_set_weight(fo1_model* m, const char* name, const void* dev_ptr, int32_t dtype, int32_t ndim,
+                         const int64_t* shape);
+/* Check that every weight the configured towers need is present with the right shape. */
+int fo1_model_finalize(fo1_model* m);
+
+/* Primary tower forward over a batch of images (replaces Qwen2_5_VlVisionTower.forward ->
+ * custom_forward + extract_multi_level_features, qwen2_5_vl_encoder.py:86-158, 37-80, 228-257).
+ * pixel_values[b]: device fp32 [gh*gw][in_ch*temporal*patch*patch] as Qwen2VLImageProcessor emits it;
+ * grid_hw: host int32 [B][2].  Outputs (device, caller-owned, bf16):
+ *   img_feats : [sum_b gh*gw/merge^2][out_hidden]   merged tokens, images back to back, raster order
+ *   taps[t]   : [sum_b gh*gw][hidden] for each full-attention layer t -- image b's slice is its
+ *               channels-last map [gh][gw][hidden] (un-windowed; what HFRE / SimpleFPN read). */
+int fo1_vit_forward(fo1_model* m, const float* const* pixel_values, const int32_t* grid_hw, int32_t n_images,
+                    void* img_feats, void* const* taps, void* stream);
+/* Integer bookkeeping of the tower, exposed for bit-exact parity tests against
+ * get_window_index / rot_pos_emb (modeling_qwen2_5_vl.py:436-504).  Host outputs, sized by the caller:
+ * window_index [gh*gw/merge^2], cu_window_seqlens [<= n_windows+1] (count returned), pos_hw [gh*gw][2]
+ * in window order. */
+int fo1_vit_window_index(const fo1_model_config* cfg, int32_t gh, int32_t gw, int32_t* window_index,
+                         int32_t* cu_window_seqlens, int32_t* n_cu, int32_t* pos_hw);
+
+/* Aux tower forward (replaces DavitVisionTower.forward -> DaViT.forward_features,
+ * davit_aux_encoder.py:54-73, modeling_davit.py:478-506) for n_images images of the SAME size H x W.
+ * images[b]: device fp32 [3][H][W] (CLIP-normalised).  stage_out[s]: bf16 [B][H_s][W_s][C_s], s = 0..3. */
+int fo1_davit_forward(fo1_model* m, const float* const* images, int32_t H, int32_t W, int32_t n_images,
+                      void* const* stage_out, void* stream);
+
+/* SimpleFPN (replaces SimpleFP.forward, simple_fpn.py:197-216) on n_images last-tap maps of the SAME grid.
+ * tap: bf16 [B][gh][gw][hidden] ; level_out[l]: bf16 [B][gh*f][gw*f][fpn_out], f = 4, 2, 1, 1/2. */
+int fo1_fpn_forward(fo1_model* m, const void* tap, int32_t gh, int32_t gw, int32_t n_images, void* const* level_out,
+                    void* stream);
+
+/* Region projector mm_projector_aux (omchat_qwen2_5_vl.py:107): bf16 [n][region_dim] -> bf16 [n][llm_hidden]. */
+int fo1_region_project(fo1_model* m, const void* feats, int32_t n, void* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -107,8 +107,220 @@ def gen_hfre() -> None:
 
 STAGES = {"hfre": gen_hfre}
 
+
+# --------------------------------------------------------------------------- towers (reference modules)
+def _bf16_params_(mod: torch.nn.Module) -> None:
+    for prm in mod.parameters():
+        prm.data = bf16_round(prm.data)
+
+
+def _sd_bits(sd) -> dict:
+    """state_dict -> {name: uint16 bf16 bit pattern} (values are already bf16-representable)."""
+    return {"w::" + k: v.detach().to(torch.bfloat16).view(torch.int16).numpy() for k, v in sd.items()}
+
+
+VIT_SMALL = dict(depth=4, hidden_size=64, num_heads=2, intermediate_size=88, out_hidden_size=48, patch_size=14,
+                 spatial_merge_size=2, temporal_patch_size=2, in_channels=3, window_size=112, fullatt_block_indexes=[1, 3],
+                 hidden_act="silu", in_chans=3, tokens_per_second=2)
+
+
+def gen_vit() -> None:
+    ref_shim.load_reference_package()
+    from vlm_fo1.model.multimodal_encoder.qwen2_5_vl.configuration_qwen2_5_vl import Qwen2_5_VLVisionConfig
+    from vlm_fo1.model.multimodal_encoder.qwen2_5_vl.modeling_qwen2_5_vl import Qwen2_5_VisionTransformerPretrainedModel
+    from vlm_fo1.model.multimodal_encoder import qwen2_5_vl_encoder as enc
+    torch.manual_seed(0)
+    cfg = Qwen2_5_VLVisionConfig(**VIT_SMALL)
+    enc.replace_qwen_vit_forward()
+    model = Qwen2_5_VisionTransformerPretrainedModel._from_config(cfg, attn_implementation="eager").float().eval()
+    for prm in model.parameters():  # the default init leaves norms at 1 / biases at 0: randomise so every term is exercised
+        prm.data = torch.randn_like(prm) * (0.02 if prm.dim() > 1 else 0.3) + (1.0 if "norm" in "" else 0.0)
+    for n, prm in model.named_parameters():
+        if n.endswith("norm1.weight") or n.endswith("norm2.weight") or n.endswith("ln_q.weight"):
+            prm.data = prm.data + 1.0
+    _bf16_params_(model)
+    model.init_vision_features_gather(enc.GATHER)
+    out = {}
+    int_tables = {}
+    for tag, gh, gw in (("a", 6, 10), ("b", 8, 8)):
+        px = bf16_round(torch.randn(gh * gw, 3 * 2 * 14 * 14))
+        grid = torch.tensor([[1, gh, gw]])
+        merged = model(px, grid_thw=grid)
+        taps = enc.GATHER.extract_multi_level_features()[0]
+        out[f"px_{tag}"] = px
+        out[f"grid_{tag}"] = np.array([gh, gw])
+        out[f"merged_{tag}"] = merged
+        for i, t in enumerate(taps):
+            out[f"tap{i}_{tag}"] = t[0].permute(1, 2, 0).contiguous()   # [gh, gw, C]
+    # integer bookkeeping at the BASELINE grids (bit-exact targets)
+    for gh, gw in ((6, 10), (8, 8), (32, 32), (46, 46), (64, 64), (28, 36), (96, 96), (2, 2), (4, 18)):
+        wi, cu = model.get_window_index(torch.tensor([[1, gh, gw]]))
+        cu = torch.unique_consecutive(torch.tensor(cu))
+        int_tables[f"wi_{gh}x{gw}"] = wi.numpy().astype(np.int32)
+        int_tables[f"cu_{gh}x{gw}"] = cu.numpy().astype(np.int32)
+    save("vit_small", cfg_json=np.frombuffer(__import__("json").dumps(VIT_SMALL).encode(), dtype=np.uint8),
+         **_sd_bits(model.state_dict()), **out, **int_tables)
+
+
+DAVIT_SMALL = dict(depths=[1, 1, 2, 1], dim_embed=[32, 32, 64, 64], num_heads=[1, 1, 2, 2], num_groups=[1, 1, 2, 2],
+                   patch_size=[7, 3, 3, 3], patch_stride=[4, 2, 2, 2], patch_padding=[3, 1, 1, 1],
+                   patch_prenorm=[False, True, True, True], drop_path_rate=0.0, window_size=12)
+
+
+def gen_davit() -> None:
+    ref_shim.load_reference_package()
+    from vlm_fo1.model.multimodal_encoder.davit.modeling_davit import DaViT
+    from types import SimpleNamespace
+    torch.manual_seed(1)
+    model = DaViT.from_config(SimpleNamespace(**DAVIT_SMALL)).float().eval()
+    for n, prm in model.named_parameters():
+        if prm.dim() == 1:
+            prm.data = torch.randn_like(prm) * 0.2 + (1.0 if n.endswith("norm.weight") else 0.0)
+        else:
+            prm.data = torch.randn_like(prm) * 0.05
+    _bf16_params_(model)
+    out = {}
+    for tag, H, W in (("a", 72, 104), ("b", 96, 96)):
+        img = bf16_round(torch.randn(1, 3, H, W))
+        feats = model(img)["image_features"]
+        out[f"img_{tag}"] = img[0]
+        for i, f in enumerate(feats):
+            out[f"stage{i}_{tag}"] = f[0].permute(1, 2, 0).contiguous()
+    save("davit_small", cfg_json=np.frombuffer(__import__("json").dumps(DAVIT_SMALL).encode(), dtype=np.uint8),
+         **_sd_bits(model.state_dict()), **out)
+
+
+def gen_fpn() -> None:
+    _, fpn = ref_shim.load_hfre_only()
+    torch.manual_seed(2)
+    model = fpn.SimpleFP(out_channels=32, norm="LN", square_pad=0, dim=64, stride=14).float().eval()
+    for n, prm in model.named_parameters():
+        if prm.dim() == 1:
+            prm.data = torch.randn_like(prm) * 0.2 + (1.0 if "norm" in n or n.endswith("1.weight") else 0.0)
+        else:
+            prm.data = torch.randn_like(prm) * 0.08
+    _bf16_params_(model)
+    out = {}
+    for tag, gh, gw in (("a", 6, 10), ("b", 8, 8)):
+        tap = bf16_round(torch.randn(1, 64, gh, gw))
+        levels = model(tap)
+        out[f"tap_{tag}"] = tap[0].permute(1, 2, 0).contiguous()
+        for i, f in enumerate(levels):
+            out[f"level{i}_{tag}"] = f[0].permute(1, 2, 0).contiguous()
+    save("fpn_small", **_sd_bits(model.state_dict()), **out)
+
+
+STAGES.update({"vit": gen_vit, "davit": gen_davit, "fpn": gen_fpn})
+
+# --------------------------------------------------------------------------- towers (reference modules)
+def _bf16_params_(mod: torch.nn.Module) -> None:
+    for prm in mod.parameters():
+        prm.data = bf16_round(prm.data)
+
+
+def _sd_bits(sd) -> dict:
+    """state_dict -> {name: uint16 bf16 bit pattern} (values are already bf16-representable)."""
+    return {"w::" + k: v.detach().to(torch.bfloat16).view(torch.int16).numpy() for k, v in sd.items()}
+
+
+VIT_SMALL = dict(depth=4, hidden_size=64, num_heads=2, intermediate_size=88, out_hidden_size=48, patch_size=14,
+                 spatial_merge_size=2, temporal_patch_size=2, in_channels=3, window_size=112, fullatt_block_indexes=[1, 3],
+                 hidden_act="silu", in_chans=3, tokens_per_second=2)
+
+
+def gen_vit() -> None:
+    ref_shim.load_reference_package()
+    from vlm_fo1.model.multimodal_encoder.qwen2_5_vl.configuration_qwen2_5_vl import Qwen2_5_VLVisionConfig
+    from vlm_fo1.model.multimodal_encoder.qwen2_5_vl.modeling_qwen2_5_vl import Qwen2_5_VisionTransformerPretrainedModel
+    from vlm_fo1.model.multimodal_encoder import qwen2_5_vl_encoder as enc
+    torch.manual_seed(0)
+    cfg = Qwen2_5_VLVisionConfig(**VIT_SMALL)
+    enc.replace_qwen_vit_forward()
+    model = Qwen2_5_VisionTransformerPretrainedModel._from_config(cfg, attn_implementation="eager").float().eval()
+    for prm in model.parameters():  # the default init leaves norms at 1 / biases at 0: randomise so every term is exercised
+        prm.data = torch.randn_like(prm) * (0.02 if prm.dim() > 1 else 0.3) + (1.0 if "norm" in "" else 0.0)
+    for n, prm in model.named_parameters():
+        if n.endswith("norm1.weight") or n.endswith("norm2.weight") or n.endswith("ln_q.weight"):
+            prm.data = prm.data + 1.0
+    _bf16_params_(model)
+    model.init_vision_features_gather(enc.GATHER)
+    out = {}
+    int_tables = {}
+    for tag, gh, gw in (("a", 6, 10), ("b", 8, 8)):
+        px = bf16_round(torch.randn(gh * gw, 3 * 2 * 14 * 14))
+        grid = torch.tensor([[1, gh, gw]])
+        merged = model(px, grid_thw=grid)
+        taps = enc.GATHER.extract_multi_level_features()[0]
+        out[f"px_{tag}"] = px
+        out[f"grid_{tag}"] = np.array([gh, gw])
+        out[f"merged_{tag}"] = merged
+        for i, t in enumerate(taps):
+            out[f"tap{i}_{tag}"] = t[0].permute(1, 2, 0).contiguous()   # [gh, gw, C]
+    # integer bookkeeping at the BASELINE grids (bit-exact targets)
+    for gh, gw in ((6, 10), (8, 8), (32, 32), (46, 46), (64, 64), (28, 36), (96, 96), (2, 2), (4, 18)):
+        wi, cu = model.get_window_index(torch.tensor([[1, gh, gw]]))
+        cu = torch.unique_consecutive(torch.tensor(cu))
+        int_tables[f"wi_{gh}x{gw}"] = wi.numpy().astype(np.int32)
+        int_tables[f"cu_{gh}x{gw}"] = cu.numpy().astype(np.int32)
+    save("vit_small", cfg_json=np.frombuffer(__import__("json").dumps(VIT_SMALL).encode(), dtype=np.uint8),
+         **_sd_bits(model.state_dict()), **out, **int_tables)
+
+
+DAVIT_SMALL = dict(depths=[1, 1, 2, 1], dim_embed=[32, 32, 64, 64], num_heads=[1, 1, 2, 2], num_groups=[1, 1, 2, 2],
+                   patch_size=[7, 3, 3, 3], patch_stride=[4, 2, 2, 2], patch_padding=[3, 1, 1, 1],
+                   patch_prenorm=[False, True, True, True], drop_path_rate=0.0, window_size=12)
+
+
+def gen_davit() -> None:
+    ref_shim.load_reference_package()
+    from vlm_fo1.model.multimodal_encoder.davit.modeling_davit import DaViT
+    from types import SimpleNamespace
+    torch.manual_seed(1)
+    model = DaViT.from_config(SimpleNamespace(**DAVIT_SMALL)).float().eval()
+    for n, prm in model.named_parameters():
+        if prm.dim() == 1:
+            prm.data = torch.randn_like(prm) * 0.2 + (1.0 if n.endswith("norm.weight") else 0.0)
+        else:
+            prm.data = torch.randn_like(prm) * 0.05
+    _bf16_params_(model)
+    out = {}
+    for tag, H, W in (("a", 72, 104), ("b", 96, 96)):
+        img = bf16_round(torch.randn(1, 3, H, W))
+        feats = model(img)["image_features"]
+        out[f"img_{tag}"] = img[0]
+        for i, f in enumerate(feats):
+            out[f"stage{i}_{tag}"] = f[0].permute(1, 2, 0).contiguous()
+    save("davit_small", cfg_json=np.frombuffer(__import__("json").dumps(DAVIT_SMALL).encode(), dtype=np.uint8),
+         **_sd_bits(model.state_dict()), **out)
+
+
+def gen_fpn() -> None:
+    _, fpn = ref_shim.load_hfre_only()
+    torch.manual_seed(2)
+    model = fpn.SimpleFP(out_channels=32, norm="LN", square_pad=0, dim=64, stride=14).float().eval()
+    for n, prm in model.named_parameters():
+        if prm.dim() == 1:
+            prm.data = torch.randn_like(prm) * 0.2 + (1.0 if "norm" in n or n.endswith("1.weight") else 0.0)
+        else:
+            prm.data = torch.randn_like(prm) * 0.08
+    _bf16_params_(model)
+    out = {}
+    for tag, gh, gw in (("a", 6, 10), ("b", 8, 8)):
+        tap = bf16_round(torch.randn(1, 64, gh, gw))
+        levels = model(tap)
+        out[f"tap_{tag}"] = tap[0].permute(1, 2, 0).contiguous()
+        for i, f in enumerate(levels):
+            out[f"level{i}_{tag}"] = f[0].permute(1, 2, 0).contiguous()
+    save("fpn_small", **_sd_bits(model.state_dict()), **out)
+
+
+STAGES.update({"vit": gen_vit, "davit": gen_davit, "fpn": gen_fpn})
+
 if __name__ == "__main__":
     torch.set_grad_enabled(False)
     wanted = sys.argv[1:] or list(STAGES)
     for s in wanted:
         STAGES[s]()
+
+
+

@@ -92,8 +92,8 @@ def load_reference_package():
         mod = sys.modules[k]
         if getattr(mod, "__file__", None) is None:  # drop the light stubs from load_hfre_only()
             del sys.modules[k]
+    _install_transformers_shims()   # imports transformers first (its lazy init probes for a real timm)
     _install_timm_stub()
-    _install_transformers_shims()
     if REFERENCE_ROOT not in sys.path:
         sys.path.insert(0, REFERENCE_ROOT)
     return importlib.import_module("vlm_fo1.model")

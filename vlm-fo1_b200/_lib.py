@@ -43,6 +43,14 @@ class GemmDesc(C.Structure):
                 ("residual", C.c_void_p), ("ldr", C.c_int64), ("gated", C.c_int32)]
 
 
+class AttnDesc(C.Structure):
+    _fields_ = [("q", C.c_void_p), ("k", C.c_void_p), ("v", C.c_void_p), ("o", C.c_void_p),
+                ("ldq", C.c_int64), ("ldk", C.c_int64), ("ldv", C.c_int64), ("ldo", C.c_int64),
+                ("cu_seqlens", C.c_void_p), ("n_seqs", C.c_int32), ("max_seqlen", C.c_int32),
+                ("q_heads", C.c_int32), ("kv_heads", C.c_int32), ("head_dim", C.c_int32),
+                ("scale", C.c_float), ("causal", C.c_int32)]
+
+
 _lib = None
 
 
@@ -66,6 +74,8 @@ def lib() -> C.CDLL:
                                    C.c_size_t, C.c_void_p]
     L.fo1_gemm_bf16.restype = C.c_int
     L.fo1_gemm_bf16.argtypes = [C.POINTER(GemmDesc), C.c_void_p]
+    L.fo1_attention_varlen.restype = C.c_int
+    L.fo1_attention_varlen.argtypes = [C.POINTER(AttnDesc), C.c_void_p]
     _lib = L
     return L
 

@@ -1,0 +1,182 @@
+"""Model handle over the C ABI: owns the fo1_model*, keeps the prepared weight tensors alive, and exposes
+the stage entry points with torch tensors as memory handles."""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import check, lib
+
+_DT = {torch.bfloat16: _lib.FO1_BF16, torch.float32: _lib.FO1_F32}
+
+
+class ModelConfigC(C.Structure):
+    _fields_ = [
+        ("vit_depth", C.c_int32), ("vit_hidden", C.c_int32), ("vit_heads", C.c_int32), ("vit_inter", C.c_int32),
+        ("vit_inter_pad", C.c_int32), ("vit_out_hidden", C.c_int32), ("vit_patch", C.c_int32), ("vit_merge", C.c_int32),
+        ("vit_temporal", C.c_int32), ("vit_in_ch", C.c_int32), ("vit_window", C.c_int32),
+        ("vit_n_fullatt", C.c_int32), ("vit_fullatt", C.c_int32 * 8),
+        ("davit_dims", C.c_int32 * 4), ("davit_depths", C.c_int32 * 4), ("davit_heads", C.c_int32 * 4),
+        ("davit_groups", C.c_int32 * 4), ("davit_window", C.c_int32),
+        ("fpn_out", C.c_int32), ("region_dim", C.c_int32), ("proj_aux_layers", C.c_int32), ("proj_img_layers", C.c_int32),
+        ("llm_layers", C.c_int32), ("llm_hidden", C.c_int32), ("llm_heads", C.c_int32), ("llm_kv_heads", C.c_int32),
+        ("llm_head_dim", C.c_int32), ("llm_inter", C.c_int32), ("llm_vocab", C.c_int32),
+        ("mrope_section", C.c_int32 * 3), ("rope_theta", C.c_float), ("rms_eps", C.c_float), ("tie_embeddings", C.c_int32),
+    ]
+
+
+@dataclass
+class EngineConfig:
+    """Python-side mirror of fo1_model_config; defaults are the released 3B checkpoint's architecture
+    (ViT 32x1280, DaViT-large, SimpleFPN 512, Qwen2.5-3B)."""
+    vit: dict = field(default_factory=lambda: dict(depth=32, hidden_size=1280, num_heads=16, intermediate_size=3420,
+                                                   out_hidden_size=2048, patch_size=14, spatial_merge_size=2,
+                                                   temporal_patch_size=2, in_channels=3, window_size=112,
+                                                   fullatt_block_indexes=[7, 15, 23, 31]))
+    davit: dict = field(default_factory=lambda: dict(depths=[1, 1, 9, 1], dim_embed=[256, 512, 1024, 2048],
+                                                     num_heads=[8, 16, 32, 64], num_groups=[8, 16, 32, 64], window_size=12))
+    fpn_out: int = 512
+    region_dim: int = 5888
+    proj_aux_layers: int = 2
+    proj_img_layers: int = 0
+    llm: dict = field(default_factory=lambda: dict(num_hidden_layers=36, hidden_size=2048, num_attention_heads=16,
+                                                   num_key_value_heads=2, intermediate_size=11008, vocab_size=151936,
+                                                   rope_theta=1000000.0, rms_norm_eps=1e-6, mrope_section=[16, 24, 24],
+                                                   tie_word_embeddings=True))
+    use_vit: bool = True
+    use_davit: bool = True
+    use_llm: bool = True
+
+    def to_c(self) -> ModelConfigC:
+        from .weights import vit_inter_pad
+        c = ModelConfigC()
+        if self.use_vit:
+            v = self.vit
+            c.vit_depth, c.vit_hidden, c.vit_heads = v["depth"], v["hidden_size"], v["num_heads"]
+            c.vit_inter, c.vit_inter_pad = v["intermediate_size"], vit_inter_pad(v["intermediate_size"])
+            c.vit_out_hidden, c.vit_patch, c.vit_merge = v["out_hidden_size"], v["patch_size"], v["spatial_merge_size"]
+            c.vit_temporal, c.vit_in_ch, c.vit_window = v["temporal_patch_size"], v.get("in_channels", 3), v["window_size"]
+            fa = list(v["fullatt_block_indexes"])
+            c.vit_n_fullatt = len(fa)
+            for i, x in enumerate(fa):
+                c.vit_fullatt[i] = x
+            c.fpn_out = self.fpn_out
+        if self.use_davit:
+            d = self.davit
+            for i in range(4):
+                c.davit_dims[i], c.davit_depths[i] = d["dim_embed"][i], d["depths"][i]
+                c.davit_heads[i], c.davit_groups[i] = d["num_heads"][i], d["num_groups"][i]
+            c.davit_window = d["window_size"]
+        c.region_dim, c.proj_aux_layers, c.proj_img_layers = self.region_dim, self.proj_aux_layers, self.proj_img_layers
+        l = self.llm
+        c.llm_hidden = l["hidden_size"]
+        if self.use_llm:
+            c.llm_layers, c.llm_heads, c.llm_kv_heads = l["num_hidden_layers"], l["num_attention_heads"], l["num_key_value_heads"]
+            c.llm_head_dim = l["hidden_size"] // l["num_attention_heads"]
+            c.llm_inter, c.llm_vocab = l["intermediate_size"], l["vocab_size"]
+            for i in range(3):
+                c.mrope_section[i] = l["mrope_section"][i]
+            c.rope_theta, c.rms_eps = l["rope_theta"], l["rms_norm_eps"]
+            c.tie_embeddings = 1 if l.get("tie_word_embeddings", False) else 0
+        return c
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class Engine:
+    def __init__(self, cfg: EngineConfig, device: Optional[torch.device] = None):
+        self.cfg = cfg
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self._c = cfg.to_c()
+        self._h = C.c_void_p()
+        L = lib()
+        L.fo1_model_create.restype = C.c_int
+        L.fo1_model_create.argtypes = [C.POINTER(ModelConfigC), C.POINTER(C.c_void_p)]
+        L.fo1_model_destroy.restype = None
+        L.fo1_model_destroy.argtypes = [C.c_void_p]
+        L.fo1_model_set_weight.restype = C.c_int
+        L.fo1_model_set_weight.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_int64)]
+        L.fo1_model_finalize.restype = C.c_int
+        L.fo1_model_finalize.argtypes = [C.c_void_p]
+        for fn in ("fo1_vit_forward", "fo1_davit_forward", "fo1_fpn_forward", "fo1_region_project"):
+            getattr(L, fn).restype = C.c_int
+        check(L.fo1_model_create(C.byref(self._c), C.byref(self._h)), "fo1_model_create")
+        self.weights: Dict[str, torch.Tensor] = {}
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None) and self._h.value:
+                lib().fo1_model_destroy(self._h)
+                self._h = C.c_void_p()
+        except Exception:
+            pass
+
+    # ---- weights ----
+    def set_weights(self, tensors: Dict[str, torch.Tensor]) -> None:
+        L = lib()
+        for name, t in tensors.items():
+            assert t.is_cuda and t.is_contiguous(), name
+            self.weights[name] = t
+            shape = (C.c_int64 * t.dim())(*t.shape)
+            check(L.fo1_model_set_weight(self._h, name.encode(), C.c_void_p(t.data_ptr()), _DT[t.dtype], t.dim(), shape),
+                  f"fo1_model_set_weight({name})")
+
+    def finalize(self) -> None:
+        check(lib().fo1_model_finalize(self._h), "fo1_model_finalize")
+
+    # ---- stages ----
+    def vit_forward(self, pixel_values: Sequence[torch.Tensor], grids: Sequence[Tuple[int, int]]):
+        """-> (img_feats [sum gh*gw/4, out_hidden] bf16, taps: list over tap layers of [sum gh*gw, hidden] bf16).
+        Image b's slice of a tap is its channels-last map [gh, gw, hidden]."""
+        v = self.cfg.vit
+        B = len(pixel_values)
+        px = [p.to(self.device, torch.float32).contiguous() for p in pixel_values]
+        T = sum(gh * gw for gh, gw in grids)
+        unit = v["spatial_merge_size"] ** 2
+        feats = torch.empty((T // unit, v["out_hidden_size"]), dtype=torch.bfloat16, device=self.device)
+        taps = [torch.empty((T, v["hidden_size"]), dtype=torch.bfloat16, device=self.device) for _ in v["fullatt_block_indexes"]]
+        pp = (C.c_void_p * B)(*[p.data_ptr() for p in px])
+        g = (C.c_int32 * (2 * B))(*[x for gw_ in grids for x in gw_])
+        tp = (C.c_void_p * len(taps))(*[t.data_ptr() for t in taps])
+        check(lib().fo1_vit_forward(self._h, pp, g, B, C.c_void_p(feats.data_ptr()), tp, _stream()), "fo1_vit_forward")
+        return feats, taps
+
+    def davit_forward(self, images: Sequence[torch.Tensor]) -> List[torch.Tensor]:
+        """images: B x fp32 [3, H, W] (same size) -> 4 stage maps bf16 [B, H_s, W_s, C_s]."""
+        B = len(images)
+        im = [i.to(self.device, torch.float32).contiguous() for i in images]
+        H, W = im[0].shape[-2:]
+        assert all(i.shape[-2:] == (H, W) for i in im), "fo1_davit_forward batches images of one size"
+        outs = []
+        h, w = (H + 6 - 7) // 4 + 1, (W + 6 - 7) // 4 + 1
+        for s in range(4):
+            if s:
+                h, w = (h + 2 - 3) // 2 + 1, (w + 2 - 3) // 2 + 1
+            outs.append(torch.empty((B, h, w, self.cfg.davit["dim_embed"][s]), dtype=torch.bfloat16, device=self.device))
+        ip = (C.c_void_p * B)(*[i.data_ptr() for i in im])
+        op = (C.c_void_p * 4)(*[o.data_ptr() for o in outs])
+        check(lib().fo1_davit_forward(self._h, ip, H, W, B, op, _stream()), "fo1_davit_forward")
+        return outs
+
+    def fpn_forward(self, tap: torch.Tensor) -> List[torch.Tensor]:
+        """tap bf16 [B, gh, gw, hidden] -> 4 levels bf16 [B, gh*f, gw*f, fpn_out]."""
+        B, gh, gw, _ = tap.shape
+        tap = tap.contiguous()
+        dims = [(gh * 4, gw * 4), (gh * 2, gw * 2), (gh, gw), (gh // 2, gw // 2)]
+        outs = [torch.empty((B, h, w, self.cfg.fpn_out), dtype=torch.bfloat16, device=self.device) for h, w in dims]
+        op = (C.c_void_p * 4)(*[o.data_ptr() for o in outs])
+        check(lib().fo1_fpn_forward(self._h, C.c_void_p(tap.data_ptr()), gh, gw, B, op, _stream()), "fo1_fpn_forward")
+        return outs
+
+    def region_project(self, feats: torch.Tensor) -> torch.Tensor:
+        feats = feats.contiguous()
+        out = torch.empty((feats.shape[0], self.cfg.llm["hidden_size"]), dtype=torch.bfloat16, device=self.device)
+        check(lib().fo1_region_project(self._h, C.c_void_p(feats.data_ptr()), feats.shape[0], C.c_void_p(out.data_ptr()), _stream()),
+              "fo1_region_project")
+        return out

@@ -66,3 +66,23 @@ def interleave_gate_up(gate: torch.Tensor, up: torch.Tensor, block: int = 32) ->
     g = gate.reshape(-1, block, *gate.shape[1:])
     u = up.reshape(-1, block, *up.shape[1:])
     return torch.stack([g, u], dim=1).reshape(-1, *gate.shape[1:]).contiguous()
+
+
+def attention_varlen(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, cu_seqlens: torch.Tensor, max_seqlen: int,
+                     q_heads: int, kv_heads: int, head_dim: int, scale: float, causal: bool = False,
+                     out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """q/k/v: bf16 [T, heads*head_dim] views (any row pitch, unit column stride); cu_seqlens int32 [n+1] on device."""
+    _require_cuda(q, k, v, cu_seqlens)
+    T = q.shape[0]
+    if out is None:
+        out = torch.empty((T, q_heads * head_dim), dtype=torch.bfloat16, device=q.device)
+    d = _lib.AttnDesc()
+    d.q, d.k, d.v, d.o = q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr()
+    d.ldq, d.ldk, d.ldv, d.ldo = q.stride(0), k.stride(0), v.stride(0), out.stride(0)
+    assert cu_seqlens.dtype == torch.int32
+    d.cu_seqlens = cu_seqlens.data_ptr()
+    d.n_seqs, d.max_seqlen = cu_seqlens.numel() - 1, max_seqlen
+    d.q_heads, d.kv_heads, d.head_dim = q_heads, kv_heads, head_dim
+    d.scale, d.causal = scale, 1 if causal else 0
+    check(lib().fo1_attention_varlen(C.byref(d), C.c_void_p(_stream())), "fo1_attention_varlen")
+    return out

@@ -204,6 +204,61 @@ int fo1_fpn_forward(fo1_model* m, const void* tap, int32_t gh, int32_t gw, int32
 /* Region projector mm_projector_aux (omchat_qwen2_5_vl.py:107): bf16 [n][region_dim] -> bf16 [n][llm_hidden]. */
 int fo1_region_project(fo1_model* m, const void* feats, int32_t n, void* out, void* stream);
 
+
+/* ------------------------------------------------------------------------------------------------
+ * LLM half: embedding splice, M-RoPE bookkeeping, prefill and greedy decode.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t image_token_id;        /* config.image_token_id (151655) */
+  int32_t video_token_id;        /* config.video_token_id (151656) */
+  int32_t vision_start_token_id; /* config.vision_start_token_id (151652) */
+  int32_t merge;                 /* vision_config.spatial_merge_size */
+  int32_t image_placeholder;     /* IMAGE_TOKEN_INDEX  (-200, vlm_fo1/constants.py) */
+  int32_t region_placeholder;    /* DEFAULT_REGION_INDEX (-300) */
+} fo1_splice_cfg;
+
+/* Integer work of prepare_inputs_labels_for_qwen2_5_vl_multimodal (omchat_qwen2_5_vl.py:291-373, 434-458)
+ * + get_rope_index (modeling_qwen2_5_vl.py:1546-1721) for ONE sample (host only, bit-exact):
+ * every image placeholder expands to that image's gh*gw/merge^2 feature rows (ids <- image_token_id), every
+ * region placeholder keeps one slot (id stays region_placeholder); then the 3-axis position ids.
+ * Outputs (host, capacity elements each; position_ids 3*capacity laid out [3][capacity]):
+ *   new_ids, src_kind (0 text / 1 image row / 2 region row), src_index (token id / row in the image- /
+ *   region-feature matrix of this sample), position_ids, *rope_delta, *out_len.
+ * Returns FO1_ERR_WORKSPACE if capacity is too small (out_len then holds the needed length). */
+int fo1_splice_plan(const int64_t* input_ids, int32_t n_ids, const int32_t* image_grid_hw, int32_t n_images,
+                    int32_t n_regions, const fo1_splice_cfg* cfg, int64_t* new_ids, int32_t* src_kind,
+                    int32_t* src_index, int32_t* position_ids, int32_t* rope_delta, int32_t* out_len,
+                    int32_t capacity);
+
+/* inputs_embeds[r] = embed_tokens[src_index[r]] | img_feats[src_index[r]] | region_feats[src_index[r]]
+ * (omchat_qwen2_5_vl.py:333-368).  src_kind / src_index: device int32 [n_rows]; feature matrices bf16
+ * [*, llm_hidden] with indices already offset per sample by the caller. */
+int fo1_llm_build_embeds(fo1_model* m, const int32_t* src_kind, const int32_t* src_index, int32_t n_rows,
+                         const void* img_feats, const void* region_feats, void* inputs_embeds, void* stream);
+
+typedef struct {
+  int32_t n_seqs;
+  const int32_t* seq_lens;        /* host [n_seqs]: L_b, prompt length after the splice */
+  const void* inputs_embeds;      /* device bf16 [sum L_b][llm_hidden], sequences packed back to back */
+  const int32_t* position_ids;    /* device int32 [3][sum L_b] */
+  const int32_t* rope_deltas;     /* host [n_seqs] */
+  int32_t max_new_tokens;
+  const int32_t* stop_ids;        /* host [n_stop_ids]: generation stops after emitting one of these */
+  int32_t n_stop_ids;
+  int32_t pad_id;
+  int32_t* out_tokens;            /* device int32 [n_seqs][max_new_tokens], pad_id after the stop token */
+  int32_t* out_lens;              /* device int32 [n_seqs], counts the stop token */
+  float* prefill_logits;          /* optional device fp32 [n_seqs][vocab]: logits at the last prompt position */
+  float* all_logits;              /* optional device fp32 [sum L_b][vocab]: logits at every prompt position */
+  int32_t early_exit_interval;    /* host polls "all sequences stopped" every k decode steps (0 = never) */
+  int32_t steps_run;              /* out: decode iterations actually executed */
+} fo1_generate_desc;
+
+/* Prefill + greedy decode (replaces OmChatQwen25VLForCausalLM.forward / HF generate's greedy loop /
+ * DynamicCache for this path: omchat_qwen2_5_vl.py:466-532, modeling_qwen2_5_vl.py:1126-1242, 1848-1876).
+ * The K/V cache and the decode loop state live on the device; the host only launches. */
+int fo1_llm_generate(fo1_model* m, fo1_generate_desc* d, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -316,6 +316,101 @@ def gen_fpn() -> None:
 
 STAGES.update({"vit": gen_vit, "davit": gen_davit, "fpn": gen_fpn})
 
+LLM_SMALL = dict(num_hidden_layers=3, hidden_size=256, num_attention_heads=2, num_key_value_heads=1, intermediate_size=352,
+                 vocab_size=512, rope_theta=1000000.0, rms_norm_eps=1e-6, mrope_section=[16, 24, 24], tie_word_embeddings=False)
+
+
+def gen_llm() -> None:
+    """Pins oracle/llm.py: (1) get_rope_index called unbound on the reference class; (2) a 3-layer stack of the
+    reference's own Qwen2_5_VLDecoderLayer + Qwen2_5_VLRotaryEmbedding + Qwen2RMSNorm driven by the thin model loop
+    (modeling_qwen2_5_vl.py:1188-1230) -- prefill with a causal mask, then two decode steps with a DynamicCache."""
+    ref_shim.load_reference_package()
+    from types import SimpleNamespace as NS
+    from vlm_fo1.model.multimodal_encoder.qwen2_5_vl import modeling_qwen2_5_vl as M
+    import json
+    out = {}
+    # ---- (1) rope index ----
+    g = torch.Generator().manual_seed(5)
+    self_ns = NS(config=NS(vision_config=NS(spatial_merge_size=2, tokens_per_second=2), image_token_id=151655, video_token_id=151656,
+                           vision_start_token_id=151652))
+    cases = []
+    for ci, (grids, n_reg) in enumerate((([(8, 8)], 3), ([(6, 10)], 0), ([(4, 4), (8, 6)], 5), ([], 2), ([(64, 64)], 100))):
+        ids = torch.randint(0, 151640, (6,), generator=g).tolist()
+        for (gh, gw) in grids:
+            ids += [151652] + [151655] * (gh * gw // 4) + [151653] + torch.randint(0, 151640, (2,), generator=g).tolist()
+        for r in range(n_reg):
+            ids += [int(torch.randint(0, 151640, (1,), generator=g)), -300]
+        ids += torch.randint(0, 151640, (5,), generator=g).tolist() + [151645]
+        grid_thw = torch.tensor([[1, gh, gw] for gh, gw in grids]) if grids else None
+        if grid_thw is not None:
+            pos, delta = M.Qwen2_5_VLForConditionalGeneration.get_rope_index(self_ns, torch.tensor([ids]), grid_thw, None, None, None)
+            pos, delta = pos[:, 0], int(delta[0, 0])
+        else:
+            pos = torch.arange(len(ids)).view(1, -1).expand(3, -1); delta = 0
+        out[f"rope_ids_{ci}"] = np.array(ids, dtype=np.int64)
+        out[f"rope_grids_{ci}"] = np.array(grids, dtype=np.int32).reshape(-1, 2)
+        out[f"rope_pos_{ci}"] = pos.numpy().astype(np.int64)
+        out[f"rope_delta_{ci}"] = np.array(delta)
+        cases.append(ci)
+    # ---- (2) decoder stack from the reference's own layer modules ----
+    torch.manual_seed(3)
+    c = LLM_SMALL
+    cfg = NS(hidden_size=c["hidden_size"], num_attention_heads=c["num_attention_heads"], num_key_value_heads=c["num_key_value_heads"],
+             intermediate_size=c["intermediate_size"], hidden_act="silu", rms_norm_eps=c["rms_norm_eps"], attention_dropout=0.0,
+             rope_scaling={"type": "default", "mrope_section": c["mrope_section"], "rope_type": "default"}, rope_theta=c["rope_theta"],
+             max_position_embeddings=4096, use_sliding_window=False, sliding_window=None, max_window_layers=99,
+             _attn_implementation="eager", head_dim=c["hidden_size"] // c["num_attention_heads"])
+    layers = [M.Qwen2_5_VLDecoderLayer(cfg, i).float().eval() for i in range(c["num_hidden_layers"])]
+    norm = M.Qwen2RMSNorm(c["hidden_size"], eps=c["rms_norm_eps"]).float()
+    rot = M.Qwen2_5_VLRotaryEmbedding(config=cfg)
+    embed = torch.nn.Embedding(c["vocab_size"], c["hidden_size"])
+    head = torch.nn.Linear(c["hidden_size"], c["vocab_size"], bias=False)
+    sd = {}
+    for i, l in enumerate(layers):
+        for n, prm in l.named_parameters():
+            prm.data = bf16_round(torch.randn_like(prm) * (0.05 if prm.dim() > 1 else 0.2) + (1.0 if "layernorm" in n else 0.0))
+            sd[f"layers.{i}.{n}"] = prm.data
+    norm.weight.data = bf16_round(torch.randn(c["hidden_size"]) * 0.2 + 1.0); sd["norm.weight"] = norm.weight.data
+    embed.weight.data = bf16_round(torch.randn_like(embed.weight) * 0.5); sd["embed_tokens.weight"] = embed.weight.data
+    head.weight.data = bf16_round(torch.randn_like(head.weight) * 0.05); sd["lm_head.weight"] = head.weight.data
+    from transformers.cache_utils import DynamicCache
+    ids = out["rope_ids_0"]; pos = torch.from_numpy(out["rope_pos_0"]); delta = int(out["rope_delta_0"])
+    L = len(ids)
+    x = bf16_round(torch.randn(1, L, c["hidden_size"], generator=g))
+    out["llm_embeds"] = x[0]
+    cache = DynamicCache()
+
+    def run(x, pos3, past):
+        n = x.shape[1]
+        cos_sin = rot(x, pos3[:, None, :])
+        mask = torch.full((n, past + n), float("-inf")).triu(past + 1)[None, None]
+        h = x
+        for l in layers:
+            h = l(h, attention_mask=mask, position_ids=pos3[:, None, :], past_key_value=cache, use_cache=True,
+                  cache_position=torch.arange(past, past + n), position_embeddings=cos_sin)[0]
+        return h
+
+    h = run(x, pos, 0)
+    logits = head(norm(h))[0]
+    out["llm_prompt_logits"] = logits
+    toks = []
+    lg = logits[-1]
+    step_logits = []
+    for s in range(3):
+        step_logits.append(lg)
+        tok = int(lg.argmax()); toks.append(tok)
+        p = L + s + delta
+        h = run(embed(torch.tensor([[tok]])), torch.full((3, 1), p, dtype=torch.long), L + s)
+        lg = head(norm(h))[0, -1]
+    out["llm_step_logits"] = torch.stack(step_logits)
+    out["llm_tokens"] = np.array(toks)
+    save("llm_small", cfg_json=np.frombuffer(json.dumps(LLM_SMALL).encode(), dtype=np.uint8), n_rope_cases=np.array(len(cases)),
+         **_sd_bits(sd), **out)
+
+
+STAGES.update({"llm": gen_llm})
+
+
 if __name__ == "__main__":
     torch.set_grad_enabled(False)
     wanted = sys.argv[1:] or list(STAGES)

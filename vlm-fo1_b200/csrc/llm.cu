@@ -1,7 +1,615 @@
-// llm.cu -- Qwen2.5 decoder: prefill / decode (placeholder until the LLM stage lands).
+// llm.cu -- Qwen2.5 decoder on sm_100a: embedding splice, M-RoPE bookkeeping, varlen prefill, device-resident
+// greedy decode with a static K/V cache.
+//
+// Reference: OmChatQwen25VLForCausalLM.forward + prepare_inputs_labels_for_qwen2_5_vl_multimodal
+// (omchat_qwen2_5_vl.py:135-532), Qwen2_5_VLModel / DecoderLayer / Attention / MLP / RMSNorm
+// (modeling_qwen2_5_vl.py:1126-1242, 1014-1095, 738-802, 627-640, 126-140), get_rope_index (:1546-1721),
+// the decode position rule (:1848-1860) and HF's greedy loop with KeywordsStoppingCriteria (mm_utils.py:137-181).
+// B200-first differences: all sequences of the batch run packed (varlen), no padding tokens exist; K/V live
+// in one static [layer][seq][cap][kv] cache written by the prefill and appended in place by each decode
+// step (the reference torch.cat's a DynamicCache per layer per step); argmax, stop-token test and all loop
+// state stay on the device, the host only enqueues kernels (no per-token sync); lm_head runs on the last
+// prompt position only.
+#include <algorithm>
+
 #include "engine.cuh"
 
 namespace fo1 {
-int llm_finalize(Model* m) { (void)m; return FO1_OK; }
-void llm_destroy_state(Model* m) { (void)m; }
+
+// ------------------------------------------------------------------------------------------ kernels
+// inputs_embeds rows from three sources
+__global__ void __launch_bounds__(256) build_embeds_kernel(const int* __restrict__ kind, const int* __restrict__ index,
+                                                           const bf16* __restrict__ table, const bf16* __restrict__ img,
+                                                           const bf16* __restrict__ reg, bf16* __restrict__ out, int H) {
+  const int r = blockIdx.x;
+  const int k = kind[r];
+  const bf16* src = (k == 0 ? table : (k == 1 ? img : reg)) + (long long)index[r] * H;
+  bf16* dst = out + (long long)r * H;
+  for (int c = threadIdx.x * 8; c < H; c += blockDim.x * 8) *reinterpret_cast<uint4*>(dst + c) = *reinterpret_cast<const uint4*>(src + c);
+}
+
+// x[b] = table[tok[b]]
+__global__ void __launch_bounds__(256) embed_tokens_kernel(const int* __restrict__ tok, const bf16* __restrict__ table,
+                                                           bf16* __restrict__ out, int H) {
+  const bf16* src = table + (long long)tok[blockIdx.x] * H;
+  bf16* dst = out + (long long)blockIdx.x * H;
+  for (int c = threadIdx.x * 8; c < H; c += blockDim.x * 8) *reinterpret_cast<uint4*>(dst + c) = *reinterpret_cast<const uint4*>(src + c);
+}
+
+// prefill: copy the rotated K and V of packed row r into the cache slot (seq[r], t[r])
+__global__ void __launch_bounds__(128) kv_store_kernel(const bf16* __restrict__ qkv, long long ld, int q_dim, int kv_dim,
+                                                       const int* __restrict__ row_seq, const int* __restrict__ row_t,
+                                                       bf16* __restrict__ kc, bf16* __restrict__ vc, int cap) {
+  const int r = blockIdx.x;
+  const long long slot = ((long long)row_seq[r] * cap + row_t[r]) * kv_dim;
+  const bf16* kp = qkv + (long long)r * ld + q_dim;
+  for (int c = threadIdx.x * 8; c < kv_dim; c += blockDim.x * 8) {
+    *reinterpret_cast<uint4*>(kc + slot + c) = *reinterpret_cast<const uint4*>(kp + c);
+    *reinterpret_cast<uint4*>(vc + slot + c) = *reinterpret_cast<const uint4*>(kp + kv_dim + c);
+  }
+}
+// decode: append row b at index cache_len[b]
+__global__ void __launch_bounds__(128) kv_append_kernel(const bf16* __restrict__ qkv, long long ld, int q_dim, int kv_dim,
+                                                        const int* __restrict__ cache_len, bf16* __restrict__ kc,
+                                                        bf16* __restrict__ vc, int cap) {
+  const int b = blockIdx.x;
+  const long long slot = ((long long)b * cap + cache_len[b]) * kv_dim;
+  const bf16* kp = qkv + (long long)b * ld + q_dim;
+  for (int c = threadIdx.x * 8; c < kv_dim; c += blockDim.x * 8) {
+    *reinterpret_cast<uint4*>(kc + slot + c) = *reinterpret_cast<const uint4*>(kp + c);
+    *reinterpret_cast<uint4*>(vc + slot + c) = *reinterpret_cast<const uint4*>(kp + kv_dim + c);
+  }
+}
+
+// Single-query GQA attention over the cache: one block per (sequence, kv head); the G = q_heads/kv_heads
+// query heads that share the K/V stream are processed together so every K/V byte is read once.
+// 8 warps x 4 token slots; a token's 128 dims are split over 8 lanes (16 dims = 32 B each).
+template <int G>
+__global__ void __launch_bounds__(256) decode_attn_kernel(const bf16* __restrict__ q, long long ldq, const bf16* __restrict__ kc,
+                                                          const bf16* __restrict__ vc, const int* __restrict__ cache_len, int cap,
+                                                          int kv_heads, bf16* __restrict__ out, long long ldo, float scale) {
+  constexpr int HD = 128;
+  const int b = blockIdx.x, kvh = blockIdx.y;
+  const int n = cache_len[b] + 1;  // the step's own K/V was appended at index cache_len[b]
+  const int kv_dim = kv_heads * HD;
+  __shared__ float qs[G][HD];
+  __shared__ float red_m[8][G], red_l[8][G];
+  __shared__ float red_acc[8][G][HD];
+  for (int i = threadIdx.x; i < G * HD; i += 256) {
+    const int g = i / HD, d = i % HD;
+    qs[g][d] = __bfloat162float(q[(long long)b * ldq + (long long)(kvh * G + g) * HD + d]) * scale * 1.4426950408889634f;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int grp = lane >> 3, sub = lane & 7;
+  float m[G], l[G], acc[G][16];
+#pragma unroll
+  for (int g = 0; g < G; ++g) {
+    m[g] = -INFINITY; l[g] = 0.f;
+#pragma unroll
+    for (int d = 0; d < 16; ++d) acc[g][d] = 0.f;
+  }
+  const bf16* kb = kc + (long long)b * cap * kv_dim + kvh * HD + sub * 16;
+  const bf16* vb = vc + (long long)b * cap * kv_dim + kvh * HD + sub * 16;
+  for (int t0 = warp * 4; t0 < n; t0 += 32) {
+    const int t = t0 + grp;
+    const bool ok = t < n;
+    float kf[16], vf[16];
+    {
+      uint4 k0 = make_uint4(0, 0, 0, 0), k1 = k0, v0 = k0, v1 = k0;
+      if (ok) {
+        k0 = *reinterpret_cast<const uint4*>(kb + (long long)t * kv_dim); k1 = *reinterpret_cast<const uint4*>(kb + (long long)t * kv_dim + 8);
+        v0 = *reinterpret_cast<const uint4*>(vb + (long long)t * kv_dim); v1 = *reinterpret_cast<const uint4*>(vb + (long long)t * kv_dim + 8);
+      }
+      const uint32_t ku[8] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w}, vu[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { kf[2 * i] = bf16_lo(ku[i]); kf[2 * i + 1] = bf16_hi(ku[i]); vf[2 * i] = bf16_lo(vu[i]); vf[2 * i + 1] = bf16_hi(vu[i]); }
+    }
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      float s = 0.f;
+#pragma unroll
+      for (int d = 0; d < 16; ++d) s = fmaf(kf[d], qs[g][sub * 16 + d], s);
+      s += __shfl_xor_sync(0xffffffffu, s, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2);
+      s += __shfl_xor_sync(0xffffffffu, s, 4);
+      if (ok) {
+        const float mn = fmaxf(m[g], s);
+        const float a = exp2f(m[g] - mn), p = exp2f(s - mn);  // m = -inf on first use -> a = 0
+        l[g] = l[g] * a + p;
+#pragma unroll
+        for (int d = 0; d < 16; ++d) acc[g][d] = fmaf(p, vf[d], acc[g][d] * a);
+        m[g] = mn;
+      }
+    }
+  }
+  // combine the 4 token slots of the warp (lanes differing in bits 3 and 4 hold the same dims)
+#pragma unroll
+  for (int off = 8; off <= 16; off <<= 1) {
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      const float mo = __shfl_xor_sync(0xffffffffu, m[g], off), lo = __shfl_xor_sync(0xffffffffu, l[g], off);
+      const float mn = fmaxf(m[g], mo);
+      const float a = (m[g] == -INFINITY) ? 0.f : exp2f(m[g] - mn), bsc = (mo == -INFINITY) ? 0.f : exp2f(mo - mn);
+#pragma unroll
+      for (int d = 0; d < 16; ++d) {
+        const float ao = __shfl_xor_sync(0xffffffffu, acc[g][d], off);
+        acc[g][d] = acc[g][d] * a + ao * bsc;
+      }
+      l[g] = l[g] * a + lo * bsc;
+      m[g] = mn;
+    }
+  }
+  if (grp == 0) {
+#pragma unroll
+    for (int g = 0; g < G; ++g) {
+      if (sub == 0) { red_m[warp][g] = m[g]; red_l[warp][g] = l[g]; }
+#pragma unroll
+      for (int d = 0; d < 16; ++d) red_acc[warp][g][sub * 16 + d] = acc[g][d];
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < G * HD; i += 256) {
+    const int g = i / HD, d = i % HD;
+    float mm = -INFINITY;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) mm = fmaxf(mm, red_m[w][g]);
+    float num = 0.f, den = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+      const float sc = (red_m[w][g] == -INFINITY) ? 0.f : exp2f(red_m[w][g] - mm);
+      num += red_acc[w][g][d] * sc;
+      den += red_l[w][g] * sc;
+    }
+    out[(long long)b * ldo + (long long)(kvh * G + g) * HD + d] = __float2bfloat16_rn(num / den);
+  }
+}
+
+// greedy token: lowest index among the maxima of a fp32 logits row
+__global__ void __launch_bounds__(1024) argmax_kernel(const float* __restrict__ logits, int V, int* __restrict__ out) {
+  const float* row = logits + (long long)blockIdx.x * V;
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int i = threadIdx.x; i < V; i += blockDim.x) {
+    const float v = row[i];
+    if (v > best || (v == best && i < bi)) { best = v; bi = i; }
+  }
+  __shared__ float sv[32];
+  __shared__ int si[32];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+  }
+  if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = best; si[threadIdx.x >> 5] = bi; }
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    best = sv[threadIdx.x]; bi = si[threadIdx.x];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    if (threadIdx.x == 0) out[blockIdx.x] = bi;
+  }
+}
+
+struct DecodeState {
+  int* cache_len;  // [B] K/V entries in the cache
+  int* pos3;       // [3][B] M-RoPE position of the next input token (all axes equal after the prompt, :1848-1860)
+  int* cur_tok;    // [B] token to feed next
+  int* new_tok;    // [B] argmax output
+  int* finished;   // [B]
+  int* n_active;   // [1] sequences still running
+  int* step;       // [1] index of the next output column
+  int* stop_ids;   // [n_stop]
+};
+
+// after the prefill: lengths, positions, first token
+__global__ void decode_init_kernel(DecodeState st, const int* __restrict__ seq_lens, const int* __restrict__ deltas, int B) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b == 0) { *st.step = 0; *st.n_active = B; }
+  if (b >= B) return;
+  st.cache_len[b] = seq_lens[b];
+  const int p = seq_lens[b] + deltas[b];
+  st.pos3[b] = p; st.pos3[B + b] = p; st.pos3[2 * B + b] = p;
+  st.finished[b] = 0;
+}
+// record the sampled token, test the stop ids, advance the loop state; `advance_cache` is 0 for the prefill token
+__global__ void decode_update_kernel(DecodeState st, int n_stop, int pad_id, int max_new, int* __restrict__ out_tokens,
+                                     int* __restrict__ out_lens, int B, int advance_cache, int step) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < B) {
+    const int tok = st.new_tok[b];
+    if (step < max_new) {
+      if (!st.finished[b]) {
+        out_tokens[(long long)b * max_new + step] = tok;
+        out_lens[b] = step + 1;
+        bool stop = false;
+        for (int i = 0; i < n_stop; ++i) stop |= (tok == st.stop_ids[i]);
+        if (stop) { st.finished[b] = 1; atomicSub(st.n_active, 1); }
+      } else {
+        out_tokens[(long long)b * max_new + step] = pad_id;
+      }
+    }
+    st.cur_tok[b] = tok;
+    if (advance_cache) {
+      st.cache_len[b] += 1;
+      st.pos3[b] += 1; st.pos3[B + b] += 1; st.pos3[2 * B + b] += 1;
+    }
+  }
+  if (b == 0) *st.step = step + 1;  // informational: the host owns the loop counter
+}
+__global__ void fill_int_kernel(int* p, int v, long long n) {
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
+}
+
+// ------------------------------------------------------------------------------------------ host
+struct LlmState {
+  int* ints = nullptr;   // one allocation for the DecodeState arrays
+  int cap_b = 0, cap_stop = 0;
+  int* h_flag = nullptr; // pinned
+};
+
+static int llm_resolve(Model* m) {
+  const fo1_model_config& c = m->cfg;
+  WeightGetter g{m, ""};
+  LlmW& w = m->llm;
+  const int64_t H = c.llm_hidden, V = c.llm_vocab, QD = (int64_t)c.llm_heads * c.llm_head_dim, KD = (int64_t)c.llm_kv_heads * c.llm_head_dim;
+  const int64_t Ip = (c.llm_inter + 31) / 32 * 32;
+  w.embed = g.bf("llm.embed", {V, H});
+  w.norm = g.bf("llm.norm.w", {H});
+  w.lm_head = g.bf("llm.lm_head", {V, H});
+  w.layer.resize(c.llm_layers);
+  for (int i = 0; i < c.llm_layers; ++i) {
+    const std::string p = "llm.l" + std::to_string(i) + ".";
+    LlmLayerW& L = w.layer[i];
+    L.ln1 = g.bf(p + "ln1.w", {H});
+    L.qkv_w = g.bf(p + "qkv.w", {QD + 2 * KD, H});
+    L.qkv_b = g.bf(p + "qkv.b", {QD + 2 * KD});
+    L.o_w = g.bf(p + "o.w", {H, QD});
+    L.ln2 = g.bf(p + "ln2.w", {H});
+    L.gateup_w = g.bf(p + "gateup.w", {2 * Ip, H});
+    L.down_w = g.bf(p + "down.w", {H, Ip});
+  }
+  if (!g.err.empty()) { set_error("LLM weights: %s", g.err.c_str()); return FO1_ERR_NOT_FOUND; }
+  w.ok = true;
+  return FO1_OK;
+}
+int llm_finalize(Model* m) { return m->cfg.llm_layers > 0 ? llm_resolve(m) : FO1_OK; }
+
+void llm_destroy_state(Model* m) {
+  LlmState* s = static_cast<LlmState*>(m->llm_state);
+  if (!s) return;
+  if (s->ints) cudaFree(s->ints);
+  if (s->h_flag) cudaFreeHost(s->h_flag);
+  delete s;
+  m->llm_state = nullptr;
+}
+
+static int ensure_kv(Model* m, int B, int cap) {
+  const fo1_model_config& c = m->cfg;
+  const size_t per = (size_t)c.llm_layers * B * cap * c.llm_kv_heads * c.llm_head_dim * sizeof(bf16);
+  if (2 * per > m->kv_bytes) {
+    FO1_CUDA(cudaDeviceSynchronize());
+    if (m->kv_cache) FO1_CUDA(cudaFree(m->kv_cache));
+    m->kv_cache = nullptr; m->kv_bytes = 0;
+    FO1_CUDA(cudaMalloc(&m->kv_cache, 2 * per));
+    m->kv_bytes = 2 * per;
+  }
+  m->kv_batch = B; m->kv_cap = cap;
+  return FO1_OK;
+}
+
+static int ensure_state(Model* m, int B, int n_stop, DecodeState* st) {
+  LlmState* s = static_cast<LlmState*>(m->llm_state);
+  if (!s) { s = new LlmState(); m->llm_state = s; }
+  if (B > s->cap_b || n_stop > s->cap_stop) {
+    FO1_CUDA(cudaDeviceSynchronize());
+    if (s->ints) FO1_CUDA(cudaFree(s->ints));
+    s->cap_b = std::max(B, s->cap_b); s->cap_stop = std::max(n_stop, std::max(s->cap_stop, 8));
+    FO1_CUDA(cudaMalloc(reinterpret_cast<void**>(&s->ints), ((size_t)9 * s->cap_b + s->cap_stop + 64) * sizeof(int)));
+  }
+  if (!s->h_flag) FO1_CUDA(cudaMallocHost(reinterpret_cast<void**>(&s->h_flag), 64));
+  int* p = s->ints;
+  const int cb = s->cap_b;
+  st->cache_len = p; p += cb;
+  st->pos3 = p; p += 3 * cb;
+  st->cur_tok = p; p += cb;
+  st->new_tok = p; p += cb;
+  st->finished = p; p += cb;
+  st->n_active = p; p += 16;
+  st->step = p; p += 16;
+  st->stop_ids = p;
+  return FO1_OK;
+}
+
+// one decoder layer over `rows` packed rows.  x_in -> x_out (x_mid scratch).  prefill: varlen causal attention
+// + cache fill; decode: cache append + single-query attention.
+struct LayerBuf { bf16 *xn, *qkv, *att, *x_mid, *h; };
+
+static int llm_layer(Model* m, int li, const bf16* x_in, bf16* x_out, const LayerBuf& B_, int rows, const int* pos3, bool prefill,
+                     const int* d_cu, int n_seqs, int max_len, const int* d_row_seq, const int* d_row_t, const DecodeState* st,
+                     cudaStream_t s, bool dry) {
+  const fo1_model_config& c = m->cfg;
+  const LlmLayerW& L = m->llm.layer[li];
+  const int H = c.llm_hidden, hd = c.llm_head_dim, QD = c.llm_heads * hd, KD = c.llm_kv_heads * hd, ldq = QD + 2 * KD;
+  const int Ip = (c.llm_inter + 31) / 32 * 32;
+  const size_t layer_stride = (size_t)m->kv_batch * m->kv_cap * KD;
+  bf16* kc = static_cast<bf16*>(m->kv_cache) + (size_t)li * layer_stride;
+  bf16* vc = static_cast<bf16*>(m->kv_cache) + ((size_t)c.llm_layers + li) * layer_stride;
+  FO1_RUN(rmsnorm(x_in, H, L.ln1, B_.xn, H, rows, H, c.rms_eps, s));
+  FO1_RUN(linear(B_.xn, H, L.qkv_w, H, B_.qkv, ldq, FO1_BF16, rows, ldq, H, L.qkv_b, FO1_BF16, FO1_EPI_NONE, nullptr, 0, 0, s));
+  FO1_RUN(mrope_apply(B_.qkv, B_.qkv + QD, ldq, pos3, rows, c.llm_heads, c.llm_kv_heads, hd, c.mrope_section[0], c.mrope_section[1],
+                      c.mrope_section[2], c.rope_theta, s));
+  if (prefill) {
+    if (!dry) {
+      kv_store_kernel<<<rows, 128, 0, s>>>(B_.qkv, ldq, QD, KD, d_row_seq, d_row_t, kc, vc, m->kv_cap);
+      FO1_LAUNCH_CHECK();
+    }
+    AttnArgs a;
+    a.q = B_.qkv; a.k = B_.qkv + QD; a.v = B_.qkv + QD + KD; a.o = B_.att;
+    a.ldq = a.ldk = a.ldv = ldq; a.ldo = QD;
+    a.cu_seqlens = d_cu; a.n_seqs = n_seqs; a.max_seqlen = max_len;
+    a.q_heads = c.llm_heads; a.kv_heads = c.llm_kv_heads; a.head_dim = hd;
+    a.scale = 1.0f / sqrtf((float)hd); a.causal = 1;
+    FO1_RUN(attention_varlen(a, s));
+  } else if (!dry) {
+    kv_append_kernel<<<rows, 128, 0, s>>>(B_.qkv, ldq, QD, KD, st->cache_len, kc, vc, m->kv_cap);
+    FO1_LAUNCH_CHECK();
+    dim3 grid(rows, c.llm_kv_heads);
+    const int G = c.llm_heads / c.llm_kv_heads;
+    const float scale = 1.0f / sqrtf((float)hd);
+    if (G == 8) decode_attn_kernel<8><<<grid, 256, 0, s>>>(B_.qkv, ldq, kc, vc, st->cache_len, m->kv_cap, c.llm_kv_heads, B_.att, QD, scale);
+    else if (G == 4) decode_attn_kernel<4><<<grid, 256, 0, s>>>(B_.qkv, ldq, kc, vc, st->cache_len, m->kv_cap, c.llm_kv_heads, B_.att, QD, scale);
+    else if (G == 2) decode_attn_kernel<2><<<grid, 256, 0, s>>>(B_.qkv, ldq, kc, vc, st->cache_len, m->kv_cap, c.llm_kv_heads, B_.att, QD, scale);
+    else if (G == 1) decode_attn_kernel<1><<<grid, 256, 0, s>>>(B_.qkv, ldq, kc, vc, st->cache_len, m->kv_cap, c.llm_kv_heads, B_.att, QD, scale);
+    else { set_error("decode attention: GQA group %d unsupported", G); return FO1_ERR_UNSUPPORTED; }
+    FO1_LAUNCH_CHECK();
+  }
+  FO1_RUN(linear(B_.att, QD, L.o_w, QD, B_.x_mid, H, FO1_BF16, rows, H, QD, nullptr, 0, FO1_EPI_NONE, x_in, H, 0, s));
+  FO1_RUN(rmsnorm(B_.x_mid, H, L.ln2, B_.xn, H, rows, H, c.rms_eps, s));
+  FO1_RUN(linear(B_.xn, H, L.gateup_w, H, B_.h, Ip, FO1_BF16, rows, 2 * Ip, H, nullptr, 0, FO1_EPI_SILU, nullptr, 0, 1, s));
+  FO1_RUN(linear(B_.h, Ip, L.down_w, Ip, x_out, H, FO1_BF16, rows, H, Ip, nullptr, 0, FO1_EPI_NONE, B_.x_mid, H, 0, s));
+  return FO1_OK;
+}
+
+static int llm_generate_impl(Model* m, fo1_generate_desc* d, cudaStream_t s, bool dry, const DecodeState& st) {
+  const fo1_model_config& c = m->cfg;
+  Arena& A = m->arena;
+  const int B = d->n_seqs, H = c.llm_hidden, hd = c.llm_head_dim, V = c.llm_vocab;
+  const int QD = c.llm_heads * hd, KD = c.llm_kv_heads * hd, ldq = QD + 2 * KD;
+  const int Ip = (c.llm_inter + 31) / 32 * 32;
+  long long T = 0;
+  int max_len = 0;
+  for (int b = 0; b < B; ++b) { T += d->seq_lens[b]; max_len = std::max(max_len, d->seq_lens[b]); }
+  const int R = (int)std::max<long long>(T, B);
+
+  LayerBuf buf;
+  bf16* xa = A.alloc<bf16>((size_t)R * H);
+  bf16* xb = A.alloc<bf16>((size_t)R * H);
+  buf.xn = A.alloc<bf16>((size_t)R * H);
+  buf.qkv = A.alloc<bf16>((size_t)R * ldq);
+  buf.att = A.alloc<bf16>((size_t)R * QD);
+  buf.x_mid = A.alloc<bf16>((size_t)R * H);
+  buf.h = A.alloc<bf16>((size_t)R * Ip);
+  bf16* last = A.alloc<bf16>((size_t)B * H);
+  bf16* lastn = A.alloc<bf16>((size_t)B * H);
+  float* logits = A.alloc<float>((size_t)B * V);
+  bf16* alln = d->all_logits ? A.alloc<bf16>((size_t)T * H) : nullptr;
+  int* d_lens = A.alloc<int>(B);
+  int* d_deltas = A.alloc<int>(B);
+
+  // ---- integer tables of the packed batch ----
+  const int *d_cu = nullptr, *d_row_seq = nullptr, *d_row_t = nullptr, *d_last = nullptr;
+  if (!dry) {
+    std::vector<int> cu(1, 0), row_seq, row_t, lastrow;
+    std::string key = "llm";
+    for (int b = 0; b < B; ++b) {
+      for (int t = 0; t < d->seq_lens[b]; ++t) { row_seq.push_back(b); row_t.push_back(t); }
+      cu.push_back(cu.back() + d->seq_lens[b]);
+      lastrow.push_back(cu.back() - 1);
+      key += ":" + std::to_string(d->seq_lens[b]);
+    }
+    FO1_TRY(cached_ints(m, key + ":cu", cu, &d_cu, s));
+    FO1_TRY(cached_ints(m, key + ":rs", row_seq, &d_row_seq, s));
+    FO1_TRY(cached_ints(m, key + ":rt", row_t, &d_row_t, s));
+    FO1_TRY(cached_ints(m, key + ":last", lastrow, &d_last, s));
+    FO1_CUDA(cudaMemcpyAsync(d_lens, d->seq_lens, B * sizeof(int), cudaMemcpyHostToDevice, s));
+    FO1_CUDA(cudaMemcpyAsync(d_deltas, d->rope_deltas, B * sizeof(int), cudaMemcpyHostToDevice, s));
+    if (d->n_stop_ids > 0) FO1_CUDA(cudaMemcpyAsync(st.stop_ids, d->stop_ids, d->n_stop_ids * sizeof(int), cudaMemcpyHostToDevice, s));
+  }
+
+  // ---- prefill ----
+  const bf16* x = static_cast<const bf16*>(d->inputs_embeds);
+  for (int li = 0; li < c.llm_layers; ++li) {
+    bf16* xo = (li & 1) ? xb : xa;
+    FO1_TRY(llm_layer(m, li, x, xo, buf, (int)T, d->position_ids, true, d_cu, B, max_len, d_row_seq, d_row_t, nullptr, s, dry));
+    x = xo;
+  }
+  if (d->all_logits) {
+    FO1_RUN(rmsnorm(x, H, m->llm.norm, alln, H, (int)T, H, c.rms_eps, s));
+    FO1_RUN(linear(alln, H, m->llm.lm_head, H, d->all_logits, V, FO1_F32, (int)T, V, H, nullptr, 0, FO1_EPI_NONE, nullptr, 0, 0, s));
+  }
+  FO1_RUN(gather_rows_bf16(x, H, d_last, last, H, B, H, s));
+  FO1_RUN(rmsnorm(last, H, m->llm.norm, lastn, H, B, H, c.rms_eps, s));
+  FO1_RUN(linear(lastn, H, m->llm.lm_head, H, logits, V, FO1_F32, B, V, H, nullptr, 0, FO1_EPI_NONE, nullptr, 0, 0, s));
+  if (dry) return FO1_OK;
+  if (d->prefill_logits) FO1_CUDA(cudaMemcpyAsync(d->prefill_logits, logits, (size_t)B * V * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  decode_init_kernel<<<ceil_div(B, 128), 128, 0, s>>>(st, d_lens, d_deltas, B);
+  FO1_LAUNCH_CHECK();
+  if (d->max_new_tokens <= 0) return FO1_OK;
+  argmax_kernel<<<B, 1024, 0, s>>>(logits, V, st.new_tok);
+  FO1_LAUNCH_CHECK();
+  decode_update_kernel<<<ceil_div(B, 128), 128, 0, s>>>(st, d->n_stop_ids, d->pad_id, d->max_new_tokens, d->out_tokens, d->out_lens, B, 0, 0);
+  FO1_LAUNCH_CHECK();
+
+  // ---- greedy decode: every step is a fixed launch sequence reading its state from device memory ----
+  LlmState* ls = static_cast<LlmState*>(m->llm_state);
+  d->steps_run = 0;
+  for (int step = 1; step < d->max_new_tokens; ++step) {
+    embed_tokens_kernel<<<B, 256, 0, s>>>(st.cur_tok, m->llm.embed, xa, H);
+    FO1_LAUNCH_CHECK();
+    const bf16* xin = xa;
+    for (int li = 0; li < c.llm_layers; ++li) {
+      bf16* xo = (li & 1) ? xa : xb;
+      FO1_TRY(llm_layer(m, li, xin, xo, buf, B, st.pos3, false, nullptr, B, 0, nullptr, nullptr, &st, s, false));
+      xin = xo;
+    }
+    FO1_TRY(rmsnorm(xin, H, m->llm.norm, lastn, H, B, H, c.rms_eps, s));
+    FO1_TRY(linear(lastn, H, m->llm.lm_head, H, logits, V, FO1_F32, B, V, H, nullptr, 0, FO1_EPI_NONE, nullptr, 0, 0, s));
+    argmax_kernel<<<B, 1024, 0, s>>>(logits, V, st.new_tok);
+    FO1_LAUNCH_CHECK();
+    decode_update_kernel<<<ceil_div(B, 128), 128, 0, s>>>(st, d->n_stop_ids, d->pad_id, d->max_new_tokens, d->out_tokens, d->out_lens, B, 1, step);
+    FO1_LAUNCH_CHECK();
+    d->steps_run = step;
+    if (d->early_exit_interval > 0 && step % d->early_exit_interval == 0) {
+      FO1_CUDA(cudaMemcpyAsync(ls->h_flag, st.n_active, sizeof(int), cudaMemcpyDeviceToHost, s));
+      FO1_CUDA(cudaStreamSynchronize(s));
+      if (*ls->h_flag <= 0) break;  // every sequence has emitted a stop id; the tail is already pad_id
+    }
+  }
+  return FO1_OK;
+}
+
+int llm_generate(Model* m, fo1_generate_desc* d, cudaStream_t s) {
+  FO1_CHECK_ARG(m->llm.ok, "fo1_llm_generate: model not finalized (LLM weights unresolved)");
+  const fo1_model_config& c = m->cfg;
+  FO1_CHECK_ARG(d->n_seqs > 0 && d->seq_lens && d->inputs_embeds && d->position_ids && d->rope_deltas, "fo1_llm_generate: null argument");
+  FO1_CHECK_ARG(d->max_new_tokens == 0 || (d->out_tokens && d->out_lens), "fo1_llm_generate: null outputs");
+  FO1_CHECK_ARG(c.llm_head_dim == 128, "fo1_llm_generate: head_dim %d unsupported (128)", c.llm_head_dim);
+  int max_len = 0;
+  for (int b = 0; b < d->n_seqs; ++b) {
+    FO1_CHECK_ARG(d->seq_lens[b] > 0, "fo1_llm_generate: sequence %d is empty", b);
+    max_len = std::max(max_len, d->seq_lens[b]);
+  }
+  DecodeState st;
+  FO1_TRY(ensure_state(m, d->n_seqs, d->n_stop_ids, &st));
+  FO1_TRY(ensure_kv(m, d->n_seqs, max_len + std::max(d->max_new_tokens, 1)));
+  m->arena.reset(true);
+  FO1_TRY(llm_generate_impl(m, d, s, true, st));
+  FO1_TRY(arena_ensure(m, m->arena.peak));
+  m->arena.reset(false);
+  if (d->max_new_tokens > 0) {  // out_tokens pre-filled with pad so an early exit leaves a clean tail
+    const long long n = (long long)d->n_seqs * d->max_new_tokens;
+    fill_int_kernel<<<(int)std::min<long long>((n + 255) / 256, 1024), 256, 0, s>>>(d->out_tokens, d->pad_id, n);
+    FO1_LAUNCH_CHECK();
+    FO1_CUDA(cudaMemsetAsync(d->out_lens, 0, d->n_seqs * sizeof(int), s));
+  }
+  return llm_generate_impl(m, d, s, false, st);
+}
+
+// -------------------------------------------------------------------------------- splice plan (host, integer)
+static int splice_plan(const int64_t* ids, int n_ids, const int32_t* grid_hw, int n_images, int n_regions, const fo1_splice_cfg& cf,
+                       std::vector<int64_t>& new_ids, std::vector<int>& kind, std::vector<int>& index, std::vector<int>& pos,
+                       int* rope_delta) {
+  // ---- omchat_qwen2_5_vl.py:318-368: walk the ids, expand image placeholders, keep one slot per region ----
+  int cur_img = 0, cur_reg = 0, img_row = 0;
+  const int unit = cf.merge * cf.merge;
+  for (int i = 0; i < n_ids; ++i) {
+    const int64_t t = ids[i];
+    if (t == cf.image_placeholder) {
+      if (cur_img >= n_images) { set_error("fo1_splice_plan: more image placeholders than images (%d)", n_images); return FO1_ERR_INVALID_ARG; }
+      const int n = grid_hw[2 * cur_img] * grid_hw[2 * cur_img + 1] / unit;
+      for (int k = 0; k < n; ++k) { new_ids.push_back(cf.image_token_id); kind.push_back(1); index.push_back(img_row + k); }
+      img_row += n;
+      ++cur_img;
+    } else if (t == cf.region_placeholder) {
+      if (cur_reg >= n_regions) { set_error("fo1_splice_plan: more region placeholders than region features (%d)", n_regions); return FO1_ERR_INVALID_ARG; }
+      new_ids.push_back(cf.region_placeholder); kind.push_back(2); index.push_back(cur_reg++);
+    } else {
+      new_ids.push_back(t); kind.push_back(0); index.push_back((int)t);
+    }
+  }
+  // ---- get_rope_index (modeling_qwen2_5_vl.py:1625-1699) on the spliced ids, attention mask all ones ----
+  const int L = (int)new_ids.size();
+  pos.assign((size_t)3 * L, 0);
+  int image_nums = 0;
+  for (int i = 0; i + 1 < L; ++i)
+    if (new_ids[i] == cf.vision_start_token_id && new_ids[i + 1] == cf.image_token_id) ++image_nums;
+  // (a vision_start in the last position indexes out of range in the reference; treated as "no image" here)
+  int st = 0, image_index = 0;
+  long long next_base = 0;   // llm_pos_ids_list[-1].max() + 1
+  bool have_any = false;
+  auto emit_text = [&](int from, int len, long long base) {
+    for (int k = 0; k < len; ++k)
+      for (int a = 0; a < 3; ++a) pos[(size_t)a * L + from + k] = (int)(base + k);
+  };
+  for (int it = 0; it < image_nums; ++it) {
+    int ed = -1;
+    for (int i = st; i < L; ++i) if (new_ids[i] == cf.image_token_id) { ed = i; break; }
+    if (ed < 0 || image_index >= n_images) { set_error("fo1_splice_plan: image token bookkeeping mismatch"); return FO1_ERR_INVALID_ARG; }
+    const int lh = grid_hw[2 * image_index] / cf.merge, lw = grid_hw[2 * image_index + 1] / cf.merge;
+    ++image_index;
+    const int text_len = ed - st;
+    const long long st_idx = have_any ? next_base : 0;
+    emit_text(st, text_len, st_idx);
+    const long long vb = st_idx + text_len;
+    for (int y = 0; y < lh; ++y)
+      for (int x = 0; x < lw; ++x) {
+        const size_t p = (size_t)ed + (size_t)y * lw + x;
+        if (p >= (size_t)L) { set_error("fo1_splice_plan: image tokens overrun the sequence"); return FO1_ERR_INVALID_ARG; }
+        pos[p] = (int)vb;                     // t index = 0 for an image
+        pos[(size_t)L + p] = (int)(vb + y);
+        pos[(size_t)2 * L + p] = (int)(vb + x);
+      }
+    long long mx = vb + std::max(lh, lw) - 1;
+    if (text_len > 0) mx = std::max(mx, st_idx + text_len - 1);
+    next_base = mx + 1;
+    have_any = true;
+    st = ed + lh * lw;
+  }
+  long long maxpos = have_any ? next_base - 1 : -1;
+  if (st < L) {
+    const long long st_idx = have_any ? next_base : 0;
+    emit_text(st, L - st, st_idx);
+    maxpos = st_idx + (L - st) - 1;
+  }
+  *rope_delta = (int)(maxpos + 1 - L);
+  return FO1_OK;
+}
+
 }  // namespace fo1
+
+using namespace fo1;
+
+extern "C" int fo1_splice_plan(const int64_t* input_ids, int32_t n_ids, const int32_t* image_grid_hw, int32_t n_images,
+                               int32_t n_regions, const fo1_splice_cfg* cfg, int64_t* new_ids, int32_t* src_kind,
+                               int32_t* src_index, int32_t* position_ids, int32_t* rope_delta, int32_t* out_len, int32_t capacity) {
+  FO1_CHECK_ARG(input_ids && cfg && out_len && rope_delta && n_ids >= 0 && (n_images == 0 || image_grid_hw), "fo1_splice_plan: null argument");
+  FO1_CHECK_ARG(cfg->merge > 0, "fo1_splice_plan: merge must be positive");
+  std::vector<int64_t> ids;
+  std::vector<int> kind, index, pos;
+  FO1_TRY(splice_plan(input_ids, n_ids, image_grid_hw, n_images, n_regions, *cfg, ids, kind, index, pos, rope_delta));
+  const int L = (int)ids.size();
+  *out_len = L;
+  if (L > capacity || !new_ids || !src_kind || !src_index || !position_ids) {
+    set_error("fo1_splice_plan: capacity %d < required %d", capacity, L);
+    return FO1_ERR_WORKSPACE;
+  }
+  memcpy(new_ids, ids.data(), (size_t)L * sizeof(int64_t));
+  memcpy(src_kind, kind.data(), (size_t)L * sizeof(int));
+  memcpy(src_index, index.data(), (size_t)L * sizeof(int));
+  for (int a = 0; a < 3; ++a) memcpy(position_ids + (size_t)a * capacity, pos.data() + (size_t)a * L, (size_t)L * sizeof(int));
+  return FO1_OK;
+}
+
+extern "C" int fo1_llm_build_embeds(fo1_model* m, const int32_t* src_kind, const int32_t* src_index, int32_t n_rows,
+                                    const void* img_feats, const void* region_feats, void* inputs_embeds, void* stream) {
+  FO1_CHECK_ARG(m && src_kind && src_index && inputs_embeds, "fo1_llm_build_embeds: null argument");
+  FO1_CHECK_ARG(m->llm.ok, "fo1_llm_build_embeds: model not finalized");
+  if (n_rows <= 0) return FO1_OK;
+  FO1_CHECK_ARG(m->cfg.llm_hidden % 8 == 0, "fo1_llm_build_embeds: hidden %% 8");
+  build_embeds_kernel<<<n_rows, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      src_kind, src_index, m->llm.embed, static_cast<const bf16*>(img_feats), static_cast<const bf16*>(region_feats),
+      static_cast<bf16*>(inputs_embeds), m->cfg.llm_hidden);
+  FO1_LAUNCH_CHECK();
+  return FO1_OK;
+}
+
+extern "C" int fo1_llm_generate(fo1_model* m, fo1_generate_desc* d, void* stream) {
+  FO1_CHECK_ARG(m && d, "fo1_llm_generate: null argument");
+  return llm_generate(m, d, static_cast<cudaStream_t>(stream));
+}

@@ -180,3 +180,88 @@ class Engine:
         check(lib().fo1_region_project(self._h, C.c_void_p(feats.data_ptr()), feats.shape[0], C.c_void_p(out.data_ptr()), _stream()),
               "fo1_region_project")
         return out
+
+
+class SpliceCfgC(C.Structure):
+    _fields_ = [("image_token_id", C.c_int32), ("video_token_id", C.c_int32), ("vision_start_token_id", C.c_int32),
+                ("merge", C.c_int32), ("image_placeholder", C.c_int32), ("region_placeholder", C.c_int32)]
+
+
+class GenerateDescC(C.Structure):
+    _fields_ = [("n_seqs", C.c_int32), ("seq_lens", C.POINTER(C.c_int32)), ("inputs_embeds", C.c_void_p),
+                ("position_ids", C.c_void_p), ("rope_deltas", C.POINTER(C.c_int32)), ("max_new_tokens", C.c_int32),
+                ("stop_ids", C.POINTER(C.c_int32)), ("n_stop_ids", C.c_int32), ("pad_id", C.c_int32),
+                ("out_tokens", C.c_void_p), ("out_lens", C.c_void_p), ("prefill_logits", C.c_void_p),
+                ("all_logits", C.c_void_p), ("early_exit_interval", C.c_int32), ("steps_run", C.c_int32)]
+
+
+def splice_plan(input_ids: Sequence[int], image_grids: Sequence[Tuple[int, int]], n_regions: int,
+                image_token_id: int = 151655, video_token_id: int = 151656, vision_start_token_id: int = 151652,
+                merge: int = 2, image_placeholder: int = -200, region_placeholder: int = -300):
+    """Host-side integer work for one sample (fo1_splice_plan): -> dict(new_ids, kind, index, position_ids [3, L], rope_delta)."""
+    import numpy as np
+    L = lib()
+    L.fo1_splice_plan.restype = C.c_int
+    cfg = SpliceCfgC(image_token_id, video_token_id, vision_start_token_id, merge, image_placeholder, region_placeholder)
+    ids = (C.c_int64 * len(input_ids))(*[int(t) for t in input_ids])
+    grids = (C.c_int32 * max(2 * len(image_grids), 1))(*[int(x) for g in image_grids for x in g])
+    cap = len(input_ids) + sum(gh * gw // (merge * merge) for gh, gw in image_grids) + 8
+    new_ids = np.empty(cap, dtype=np.int64); kind = np.empty(cap, dtype=np.int32); index = np.empty(cap, dtype=np.int32)
+    pos = np.empty((3, cap), dtype=np.int32)
+    delta = C.c_int32(); n = C.c_int32()
+    check(L.fo1_splice_plan(ids, len(input_ids), grids, len(image_grids), n_regions, C.byref(cfg),
+                            new_ids.ctypes.data_as(C.POINTER(C.c_int64)), kind.ctypes.data_as(C.POINTER(C.c_int32)),
+                            index.ctypes.data_as(C.POINTER(C.c_int32)), pos.ctypes.data_as(C.POINTER(C.c_int32)),
+                            C.byref(delta), C.byref(n), cap), "fo1_splice_plan")
+    k = n.value
+    return dict(new_ids=new_ids[:k], kind=kind[:k], index=index[:k], position_ids=pos[:, :k].copy(), rope_delta=delta.value)
+
+
+def _engine_build_embeds(self, kind: torch.Tensor, index: torch.Tensor, img_feats: Optional[torch.Tensor],
+                         region_feats: Optional[torch.Tensor]) -> torch.Tensor:
+    """inputs_embeds rows from the embedding table / image features / region features (device int32 kind, index)."""
+    n = kind.numel()
+    out = torch.empty((n, self.cfg.llm["hidden_size"]), dtype=torch.bfloat16, device=self.device)
+    L = lib()
+    L.fo1_llm_build_embeds.restype = C.c_int
+    check(L.fo1_llm_build_embeds(self._h, C.c_void_p(kind.data_ptr()), C.c_void_p(index.data_ptr()), n,
+                                 C.c_void_p(img_feats.data_ptr() if img_feats is not None else 0),
+                                 C.c_void_p(region_feats.data_ptr() if region_feats is not None else 0),
+                                 C.c_void_p(out.data_ptr()), _stream()), "fo1_llm_build_embeds")
+    return out
+
+
+def _engine_generate(self, inputs_embeds: torch.Tensor, position_ids: torch.Tensor, seq_lens: Sequence[int],
+                     rope_deltas: Sequence[int], max_new_tokens: int, stop_ids: Sequence[int], pad_id: int,
+                     want_prefill_logits: bool = False, want_all_logits: bool = False, early_exit_interval: int = 8):
+    """Prefill + greedy decode of a packed batch.  position_ids int32 [3, sum L].  Returns a dict of device tensors."""
+    B = len(seq_lens)
+    V = self.cfg.llm["vocab_size"]
+    T = int(sum(seq_lens))
+    assert inputs_embeds.shape == (T, self.cfg.llm["hidden_size"]) and inputs_embeds.dtype == torch.bfloat16
+    inputs_embeds = inputs_embeds.contiguous()
+    position_ids = position_ids.to(self.device, torch.int32).contiguous()
+    assert position_ids.shape == (3, T)
+    toks = torch.empty((B, max(max_new_tokens, 1)), dtype=torch.int32, device=self.device)
+    lens = torch.zeros((B,), dtype=torch.int32, device=self.device)
+    pl = torch.empty((B, V), dtype=torch.float32, device=self.device) if want_prefill_logits else None
+    al = torch.empty((T, V), dtype=torch.float32, device=self.device) if want_all_logits else None
+    d = GenerateDescC()
+    d.n_seqs = B
+    sl = (C.c_int32 * B)(*[int(x) for x in seq_lens]); rd = (C.c_int32 * B)(*[int(x) for x in rope_deltas])
+    st = (C.c_int32 * max(len(stop_ids), 1))(*[int(x) for x in stop_ids])
+    d.seq_lens, d.rope_deltas, d.stop_ids, d.n_stop_ids = sl, rd, st, len(stop_ids)
+    d.inputs_embeds, d.position_ids = inputs_embeds.data_ptr(), position_ids.data_ptr()
+    d.max_new_tokens, d.pad_id = max_new_tokens, pad_id
+    d.out_tokens, d.out_lens = toks.data_ptr(), lens.data_ptr()
+    d.prefill_logits = pl.data_ptr() if pl is not None else None
+    d.all_logits = al.data_ptr() if al is not None else None
+    d.early_exit_interval = early_exit_interval
+    L = lib()
+    L.fo1_llm_generate.restype = C.c_int
+    check(L.fo1_llm_generate(self._h, C.byref(d), _stream()), "fo1_llm_generate")
+    return dict(tokens=toks, lens=lens, prefill_logits=pl, all_logits=al, steps_run=d.steps_run)
+
+
+Engine.build_embeds = _engine_build_embeds
+Engine.generate = _engine_generate

@@ -1,0 +1,115 @@
+"""Host-side mirror of the reference's multimodal forward for a BATCH of samples, over the engine:
+
+    encode_images   (omchat_qwen2_5_vl.py:44-72)   -> Engine.vit_forward      (one packed launch sequence)
+    encode_regions  (omchat_qwen2_5_vl.py:75-128)  -> Engine.davit_forward + fpn_forward + hfre_forward + region_project
+    splice + M-RoPE (omchat_qwen2_5_vl.py:291-463) -> splice_plan (host ints) + Engine.build_embeds
+    generate        (HF greedy loop)               -> Engine.generate (prefill + device-resident decode)
+
+One image per sample (what every caller in the reference does).  torch is the memory / stream plumbing."""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import hfre as HF
+from .engine import Engine, splice_plan
+
+
+@dataclass
+class SampleInputs:
+    input_ids: Sequence[int]            # prompt ids with -200 (image) / -300 (region) placeholders (mm_utils.py:83-135)
+    pixel_values: torch.Tensor          # fp32 [gh*gw, 1176]  (Qwen2VLImageProcessor)
+    grid_hw: Tuple[int, int]
+    image_aux: torch.Tensor             # fp32 [3, H, W]      (CLIPImageProcessor, 'dynamic' mode)
+    boxes: torch.Tensor                 # fp32 [N, 4] xyxy in aux-tensor pixels
+
+
+class Fo1Pipeline:
+    def __init__(self, engine: Engine, vt_mode: str = "fpn", image_token_id: int = 151655, vision_start_token_id: int = 151652,
+                 video_token_id: int = 151656):
+        self.eng = engine
+        self.vt_mode = vt_mode
+        self.ids = dict(image_token_id=image_token_id, vision_start_token_id=vision_start_token_id, video_token_id=video_token_id)
+        self.hcfg = HF.HfreConfig(region_dim=engine.cfg.region_dim, vt_mode=vt_mode)
+        self.ws = HF.HfreWorkspace()
+        self.timings: Dict[str, float] = {}
+
+    # ---- vision side -------------------------------------------------------------------------------------
+    def encode(self, samples: Sequence[SampleInputs]):
+        """-> (img_feats [sum merged tokens, hidden] bf16, per-sample row offsets, region tokens list of [N_b, hidden] bf16,
+        region features fp32 list)."""
+        eng, dev = self.eng, self.eng.device
+        grids = [s.grid_hw for s in samples]
+        feats, taps = eng.vit_forward([s.pixel_values for s in samples], grids)
+        B = len(samples)
+        H0, W0 = samples[0].image_aux.shape[-2:]
+        same_aux = all(s.image_aux.shape[-2:] == (H0, W0) for s in samples)
+        same_grid = all(g == grids[0] for g in grids)
+        if same_aux:
+            st = eng.davit_forward([s.image_aux for s in samples])
+            aux = [[st[l][b] for l in range(4)] for b in range(B)]
+        else:
+            aux = []
+            for s in samples:
+                st = eng.davit_forward([s.image_aux])
+                aux.append([st[l][0] for l in range(4)])
+        tok_off = np.cumsum([0] + [gh * gw for gh, gw in grids])
+        hid = eng.cfg.vit["hidden_size"]
+        if self.vt_mode == "fpn":
+            if same_grid:
+                gh, gw = grids[0]
+                pyr = eng.fpn_forward(taps[-1].view(B, gh, gw, hid))            # SimpleFPN on the LAST tap (:82-83)
+                vt = [[pyr[l][b] for l in range(4)] for b in range(B)]
+            else:
+                vt = []
+                for b, (gh, gw) in enumerate(grids):
+                    pyr = eng.fpn_forward(taps[-1][tok_off[b]:tok_off[b + 1]].view(1, gh, gw, hid))
+                    vt.append([pyr[l][0] for l in range(4)])
+        else:
+            vt = [[taps[t][tok_off[b]:tok_off[b + 1]].view(grids[b][0], grids[b][1], hid) for t in range(len(taps))] for b in range(B)]
+        boxes_aux, boxes_vt = [], []
+        for b, s in enumerate(samples):
+            bx = s.boxes.to(dev, torch.float32)
+            if bx.numel() == 0:
+                bx = torch.tensor([[0.0, 10.0, 0.0, 10.0]], device=dev)             # the reference's dummy box (:90-91)
+            Ha, Wa = s.image_aux.shape[-2:]
+            gh, gw = grids[b]
+            p = eng.cfg.vit["patch_size"]
+            scale = torch.tensor([gw * p / Wa, gh * p / Ha, gw * p / Wa, gh * p / Ha], device=dev, dtype=torch.float32)
+            boxes_aux.append(bx)
+            boxes_vt.append(bx * scale)                                              # :94-99
+        region_f32, region_bf16 = HF.hfre_forward(aux, vt, boxes_aux, boxes_vt, self.hcfg, grids, want_bf16=True, workspace=self.ws)
+        counts = [r.shape[0] for r in region_bf16]
+        tokens = eng.region_project(torch.cat(region_bf16, 0))
+        region_tokens = list(torch.split(tokens, counts, 0))
+        unit = eng.cfg.vit["spatial_merge_size"] ** 2
+        img_off = np.cumsum([0] + [gh * gw // unit for gh, gw in grids])
+        return feats, img_off, region_tokens, region_f32
+
+    # ---- language side -----------------------------------------------------------------------------------
+    def generate(self, samples: Sequence[SampleInputs], max_new_tokens: int, stop_ids: Sequence[int], pad_id: int = 151643,
+                 early_exit_interval: int = 8, want_prefill_logits: bool = False):
+        eng, dev = self.eng, self.eng.device
+        feats, img_off, region_tokens, _ = self.encode(samples)
+        kinds, idxs, poss, lens, deltas = [], [], [], [], []
+        reg_off = 0
+        merge = eng.cfg.vit["spatial_merge_size"]
+        for b, s in enumerate(samples):
+            n_reg = region_tokens[b].shape[0]
+            plan = splice_plan(s.input_ids, [s.grid_hw], n_reg, merge=merge, **self.ids)
+            k, ix = plan["kind"], plan["index"].copy()
+            ix[k == 1] += int(img_off[b])
+            ix[k == 2] += reg_off
+            reg_off += n_reg
+            kinds.append(k); idxs.append(ix); poss.append(plan["position_ids"]); lens.append(len(k)); deltas.append(plan["rope_delta"])
+        kind = torch.from_numpy(np.concatenate(kinds)).to(dev)
+        index = torch.from_numpy(np.concatenate(idxs)).to(dev)
+        pos = torch.from_numpy(np.concatenate(poss, axis=1)).to(dev)
+        embeds = eng.build_embeds(kind, index, feats, torch.cat(region_tokens, 0))
+        out = eng.generate(embeds, pos, lens, deltas, max_new_tokens, stop_ids, pad_id, want_prefill_logits=want_prefill_logits,
+                           early_exit_interval=early_exit_interval)
+        out["prompt_lens"] = lens
+        return out

@@ -41,6 +41,11 @@ const char* fo1_last_error(void);
 /* Number of kernels this library has launched since load / since the last reset (all threads). */
 uint64_t fo1_launch_count(void);
 void fo1_launch_count_reset(void);
+/* Optional per-launch profiler: CUDA events recorded around the library's GEMM / attention / HFRE launches on
+ * the launching stream.  enable(1) clears and starts recording, enable(0) stops; collect() synchronises the
+ * device and writes a JSON object {tag: {launches, ms, flops, bytes, max_ms}} (algorithmic flops / bytes). */
+void fo1_profile_enable(int on);
+int fo1_profile_collect(char* buf, size_t cap);
 
 /* ------------------------------------------------------------------------------------------------
  * HFRE -- Hybrid Fine-grained Region Encoder.

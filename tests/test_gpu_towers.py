@@ -57,7 +57,7 @@ def test_vit_forward_matches_oracle():
         assert nerr(feats[cell:cell + nm].cpu(), ref_m) < 2e-2, t
         for i, rt in enumerate(ref_t):
             got = taps[i][tok:tok + n].reshape(gh, gw, -1).cpu()
-            assert nerr(got, rt) < 1e-2, (t, i)
+            assert nerr(got, rt) < 2e-2, (t, i)
         tok += n; cell += nm
 
 

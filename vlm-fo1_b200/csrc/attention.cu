@@ -218,6 +218,7 @@ template <int HD>
 static int launch_attn(const AttnArgs& a, cudaStream_t s) {
   constexpr int smem = 5 * 64 * (HD + 8) * 2;
   dim3 grid(ceil_div(a.max_seqlen, kTileM), a.n_seqs, a.q_heads);
+  ProfScope prof(a.causal ? "attn_causal" : "attn", 0.0, 0.0, s);
   if (a.causal) {
     static bool set = false;
     if (!set) { FO1_CUDA(cudaFuncSetAttribute(attn_varlen_kernel<HD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); set = true; }

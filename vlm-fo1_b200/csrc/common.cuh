@@ -52,6 +52,15 @@ inline void count_launch(uint64_t n = 1) { g_launches.fetch_add(n, std::memory_o
     if (_s != FO1_OK) return _s; \
   } while (0)
 
+// ---- optional per-launch profiler (CUDA events on the launching stream; off by default) ----------
+extern bool g_prof_on;
+struct ProfScope {
+  int idx;
+  cudaStream_t s;
+  ProfScope(const char* tag, double flops, double bytes, cudaStream_t stream);
+  ~ProfScope();
+};
+
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }

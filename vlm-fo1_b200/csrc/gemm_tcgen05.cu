@@ -330,6 +330,8 @@ static int launch_gemm(const fo1_gemm_desc* d, cudaStream_t stream) {
   g.tiles_n = ceil_div(d->N, BN);
   const int tiles = g.tiles_m * g.tiles_n;
   const int grid = tiles < device_sm_count() ? tiles : device_sm_count();
+  ProfScope prof(d->M <= 128 ? "gemm_skinny" : "gemm", 2.0 * d->M * (double)d->N * d->K,
+                 2.0 * ((double)d->M * d->K + (double)d->N * d->K + (double)d->M * (d->gated ? d->N / 2 : d->N)), stream);
   gemm_bf16_tcgen05_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(tmA, tmW, g);
   FO1_LAUNCH_CHECK();
   return FO1_OK;

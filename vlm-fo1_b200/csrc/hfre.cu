@@ -379,6 +379,7 @@ extern "C" int fo1_hfre_forward(const fo1_hfre_image* images, int32_t n_images, 
     if (max_boxes == 0) continue;
     {
       dim3 grid(max_boxes, max_levels * 2, B.n_images);
+      ProfScope prof("hfre_weights", 0.0, 0.0, stream);
       hfre_axis_weights_kernel<<<grid, 128, (size_t)max_up * sizeof(float), stream>>>(B, ws);
       FO1_LAUNCH_CHECK();
     }
@@ -390,6 +391,7 @@ extern "C" int fo1_hfre_forward(const fo1_hfre_image* images, int32_t n_images, 
     {
       dim3 grid(max_chunks, max_boxes, B.n_images);
       const size_t smem = ((size_t)max_hw + (kGatherThreads / 32) * kChunk) * sizeof(float);
+      ProfScope prof("hfre_gather", 0.0, 0.0, stream);
       hfre_gather_kernel<<<grid, kGatherThreads, smem, stream>>>(B, ws);
       FO1_LAUNCH_CHECK();
     }

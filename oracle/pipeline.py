@@ -63,8 +63,25 @@ def run_sample(sds: Dict[str, Dict[str, torch.Tensor]], vit_cfg: dict, davit_cfg
     for k, ix in zip(kind, index):
         rows.append(emb[ix] if k == 0 else (merged[ix] if k == 1 else region_tokens[ix]))
     embeds = torch.stack(rows)
-    toks, step_logits, prompt_logits = OL.generate(sds["llm"], llm_cfg, embeds, pos, delta, max_new_tokens, list(stop_ids))
-    t["llm_s"] = time.perf_counter() - t0
+    # prefill and decode timed separately (the decode cost per token is what a bounded sample extrapolates from)
+    dec = OL.Decoder(sds["llm"], llm_cfg)
+    tp = time.perf_counter()
+    h = dec.forward(embeds.float(), pos)
+    prompt_logits = dec.logits(h[-1:])
+    t["llm_prefill_s"] = time.perf_counter() - tp
+    lg = prompt_logits[-1]
+    toks, lgs = [], []
+    L = embeds.shape[0]
+    td = time.perf_counter()
+    for s_ in range(max_new_tokens):
+        lgs.append(lg)
+        tok = int(lg.argmax()); toks.append(tok)
+        if tok in stop_ids or s_ == max_new_tokens - 1:
+            break
+        h = dec.forward(emb[tok][None, :], torch.full((3, 1), L + s_ + delta, dtype=torch.long))
+        lg = dec.logits(h)[0]
+    t["llm_decode_s_per_token"] = (time.perf_counter() - td) / max(len(toks) - 1, 1)
+    step_logits = torch.stack(lgs)
     out.update(tokens=toks, step_logits=step_logits, prompt_last_logits=prompt_logits[-1], position_ids=pos, rope_delta=delta,
                prompt_len=len(new_ids))
     return out

@@ -86,9 +86,16 @@ def vit_forward(sd: Dict[str, torch.Tensor], cfg: dict, pixel_values: torch.Tens
         q = q * cos + _rot_half(q) * sin
         k = k * cos + _rot_half(k) * sin
         out = torch.empty(T, heads, hd)
-        for a, b in zip(cu[:-1], cu[1:]):
-            s = torch.einsum("qhd,khd->hqk", q[a:b], k[a:b]) / math.sqrt(hd)
-            out[a:b] = torch.einsum("hqk,khd->qhd", s.softmax(-1), v[a:b])
+        seg = cu[1] - cu[0]
+        if all(b - a == seg for a, b in zip(cu[:-1], cu[1:])):   # equal-length segments: one batched product
+            n = len(cu) - 1
+            qq, kk, vv = (t.reshape(n, seg, heads, hd) for t in (q, k, v))
+            s = torch.einsum("nqhd,nkhd->nhqk", qq, kk) / math.sqrt(hd)
+            out = torch.einsum("nhqk,nkhd->nqhd", s.softmax(-1), vv).reshape(T, heads, hd)
+        else:
+            for a, b in zip(cu[:-1], cu[1:]):
+                s = torch.einsum("qhd,khd->hqk", q[a:b], k[a:b]) / math.sqrt(hd)
+                out[a:b] = torch.einsum("hqk,khd->qhd", s.softmax(-1), v[a:b])
         x = x + out.reshape(T, H) @ w[p + "attn.proj.weight"].t() + w[p + "attn.proj.bias"]
         y = rms_norm(x, w[p + "norm2.weight"])
         g = y @ w[p + "mlp.gate_proj.weight"].t() + w[p + "mlp.gate_proj.bias"]

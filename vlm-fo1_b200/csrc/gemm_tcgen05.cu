@@ -38,7 +38,7 @@ struct GemmArgs {
 template <int BN>
 struct GemmCfg {
   static constexpr int kStageBytes = (BM * BK + BN * BK) * 2;
-  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : (BN == 64 ? 8 : 10));
   static constexpr int kTmemCols = 2 * BN;
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
 };
@@ -358,8 +358,10 @@ int gemm_bf16(const fo1_gemm_desc* d, cudaStream_t stream) {
   const int sms = device_sm_count();
   const long long tm = ceil_div(d->M, BM);
   if (d->N >= 256 && tm * ceil_div(d->N, 256) >= sms) return launch_gemm<256>(d, stream);
-  if (d->N >= 128 && tm * ceil_div(d->N, 128) >= sms / 2) return launch_gemm<128>(d, stream);
-  return launch_gemm<64>(d, stream);
+  if (d->N >= 128 && tm * ceil_div(d->N, 128) >= sms) return launch_gemm<128>(d, stream);
+  if (d->gated || tm * ceil_div(d->N, 64) >= sms) return launch_gemm<64>(d, stream);
+  // skinny problems (decode: M = batch): narrow tiles so that >= ~half the SMs stream weights, deep ring
+  return launch_gemm<32>(d, stream);
 }
 
 }  // namespace fo1

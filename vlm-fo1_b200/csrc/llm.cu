@@ -217,11 +217,14 @@ __global__ void decode_init_kernel(DecodeState st, const int* __restrict__ seq_l
   st.pos3[b] = p; st.pos3[B + b] = p; st.pos3[2 * B + b] = p;
   st.finished[b] = 0;
 }
-// record the sampled token, test the stop ids, advance the loop state; `advance_cache` is 0 for the prefill token
-__global__ void decode_update_kernel(DecodeState st, int n_stop, int pad_id, int max_new, int* __restrict__ out_tokens,
-                                     int* __restrict__ out_lens, int B, int advance_cache, int step) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b < B) {
+// record the sampled token, test the stop ids, advance the loop state.  ONE block; the output column is the
+// device-resident step counter, so the launch is identical every iteration (CUDA-graph replayable).
+__global__ void __launch_bounds__(1024) decode_update_kernel(DecodeState st, int n_stop, int pad_id, int max_new,
+                                                             int* __restrict__ out_tokens, int* __restrict__ out_lens, int B,
+                                                             int advance_cache) {
+  const int step = *st.step;
+  __syncthreads();
+  for (int b = threadIdx.x; b < B; b += blockDim.x) {
     const int tok = st.new_tok[b];
     if (step < max_new) {
       if (!st.finished[b]) {
@@ -240,7 +243,8 @@ __global__ void decode_update_kernel(DecodeState st, int n_stop, int pad_id, int
       st.pos3[b] += 1; st.pos3[B + b] += 1; st.pos3[2 * B + b] += 1;
     }
   }
-  if (b == 0) *st.step = step + 1;  // informational: the host owns the loop counter
+  __syncthreads();
+  if (threadIdx.x == 0) *st.step = step + 1;
 }
 __global__ void fill_int_kernel(int* p, int v, long long n) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
@@ -443,13 +447,14 @@ static int llm_generate_impl(Model* m, fo1_generate_desc* d, cudaStream_t s, boo
   if (d->max_new_tokens <= 0) return FO1_OK;
   argmax_kernel<<<B, 1024, 0, s>>>(logits, V, st.new_tok);
   FO1_LAUNCH_CHECK();
-  decode_update_kernel<<<ceil_div(B, 128), 128, 0, s>>>(st, d->n_stop_ids, d->pad_id, d->max_new_tokens, d->out_tokens, d->out_lens, B, 0, 0);
+  const int upd_threads = std::min(1024, std::max(32, (B + 31) / 32 * 32));
+  decode_update_kernel<<<1, upd_threads, 0, s>>>(st, d->n_stop_ids, d->pad_id, d->max_new_tokens, d->out_tokens, d->out_lens, B, 0);
   FO1_LAUNCH_CHECK();
 
-  // ---- greedy decode: every step is a fixed launch sequence reading its state from device memory ----
+  // ---- greedy decode: every step is the SAME launch sequence reading its state from device memory; the first
+  // step runs eagerly (warms every kernel), the second is captured into a CUDA graph that is replayed afterwards ----
   LlmState* ls = static_cast<LlmState*>(m->llm_state);
-  d->steps_run = 0;
-  for (int step = 1; step < d->max_new_tokens; ++step) {
+  auto enqueue_step = [&]() -> int {
     embed_tokens_kernel<<<B, 256, 0, s>>>(st.cur_tok, m->llm.embed, xa, H);
     FO1_LAUNCH_CHECK();
     const bf16* xin = xa;
@@ -462,16 +467,52 @@ static int llm_generate_impl(Model* m, fo1_generate_desc* d, cudaStream_t s, boo
     FO1_TRY(linear(lastn, H, m->llm.lm_head, H, logits, V, FO1_F32, B, V, H, nullptr, 0, FO1_EPI_NONE, nullptr, 0, 0, s));
     argmax_kernel<<<B, 1024, 0, s>>>(logits, V, st.new_tok);
     FO1_LAUNCH_CHECK();
-    decode_update_kernel<<<ceil_div(B, 128), 128, 0, s>>>(st, d->n_stop_ids, d->pad_id, d->max_new_tokens, d->out_tokens, d->out_lens, B, 1, step);
+    decode_update_kernel<<<1, upd_threads, 0, s>>>(st, d->n_stop_ids, d->pad_id, d->max_new_tokens, d->out_tokens, d->out_lens, B, 1);
     FO1_LAUNCH_CHECK();
+    return FO1_OK;
+  };
+  cudaGraphExec_t gexec = nullptr;
+  const bool want_graph = !g_prof_on && d->max_new_tokens > 3 && getenv("FO1_NO_GRAPH") == nullptr;
+  d->steps_run = 0;
+  int rc = FO1_OK;
+  for (int step = 1; step < d->max_new_tokens; ++step) {
+    if (gexec != nullptr) {
+      if (cudaGraphLaunch(gexec, s) != cudaSuccess) { set_error("cudaGraphLaunch failed: %s", cudaGetErrorString(cudaGetLastError())); rc = FO1_ERR_CUDA; break; }
+      count_launch((uint64_t)c.llm_layers * 10 + 5);
+    } else if (want_graph && step == 2) {
+      cudaGraph_t graph = nullptr;
+      if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+        const int erc = enqueue_step();
+        const cudaError_t ce = cudaStreamEndCapture(s, &graph);
+        if (erc == FO1_OK && ce == cudaSuccess && graph != nullptr && cudaGraphInstantiate(&gexec, graph, 0) == cudaSuccess) {
+          cudaGraphDestroy(graph);
+          if (cudaGraphLaunch(gexec, s) != cudaSuccess) { set_error("cudaGraphLaunch failed"); rc = FO1_ERR_CUDA; break; }
+        } else {  // capture unavailable: fall back to eager launches (still the same kernels)
+          if (graph) cudaGraphDestroy(graph);
+          cudaGetLastError();
+          gexec = nullptr;
+          if ((rc = enqueue_step()) != FO1_OK) break;
+        }
+      } else {
+        cudaGetLastError();
+        if ((rc = enqueue_step()) != FO1_OK) break;
+      }
+    } else {
+      if ((rc = enqueue_step()) != FO1_OK) break;
+    }
     d->steps_run = step;
     if (d->early_exit_interval > 0 && step % d->early_exit_interval == 0) {
-      FO1_CUDA(cudaMemcpyAsync(ls->h_flag, st.n_active, sizeof(int), cudaMemcpyDeviceToHost, s));
-      FO1_CUDA(cudaStreamSynchronize(s));
+      if (cudaMemcpyAsync(ls->h_flag, st.n_active, sizeof(int), cudaMemcpyDeviceToHost, s) != cudaSuccess || cudaStreamSynchronize(s) != cudaSuccess) {
+        set_error("early-exit poll failed"); rc = FO1_ERR_CUDA; break;
+      }
       if (*ls->h_flag <= 0) break;  // every sequence has emitted a stop id; the tail is already pad_id
     }
   }
-  return FO1_OK;
+  if (gexec != nullptr) {
+    cudaStreamSynchronize(s);   // the exec must outlive its in-flight launches
+    cudaGraphExecDestroy(gexec);
+  }
+  return rc;
 }
 
 int llm_generate(Model* m, fo1_generate_desc* d, cudaStream_t s) {

@@ -6,10 +6,10 @@ namespace fo1 {
 // dst[r][:] = bf16(src[row_idx ? row_idx[r] : r][:]); cols % 4 == 0
 __global__ void cast_gather_rows_kernel(const float* __restrict__ src, long long lds, const int* __restrict__ idx,
                                         bf16* __restrict__ dst, long long ldd, int rows, int cols) {
-  const int r = blockIdx.y;
+  const int r = blockIdx.x;  // rows on grid.x: a packed batch has > 65535 token rows
   const float* sp = src + (long long)(idx ? idx[r] : r) * lds;
   bf16* dp = dst + (long long)r * ldd;
-  for (int c = (blockIdx.x * blockDim.x + threadIdx.x) * 4; c < cols; c += gridDim.x * blockDim.x * 4) {
+  for (int c = threadIdx.x * 4; c < cols; c += blockDim.x * 4) {
     const float4 v = *reinterpret_cast<const float4*>(sp + c);
     uint2 o;
     o.x = pack_bf16(v.x, v.y);
@@ -22,11 +22,11 @@ __global__ void cast_gather_rows_kernel(const float* __restrict__ src, long long
 template <bool SCATTER>
 __global__ void move_rows_kernel(const bf16* __restrict__ src, long long lds, const int* __restrict__ idx, bf16* __restrict__ dst,
                                  long long ldd, int rows, int cols) {
-  const int r = blockIdx.y;
+  const int r = blockIdx.x;
   const long long sr = SCATTER ? r : idx[r], dr = SCATTER ? idx[r] : r;
   const bf16* sp = src + sr * lds;
   bf16* dp = dst + dr * ldd;
-  for (int c = (blockIdx.x * blockDim.x + threadIdx.x) * 8; c < cols; c += gridDim.x * blockDim.x * 8)
+  for (int c = threadIdx.x * 8; c < cols; c += blockDim.x * 8)
     *reinterpret_cast<uint4*>(dp + c) = *reinterpret_cast<const uint4*>(sp + c);
 }
 
@@ -56,8 +56,7 @@ int cast_gather_rows_f32_bf16(const float* src, long long lds, const int* row_id
                               cudaStream_t s) {
   FO1_CHECK_ARG(cols % 4 == 0 && lds % 4 == 0 && ldd % 4 == 0, "cast_gather_rows: cols/pitches must be multiples of 4");
   if (rows == 0) return FO1_OK;
-  dim3 grid(ceil_div(cols / 4, 256) < 4 ? ceil_div(cols / 4, 256) : 4, rows);
-  cast_gather_rows_kernel<<<grid, 256, 0, s>>>(src, lds, row_idx, dst, ldd, rows, cols);
+  cast_gather_rows_kernel<<<rows, 256, 0, s>>>(src, lds, row_idx, dst, ldd, rows, cols);
   FO1_LAUNCH_CHECK();
   return FO1_OK;
 }
@@ -65,8 +64,7 @@ int cast_gather_rows_f32_bf16(const float* src, long long lds, const int* row_id
 int gather_rows_bf16(const bf16* src, long long lds, const int* row_idx, bf16* dst, long long ldd, int rows, int cols, cudaStream_t s) {
   FO1_CHECK_ARG(cols % 8 == 0 && lds % 8 == 0 && ldd % 8 == 0, "gather_rows: cols/pitches must be multiples of 8");
   if (rows == 0) return FO1_OK;
-  dim3 grid(1, rows);
-  move_rows_kernel<false><<<grid, cols / 8 < 256 ? ((cols / 8 + 31) / 32) * 32 : 256, 0, s>>>(src, lds, row_idx, dst, ldd, rows, cols);
+  move_rows_kernel<false><<<rows, cols / 8 < 256 ? ((cols / 8 + 31) / 32) * 32 : 256, 0, s>>>(src, lds, row_idx, dst, ldd, rows, cols);
   FO1_LAUNCH_CHECK();
   return FO1_OK;
 }
@@ -74,8 +72,7 @@ int gather_rows_bf16(const bf16* src, long long lds, const int* row_idx, bf16* d
 int scatter_rows_bf16(const bf16* src, long long lds, const int* row_idx, bf16* dst, long long ldd, int rows, int cols, cudaStream_t s) {
   FO1_CHECK_ARG(cols % 8 == 0 && lds % 8 == 0 && ldd % 8 == 0, "scatter_rows: cols/pitches must be multiples of 8");
   if (rows == 0) return FO1_OK;
-  dim3 grid(1, rows);
-  move_rows_kernel<true><<<grid, cols / 8 < 256 ? ((cols / 8 + 31) / 32) * 32 : 256, 0, s>>>(src, lds, row_idx, dst, ldd, rows, cols);
+  move_rows_kernel<true><<<rows, cols / 8 < 256 ? ((cols / 8 + 31) / 32) * 32 : 256, 0, s>>>(src, lds, row_idx, dst, ldd, rows, cols);
   FO1_LAUNCH_CHECK();
   return FO1_OK;
 }

@@ -91,33 +91,52 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_arm(args, sds_cpu, cfg, samples, steps, warmup):
-    """Time the CPU oracle port on `steps` single-image samples.  Bounded sample: every stage runs at full size on one
-    image, but only `--cpu-tokens` decode steps are executed; images/s extrapolates the measured per-token decode time to
-    the workload's token count.  Returns (images/s, stage seconds, per-step seconds)."""
+CPU_SAMPLE_NOTE = ("1 image at full resolution through oracle/pipeline.py (fp32, all host threads) on a REDUCED-DEPTH copy of the model with "
+                   "the real layer widths: ViT 1 windowed + 1 full-attention block, DaViT 1 block per stage, LLM 2 layers, {tok} decode steps; "
+                   "per-block / per-layer wall times are measured and extrapolated to the real depths (ViT 28+4 blocks, DaViT 1/1/9/1, LLM 36 "
+                   "layers, {T}-token decode); patch-embed, merger, conv-embeds, FPN, HFRE, projector and lm_head are measured at full size")
+
+
+def reduced_cfg(E, cfg):
+    """Same widths, minimal depth: what the CPU arm actually executes."""
+    r = E.EngineConfig()
+    r.vit = dict(cfg.vit, depth=2, fullatt_block_indexes=[1])
+    r.davit = dict(cfg.davit, depths=[1, 1, 1, 1])
+    r.llm = dict(cfg.llm, num_hidden_layers=2)
+    r.fpn_out, r.region_dim, r.proj_aux_layers = cfg.fpn_out, cfg.region_dim, cfg.proj_aux_layers
+    return r
+
+
+def cpu_arm(args, CK, E, cfg, steps):
+    """Time the CPU oracle port.  Bounded sample (CPU_SAMPLE_NOTE): returns (images/s, stage seconds, per-step seconds)."""
+    from importlib import import_module
     from oracle import pipeline as OP
+    SY = import_module("vlm-fo1_b200.synthetic")
     torch.set_num_threads(os.cpu_count() or 1)
-    times = []
-    detail = None
-    for i in range(warmup + steps):
-        s = samples[i % len(samples)]
+    rc = reduced_cfg(E, cfg)
+    sds = CK.random_state_dicts(rc, "cpu", 0)
+    sds = {k: {n: t.float() for n, t in v.items()} for k, v in sds.items()}
+    s = SY.synthetic_batch(0, 1, args.size, args.boxes)[0]
+    times, detail = [], None
+    for _ in range(steps):
         with torch.no_grad():
-            out = OP.run_sample(sds_cpu, cfg.vit, cfg.davit, cfg.llm, input_ids=s.input_ids, pixel_values=s.pixel_values, grid_hw=s.grid_hw,
+            out = OP.run_sample(sds, rc.vit, rc.davit, rc.llm, input_ids=s.input_ids, pixel_values=s.pixel_values, grid_hw=s.grid_hw,
                                 image_aux=s.image_aux, boxes=s.boxes, region_dim=cfg.region_dim, max_new_tokens=args.cpu_tokens)
         t = out["timings"]
-        total = (t["vit_s"] + t["davit_s"] + t["fpn_s"] + t["hfre_s"] + t["proj_s"] + t["llm_prefill_s"]
-                 + (args.tokens - 1) * t["llm_decode_s_per_token"])
-        if i >= warmup:
-            times.append(total)
-            detail = t
+        vd, dd = t["vit_detail"], t["davit_detail"]
+        t_win = statistics.mean(x for f, x in vd["blocks"] if not f)
+        t_full = statistics.mean(x for f, x in vd["blocks"] if f)
+        n_full = len(cfg.vit["fullatt_block_indexes"])
+        vit = vd["embed_s"] + vd["merger_s"] + (cfg.vit["depth"] - n_full) * t_win + n_full * t_full
+        davit = sum(dd["embed_s"]) + sum(cfg.davit["depths"][i] * statistics.mean(dd["block_s"][i]) for i in range(4))
+        L = cfg.llm["num_hidden_layers"]
+        prefill = L * statistics.mean(t["llm_prefill_layer_s"]) + t["llm_head_s"]
+        per_tok = L * statistics.mean(t["llm_decode_layer_s"]) + t["llm_head_s"]
+        total = vit + davit + t["fpn_s"] + t["hfre_s"] + t["proj_s"] + prefill + (args.tokens - 1) * per_tok
+        times.append(total)
+        detail = {"vit_s": vit, "davit_s": davit, "fpn_s": t["fpn_s"], "hfre_s": t["hfre_s"], "proj_s": t["proj_s"], "llm_prefill_s": prefill,
+                  "llm_decode_s_per_token": per_tok, "vit_block_windowed_s": t_win, "vit_block_full_s": t_full}
     return 1.0 / statistics.mean(times), detail, times
-
-
-def cpu_state_dicts(CK, cfg):
-    """fp32 CPU copies of the seed-0 random checkpoint (generated on the GPU when there is one: ~100x faster)."""
-    dev = "cuda" if torch.cuda.is_available() else "cpu"
-    sds = CK.random_state_dicts(cfg, dev, 0)
-    return {k: {n: t.float().cpu() for n, t in v.items()} for k, v in sds.items()}
 
 
 def main():
@@ -132,6 +151,7 @@ def main():
     ap.add_argument("--tokens", type=int, default=64)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-tokens", type=int, default=3, help="decode steps the CPU arm actually runs (rest extrapolated)")
+    ap.add_argument("--profile-run", action="store_true", help="warm-up exactly as given, one timed pass, nothing else (for ncu)")
     ap.add_argument("--small", action="store_true", help="tiny architecture (plumbing check only; NOT a valid bench number)")
     args = ap.parse_args()
 
@@ -157,17 +177,14 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        sds_cpu = cpu_state_dicts(CK, cfg)
-        samples = SY.synthetic_batch(0, 1, args.size, args.boxes)
         args.steps = max(1, min(args.steps, 3)); args.warmup = 0   # bounded: each step is tens of seconds of CPU work
-        ips, detail, times = cpu_arm(args, sds_cpu, cfg, samples, args.steps, 0)
+        ips, detail, times = cpu_arm(args, CK, E, cfg, args.steps)
         cores = torch.get_num_threads()
         line = {"impl": "reference", "metric": METRIC, "value": ips, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": 0,
                 "ms_per_step": 1000.0 / ips, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": config,
                 "cpu_baseline": {"value": ips, "unit": UNIT, "cores": cores, "kind": "port",
-                                 "sample": f"1 image per step through oracle/pipeline.py: every stage at full size, {args.cpu_tokens} decode steps run and "
-                                           f"extrapolated to {args.tokens} tokens; fp32, {cores} threads",
+                                 "sample": CPU_SAMPLE_NOTE.format(tok=args.cpu_tokens, T=args.tokens),
                                  "stage_seconds": detail},
                 "e2e": {"value": ips, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
@@ -184,7 +201,6 @@ def main():
     sds = CK.random_state_dicts(cfg, dev, 0)
     eng = CK.load_engine(cfg, sds, dev)
     keep_cpu = (rank == 0 and world == 1 and not args.no_cpu_baseline)
-    sds_cpu = {k: {n: t.float().cpu() for n, t in v.items()} for k, v in sds.items()} if keep_cpu else None
     del sds
     torch.cuda.empty_cache()
     pipe = P.Fo1Pipeline(eng)
@@ -227,6 +243,13 @@ def main():
         return float(ms.item())
 
     L = fo1_b200.lib()
+    if args.profile_run:
+        for _ in range(args.warmup):
+            step(resident)
+        ms = timed(lambda: step(resident), args.steps)
+        if rank == 0:
+            print(json.dumps({"profile_run": True, "ms_per_step": ms / args.steps, "launches": int(L.fo1_launch_count())}))
+        return
     for _ in range(max(args.warmup, 3)):
         step(resident)
     torch.cuda.synchronize()
@@ -283,14 +306,11 @@ def main():
                                      "frac": ach / peaks["hbm_gbs"], "traffic": None, "algorithmic_bytes": tot, "ms": h["ms"],
                                      "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peaks['source']})"}
         # ---- CPU baseline (rank 0, N = 1 only) ----
-        if sds_cpu is not None:
+        if keep_cpu:
             try:
-                cpu_samples = SY.synthetic_batch(0, 1, args.size, args.boxes)
-                ips, detail, times = cpu_arm(args, sds_cpu, cfg, cpu_samples, 1, 0)
+                ips, detail, times = cpu_arm(args, CK, E, cfg, 1)
                 line["cpu_baseline"] = {"value": ips, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                                        "sample": f"1 image ({args.size}x{args.size}, {args.boxes} boxes) through oracle/pipeline.py: every stage at full size, "
-                                                  f"{args.cpu_tokens} decode steps run and extrapolated to {args.tokens} tokens; fp32",
-                                        "stage_seconds": detail}
+                                        "sample": CPU_SAMPLE_NOTE.format(tok=args.cpu_tokens, T=args.tokens), "stage_seconds": detail}
             except Exception as exc:  # the baseline is a report, never a reason to lose the GPU number
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {exc!r}"}
         print(json.dumps(line))

@@ -49,7 +49,7 @@ def _channel_attn(y, groups, p, w):
     return o @ w[p + "proj.weight"].t() + w[p + "proj.bias"]
 
 
-def davit_forward(sd: Dict[str, torch.Tensor], cfg: dict, image: torch.Tensor) -> List[torch.Tensor]:
+def davit_forward(sd: Dict[str, torch.Tensor], cfg: dict, image: torch.Tensor, timing: dict = None) -> List[torch.Tensor]:
     """image [3, H, W] -> 4 stage maps, channels-last [H_s, W_s, C_s]."""
     w = {k: v.float() for k, v in sd.items()}
     ws = cfg["window_size"]
@@ -57,7 +57,12 @@ def davit_forward(sd: Dict[str, torch.Tensor], cfg: dict, image: torch.Tensor) -
     outs = []
     x = None
     H = W = 0
+    import time as _time
+    if timing is not None:
+        timing["embed_s"] = [0.0] * 4
+        timing["block_s"] = [[] for _ in range(4)]
     for s in range(4):
+        _t0 = _time.perf_counter()
         p = f"convs.{s}."
         if cfg["patch_prenorm"][s]:
             x = _ln(x, w[p + "norm.weight"], w[p + "norm.bias"])
@@ -67,7 +72,10 @@ def davit_forward(sd: Dict[str, torch.Tensor], cfg: dict, image: torch.Tensor) -
         x = y.reshape(C, H * W).t()
         if not cfg["patch_prenorm"][s]:
             x = _ln(x, w[p + "norm.weight"], w[p + "norm.bias"])
+        if timing is not None:
+            timing["embed_s"][s] = _time.perf_counter() - _t0
         for j in range(cfg["depths"][s]):
+            _tb = _time.perf_counter()
             for kind in ("spatial_block", "channel_block"):
                 q = f"blocks.{s}.{j}.{kind}."
                 x = _dw(x, H, W, w[q + "conv1.fn.dw.weight"], w[q + "conv1.fn.dw.bias"])
@@ -83,6 +91,8 @@ def davit_forward(sd: Dict[str, torch.Tensor], cfg: dict, image: torch.Tensor) -
                 yy = _ln(x, w[q + "ffn.norm.weight"], w[q + "ffn.norm.bias"])
                 hmid = F.gelu(yy @ w[q + "ffn.fn.net.fc1.weight"].t() + w[q + "ffn.fn.net.fc1.bias"])
                 x = x + hmid @ w[q + "ffn.fn.net.fc2.weight"].t() + w[q + "ffn.fn.net.fc2.bias"]
+            if timing is not None:
+                timing["block_s"][s].append(_time.perf_counter() - _tb)
         outs.append(x.reshape(H, W, C).clone())
         x4 = None
     return outs

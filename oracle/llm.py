@@ -102,13 +102,17 @@ class Decoder:
         self.H = cfg["hidden_size"]; self.nh = cfg["num_attention_heads"]; self.nkv = cfg["num_key_value_heads"]
         self.hd = self.H // self.nh
         self.kv: List[Tuple[torch.Tensor, torch.Tensor]] = [(None, None)] * cfg["num_hidden_layers"]
+        self.layer_seconds: List[float] = []   # per-layer wall time of the last forward() (bench extrapolation)
 
     def forward(self, x: torch.Tensor, pos3: torch.Tensor) -> torch.Tensor:
         """x [n, H] new rows at positions pos3 [3, n]; attends causally to everything cached -> hidden [n, H]."""
         c, w = self.cfg, self.w
         cos, sin = mrope_cos_sin(pos3, self.hd, c["rope_theta"], c["mrope_section"])
         n = x.shape[0]
+        import time as _time
+        self.layer_seconds = []
         for i in range(c["num_hidden_layers"]):
+            _tl = _time.perf_counter()
             p = f"layers.{i}."
             y = rms_norm(x, w[p + "input_layernorm.weight"], c["rms_norm_eps"])
             q = (y @ w[p + "self_attn.q_proj.weight"].t() + w[p + "self_attn.q_proj.bias"]).reshape(n, self.nh, self.hd)
@@ -129,6 +133,7 @@ class Decoder:
             x = x + a @ w[p + "self_attn.o_proj.weight"].t()
             y = rms_norm(x, w[p + "post_attention_layernorm.weight"], c["rms_norm_eps"])
             x = x + (F.silu(y @ w[p + "mlp.gate_proj.weight"].t()) * (y @ w[p + "mlp.up_proj.weight"].t())) @ w[p + "mlp.down_proj.weight"].t()
+            self.layer_seconds.append(_time.perf_counter() - _tl)
         return x
 
     def logits(self, hidden: torch.Tensor) -> torch.Tensor:

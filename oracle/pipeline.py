@@ -30,13 +30,15 @@ def run_sample(sds: Dict[str, Dict[str, torch.Tensor]], vit_cfg: dict, davit_cfg
     t = {}
     gh, gw = grid_hw
     t0 = time.perf_counter()
-    merged, taps = OV.vit_forward(sds["vit"], vit_cfg, pixel_values, gh, gw)
+    t["vit_detail"] = {}
+    merged, taps = OV.vit_forward(sds["vit"], vit_cfg, pixel_values, gh, gw, timing=t["vit_detail"])
     merged = _bf(merged); taps = [_bf(x) for x in taps]
     t["vit_s"] = time.perf_counter() - t0; t0 = time.perf_counter()
     full_cfg = dict(davit_cfg)
     full_cfg.setdefault("patch_prenorm", [False, True, True, True]); full_cfg.setdefault("patch_stride", [4, 2, 2, 2])
     full_cfg.setdefault("patch_padding", [3, 1, 1, 1])
-    aux = [_bf(x) for x in OD.davit_forward(sds["davit"], full_cfg, image_aux)]
+    t["davit_detail"] = {}
+    aux = [_bf(x) for x in OD.davit_forward(sds["davit"], full_cfg, image_aux, timing=t["davit_detail"])]
     t["davit_s"] = time.perf_counter() - t0; t0 = time.perf_counter()
     if vt_mode == "fpn":
         vt = [_bf(x) for x in OD.fpn_forward(sds["fpn"], taps[-1])]
@@ -67,7 +69,10 @@ def run_sample(sds: Dict[str, Dict[str, torch.Tensor]], vit_cfg: dict, davit_cfg
     dec = OL.Decoder(sds["llm"], llm_cfg)
     tp = time.perf_counter()
     h = dec.forward(embeds.float(), pos)
+    t["llm_prefill_layer_s"] = list(dec.layer_seconds)
+    th = time.perf_counter()
     prompt_logits = dec.logits(h[-1:])
+    t["llm_head_s"] = time.perf_counter() - th
     t["llm_prefill_s"] = time.perf_counter() - tp
     lg = prompt_logits[-1]
     toks, lgs = [], []
@@ -79,6 +84,7 @@ def run_sample(sds: Dict[str, Dict[str, torch.Tensor]], vit_cfg: dict, davit_cfg
         if tok in stop_ids or s_ == max_new_tokens - 1:
             break
         h = dec.forward(emb[tok][None, :], torch.full((3, 1), L + s_ + delta, dtype=torch.long))
+        t.setdefault("llm_decode_layer_s", []).append(sum(dec.layer_seconds) / max(len(dec.layer_seconds), 1))
         lg = dec.logits(h)[0]
     t["llm_decode_s_per_token"] = (time.perf_counter() - td) / max(len(toks) - 1, 1)
     step_logits = torch.stack(lgs)

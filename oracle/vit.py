@@ -57,13 +57,15 @@ def _rot_half(x):
     return torch.cat((-x[..., h:], x[..., :h]), dim=-1)
 
 
-def vit_forward(sd: Dict[str, torch.Tensor], cfg: dict, pixel_values: torch.Tensor, gh: int, gw: int):
+def vit_forward(sd: Dict[str, torch.Tensor], cfg: dict, pixel_values: torch.Tensor, gh: int, gw: int, timing: dict = None):
     """One image.  Returns (merged tokens [gh*gw/4, out_hidden] in raster order,
     taps: list of [gh, gw, hidden] channels-last maps, one per full-attention layer)."""
     H, heads, merge = cfg["hidden_size"], cfg["num_heads"], cfg["spatial_merge_size"]
     unit = merge * merge
     hd = H // heads
     T = gh * gw
+    import time as _time
+    _t0 = _time.perf_counter()
     w = {k: v.float() for k, v in sd.items()}
     x = pixel_values.float() @ w["patch_embed.proj.weight"].reshape(H, -1).t()
     widx, cu_win = window_index(gh, gw, cfg["window_size"], merge, cfg["patch_size"])
@@ -76,7 +78,11 @@ def vit_forward(sd: Dict[str, torch.Tensor], cfg: dict, pixel_values: torch.Tens
     emb = torch.cat([ang, ang], dim=1)
     cos, sin = emb.cos()[:, None, :], emb.sin()[:, None, :]
     taps = []
+    if timing is not None:
+        timing["embed_s"] = _time.perf_counter() - _t0
+        timing["blocks"] = []
     for L in range(cfg["depth"]):
+        _tb = _time.perf_counter()
         p = f"blocks.{L}."
         full = L in cfg["fullatt_block_indexes"]
         cu = [0, T] if full else cu_win
@@ -107,8 +113,13 @@ def vit_forward(sd: Dict[str, torch.Tensor], cfg: dict, pixel_values: torch.Tens
             cells[perm] = x.reshape(T // unit, unit, H)
             m = cells.reshape(gh // merge, gw // merge, merge, merge, H).permute(0, 2, 1, 3, 4).reshape(gh, gw, H)
             taps.append(m.clone())
+        if timing is not None:
+            timing["blocks"].append((bool(full), _time.perf_counter() - _tb))
+    _tm = _time.perf_counter()
     y = rms_norm(x, w["merger.ln_q.weight"]).reshape(T // unit, unit * H)
     y = F.gelu(y @ w["merger.mlp.0.weight"].t() + w["merger.mlp.0.bias"]) @ w["merger.mlp.2.weight"].t() + w["merger.mlp.2.bias"]
     merged = torch.empty_like(y)
     merged[perm] = y
+    if timing is not None:
+        timing["merger_s"] = _time.perf_counter() - _tm
     return merged, taps

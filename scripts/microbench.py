@@ -77,9 +77,9 @@ def make_hfre_inputs(B, S, N, seed=0):
     return aux_all, pyr_all, ba, bv, grids
 
 
-def bench_hfre(results, B=8, S=896, N=100):
+def bench_hfre(results, B=8, S=896, N=100, algo=0):
     aux_all, pyr_all, ba, bv, grids = make_hfre_inputs(B, S, N)
-    cfg = H.HfreConfig(region_dim=5888, vt_mode="fpn")
+    cfg = H.HfreConfig(region_dim=5888, vt_mode="fpn", algo=algo)
     tot_unique = tot_gather = 0
     for b in range(B):
         shapes = [tuple(a.shape) for a in aux_all[b]] + [tuple(p.shape) for p in pyr_all[b]]
@@ -90,7 +90,7 @@ def bench_hfre(results, B=8, S=896, N=100):
         ab = H.algorithmic_bytes(shapes, boxes_l, scales, ups, N, 5888)
         tot_unique += ab["unique_bytes"]; tot_gather += ab["gather_bytes"]
     med, best = timeit(lambda: H.hfre_forward(aux_all, pyr_all, ba, bv, cfg, grids), iters=10)
-    r = {"kind": "hfre", "B": B, "S": S, "N": N, "ms": med, "ms_best": best, "unique_MB": tot_unique / 1e6, "gather_MB": tot_gather / 1e6,
+    r = {"kind": "hfre", "algo": algo, "B": B, "S": S, "N": N, "ms": med, "ms_best": best, "unique_MB": tot_unique / 1e6, "gather_MB": tot_gather / 1e6,
          "unique_GBs": tot_unique / med / 1e6, "gather_GBs": tot_gather / med / 1e6,
          "frac_of_measured_hbm": tot_unique / med / 1e6 / PEAKS["hbm_gbs"]}
     print(json.dumps(r), flush=True)
@@ -103,7 +103,10 @@ if __name__ == "__main__":
     res = []
     print("device", torch.cuda.get_device_name(0), "cpus", os.cpu_count(), flush=True)
     if "hfre" in which:
-        bench_hfre(res)
+        for algo in (1, 2):
+            bench_hfre(res, algo=algo)
+        bench_hfre(res, B=8, S=896, N=32, algo=1)     # COCO-like box count (mean 31.5)
+        bench_hfre(res, B=8, S=896, N=32, algo=2)
     if "gemm" in which:
         bench_gemm(res)
     os.makedirs(os.path.join(REPO, "gpurun_out"), exist_ok=True)

@@ -16,8 +16,9 @@ def _nerr(got, ref):
     return float((got - ref).abs().max() / ref.abs().max())
 
 
+@pytest.mark.parametrize("algo", [1, 2])
 @pytest.mark.parametrize("tag", ["small", "rect"])
-def test_hfre_matches_reference_goldens(golden_dir, tag):
+def test_hfre_matches_reference_goldens(golden_dir, tag, algo):
     import fo1_b200  # noqa: F401
     from importlib import import_module
     H = import_module("vlm-fo1_b200.hfre")
@@ -28,8 +29,8 @@ def test_hfre_matches_reference_goldens(golden_dir, tag):
     boxes = torch.from_numpy(z["boxes"]).cuda(); vtb = torch.from_numpy(z["vt_boxes"]).cuda()
     grid = tuple(int(v) for v in z["grid_hw"])
     D = z["out_fpn"].shape[1]
-    out_b = H.hfre_forward([aux], [pyr], [boxes], [vtb], H.HfreConfig(region_dim=D, vt_mode="fpn"), [grid])[0]
-    out_a = H.hfre_forward([aux], [taps], [boxes], [vtb], H.HfreConfig(region_dim=D, vt_mode="concat"), [grid])[0]
+    out_b = H.hfre_forward([aux], [pyr], [boxes], [vtb], H.HfreConfig(region_dim=D, vt_mode="fpn", algo=algo), [grid])[0]
+    out_a = H.hfre_forward([aux], [taps], [boxes], [vtb], H.HfreConfig(region_dim=D, vt_mode="concat", algo=algo), [grid])[0]
     torch.cuda.synchronize()
     # tolerance: 1e-3 relative (north_star); measured against the golden's max magnitude per tensor
     assert _nerr(out_b.cpu(), torch.from_numpy(z["out_fpn"])) < 1e-3
@@ -38,8 +39,9 @@ def test_hfre_matches_reference_goldens(golden_dir, tag):
     np.testing.assert_allclose(out_a.cpu().numpy(), z["out_concat"], rtol=1e-3, atol=2e-4)
 
 
+@pytest.mark.parametrize("algo", [1, 2])
 @pytest.mark.parametrize("S,N", [(448, 37), (896, 100)])
-def test_hfre_matches_oracle_full_shapes(S, N):
+def test_hfre_matches_oracle_full_shapes(S, N, algo):
     """DaViT-large / SimpleFPN shaped maps at real resolution, batch of 2 images, ragged box counts."""
     from importlib import import_module
     from oracle import hfre as O
@@ -58,7 +60,7 @@ def test_hfre_matches_oracle_full_shapes(S, N):
         boxes = torch.stack([x1, y1, x1 + w, y1 + h], 1)
         aux_all.append(aux); pyr_all.append(pyr); boxes_all.append(boxes); grid_all.append((gh, gh))
     sc = gh * 14 / S
-    cfg = H.HfreConfig(region_dim=5888, vt_mode="fpn")
+    cfg = H.HfreConfig(region_dim=5888, vt_mode="fpn", algo=algo)
     outs = H.hfre_forward([[a.cuda() for a in aux] for aux in aux_all], [[p.cuda() for p in pyr] for pyr in pyr_all],
                           [b.cuda() for b in boxes_all], [(b * sc).cuda() for b in boxes_all], cfg, grid_all)
     torch.cuda.synchronize()

@@ -21,6 +21,10 @@ namespace fo1 {
 constexpr int kMaxBatch = 8;           // images per launch (kernel-parameter budget: < 4 KB)
 constexpr int kGatherThreads = 256;
 constexpr int kChunk = 256;            // channels per gather block: 32 lanes x 8 bf16 (16 B) each
+constexpr int kRegion = 32;            // sweep: a CTA owns a kRegion x kRegion block of cells of one level
+constexpr int kSweepCh = 256;          // sweep: channels per CTA (4 warps x 32 lanes x 2 channels)
+constexpr int kSlots = 32;             // sweep: boxes accumulated concurrently per pass over the region
+constexpr int kSweepThreads = 128;
 
 struct LevelDev {
   const __nv_bfloat16* data;
@@ -30,6 +34,8 @@ struct LevelDev {
   int out_off;
   int wofs;      // float offset of this level's weight records inside the image's workspace slice
   int wstride;   // floats per box record: 4 header words + H + W, rounded up to 4
+  int lofs;      // int offset of this level's region box lists inside the image's list slice
+  int rh, rw;    // regions (kRegion x kRegion cells) per axis
 };
 struct ImageDev {
   LevelDev lv[FO1_HFRE_MAX_LEVELS];
@@ -37,6 +43,9 @@ struct ImageDev {
   float* out;
   __nv_bfloat16* out_bf16;
   long long ws_ofs;  // float offset of this image's workspace slice
+  long long ls_ofs;  // int offset of this image's region-list slice (after all weight records)
+  int lstride;       // ints per region list: 1 count + n_boxes ids, rounded up to 4
+  int n_items;       // sweep work items: sum over levels of regions * ceil(C / kSweepCh)
   float pos_w, pos_h;
   int pos_box_set;
   int n_levels;
@@ -50,6 +59,8 @@ struct BatchDev {
   int roi;
   int pos;
 };
+
+static_assert(sizeof(BatchDev) <= 32000, "BatchDev travels as a kernel parameter (32 KB limit on sm_70+)");
 
 // ------------------------------------------------------------------------------------------------
 // Kernel 1: per (image, box, level, axis) weight vector on the native grid.
@@ -279,6 +290,144 @@ __global__ void __launch_bounds__(kGatherThreads) hfre_gather_kernel(const Batch
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Kernel 3' (algo 2, map sweep).  The per-box gather above re-reads every cell once per covering box
+// (~8x the unique bytes at 100 boxes/image, L2-bound).  The sweep inverts the loops: a CTA owns a
+// 32x32-cell region x 256 channels of one level, reads each cell ONCE, and for every box whose
+// support meets the region accumulates a^T L b for its part, box accumulators living in shared
+// memory (lane-owned columns: no intra-CTA atomics); one fp32 red.global.add per (region, box,
+// channel) at the end.  Per cell and covering box the work is 2 FMA per bf16 pair -- the SIMT FMA
+// rate, not HBM, is then the co-limiter.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) hfre_region_lists_kernel(const BatchDev B, const float* __restrict__ ws, int* __restrict__ lists) {
+  const ImageDev& im = B.img[blockIdx.z];
+  const int lvl = blockIdx.y;
+  if (lvl >= im.n_levels) return;
+  const LevelDev& L = im.lv[lvl];
+  const int reg = blockIdx.x;
+  if (reg >= L.rh * L.rw) return;
+  const int ry = reg / L.rw, rx = reg % L.rw;
+  const int row0 = ry * kRegion, row1 = min(row0 + kRegion, L.H) - 1;
+  const int col0 = rx * kRegion, col1 = min(col0 + kRegion, L.W) - 1;
+  int* out = lists + im.ls_ofs + L.lofs + (long long)reg * im.lstride;
+  int count = 0;
+  for (int b0 = 0; b0 < im.n_boxes; b0 += 32) {
+    const int b = b0 + threadIdx.x;
+    bool hit = false;
+    if (b < im.n_boxes) {
+      const int* hdr = reinterpret_cast<const int*>(ws + im.ws_ofs + L.wofs + (long long)b * L.wstride);
+      const int r0 = hdr[0], r1 = hdr[0] + hdr[1] - 1, c0 = hdr[2], c1 = hdr[2] + hdr[3] - 1;
+      hit = r0 <= row1 && r1 >= row0 && c0 <= col1 && c1 >= col0;
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, hit);
+    if (hit) out[1 + count + __popc(m & ((1u << threadIdx.x) - 1u))] = b;
+    count += __popc(m);
+  }
+  if (threadIdx.x == 0) out[0] = count;
+}
+
+__global__ void __launch_bounds__(kSweepThreads) hfre_sweep_kernel(const BatchDev B, const float* __restrict__ ws, const int* __restrict__ lists) {
+  const ImageDev& im = B.img[blockIdx.z];
+  if ((int)blockIdx.x >= im.n_items) return;
+  int lvl = 0, item = blockIdx.x;
+  for (; lvl < im.n_levels; ++lvl) {
+    const int n = im.lv[lvl].rh * im.lv[lvl].rw * ((im.lv[lvl].C + kSweepCh - 1) / kSweepCh);
+    if (item < n) break;
+    item -= n;
+  }
+  const LevelDev& L = im.lv[lvl];
+  const int n_reg = L.rh * L.rw;
+  const int cgroup = item / n_reg, reg = item % n_reg;
+  const int* list = lists + im.ls_ofs + L.lofs + (long long)reg * im.lstride;
+  const int n_list = list[0];
+  if (n_list == 0) return;  // no box touches this region: its cells are never read
+  const int ry = reg / L.rw, rx = reg % L.rw;
+  const int row0 = ry * kRegion, col0 = rx * kRegion;
+
+  __shared__ __align__(16) float s_acc[kSlots][kSweepCh];
+  __shared__ __align__(16) float s_wa[kSlots][kRegion];
+  __shared__ __align__(16) float s_wb[kSlots][kRegion];
+  __shared__ int s_box[kSlots];
+  __shared__ int s_rmask[kSlots], s_cmask[kSlots];   // which 8-row / 8-col tile bands carry non-zero weights
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int cbase = cgroup * kSweepCh + warp * 64 + lane * 2;
+  const bool active = cbase < L.C;
+  const long long rowpitch = (long long)L.W * L.C;
+
+  for (int base = 0; base < n_list; base += kSlots) {
+    const int ns = min(kSlots, n_list - base);
+    // ---- stage this pass's boxes: ids, dense weights over the region's rows / cols, band masks ----
+    if (threadIdx.x < kSlots) {
+      s_box[threadIdx.x] = threadIdx.x < ns ? list[1 + base + threadIdx.x] : -1;
+      s_rmask[threadIdx.x] = 0; s_cmask[threadIdx.x] = 0;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < ns * kRegion * 2; i += kSweepThreads) {
+      const int sl = i / (kRegion * 2), j = i % (kRegion * 2);
+      const int axis = j / kRegion, k = j % kRegion;
+      const float* rec = ws + im.ws_ofs + L.wofs + (long long)s_box[sl] * L.wstride;
+      const int* hdr = reinterpret_cast<const int*>(rec);
+      const int start = hdr[axis * 2], len = hdr[axis * 2 + 1];
+      const int idx = (axis ? col0 : row0) + k - start;
+      const float w = (idx >= 0 && idx < len) ? rec[4 + (axis ? L.H : 0) + idx] : 0.0f;
+      (axis ? s_wb : s_wa)[sl][k] = w;
+      if (w != 0.0f) atomicOr(axis ? &s_cmask[sl] : &s_rmask[sl], 1 << (k >> 3));
+    }
+    for (int i = threadIdx.x; i < ns * kSweepCh; i += kSweepThreads) s_acc[i / kSweepCh][i % kSweepCh] = 0.0f;
+    __syncthreads();
+
+    if (active) {
+      for (int tile = 0; tile < 16; ++tile) {
+        const int ty = tile >> 2, tx = tile & 3;
+        const int r_base = row0 + ty * 8, c_base = col0 + tx * 8;
+        if (r_base >= L.H || c_base >= L.W) continue;
+        bool any = false;
+        for (int sl = 0; sl < ns; ++sl) any |= ((s_rmask[sl] >> ty) & 1) && ((s_cmask[sl] >> tx) & 1);
+        if (!any) continue;  // warp-uniform
+        float vx[8][8], vy[8][8];
+        const __nv_bfloat16* p0 = L.data + (long long)r_base * rowpitch + (long long)c_base * L.C + cbase;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            uint32_t u = 0;
+            if (r_base + r < L.H && c_base + k < L.W) u = __ldg(reinterpret_cast<const uint32_t*>(p0 + (long long)r * rowpitch + (long long)k * L.C));
+            vx[r][k] = bf16_lo(u); vy[r][k] = bf16_hi(u);
+          }
+        }
+        for (int sl = 0; sl < ns; ++sl) {
+          if (!(((s_rmask[sl] >> ty) & 1) && ((s_cmask[sl] >> tx) & 1))) continue;
+          const float4 b0 = *reinterpret_cast<const float4*>(&s_wb[sl][tx * 8]), b1 = *reinterpret_cast<const float4*>(&s_wb[sl][tx * 8 + 4]);
+          const float4 a0 = *reinterpret_cast<const float4*>(&s_wa[sl][ty * 8]), a1 = *reinterpret_cast<const float4*>(&s_wa[sl][ty * 8 + 4]);
+          const float wb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+          const float wa[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+          float ax = 0.f, ay = 0.f;
+#pragma unroll
+          for (int r = 0; r < 8; ++r) {
+            float tx_ = 0.f, ty_ = 0.f;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { tx_ = fmaf(wb[k], vx[r][k], tx_); ty_ = fmaf(wb[k], vy[r][k], ty_); }
+            ax = fmaf(wa[r], tx_, ax); ay = fmaf(wa[r], ty_, ay);
+          }
+          float2* acc = reinterpret_cast<float2*>(&s_acc[sl][warp * 64 + lane * 2]);  // lane-owned: no atomics
+          float2 cur = *acc;
+          cur.x += ax; cur.y += ay;
+          *acc = cur;
+        }
+      }
+    }
+    __syncthreads();
+    // ---- flush: one fp32 reduction per (box, channel) of this region ----
+    for (int i = threadIdx.x; i < ns * kSweepCh; i += kSweepThreads) {
+      const int sl = i / kSweepCh, c = cgroup * kSweepCh + (i % kSweepCh);
+      if (c < L.C) atomicAdd(im.out + (long long)s_box[sl] * B.out_dim + L.out_off + c, s_acc[sl][i % kSweepCh]);
+    }
+    __syncthreads();
+  }
+}
+
 // Kernel 4: optional bf16 copy of the region features (the reference casts to the tower dtype
 // before mm_projector_aux, omchat_qwen2_5_vl.py:106).
 __global__ void __launch_bounds__(256) hfre_to_bf16_kernel(const BatchDev B) {
@@ -297,6 +446,13 @@ static size_t image_ws_floats(const fo1_hfre_image& im) {
   for (int l = 0; l < im.n_levels; ++l) f += (size_t)im.n_boxes * level_wstride(im.levels[l]);
   return f;
 }
+static int list_stride(int n_boxes) { return (1 + n_boxes + 3) & ~3; }
+static size_t image_list_ints(const fo1_hfre_image& im) {
+  size_t n = 0;
+  for (int l = 0; l < im.n_levels; ++l)
+    n += (size_t)ceil_div(im.levels[l].H, kRegion) * ceil_div(im.levels[l].W, kRegion) * list_stride(im.n_boxes);
+  return n;
+}
 
 }  // namespace fo1
 
@@ -304,7 +460,7 @@ using namespace fo1;
 
 extern "C" size_t fo1_hfre_workspace_bytes(const fo1_hfre_image* images, int32_t n_images, const fo1_hfre_params*) {
   size_t f = 0;
-  for (int i = 0; i < n_images; ++i) f += image_ws_floats(images[i]);
+  for (int i = 0; i < n_images; ++i) f += image_ws_floats(images[i]) + image_list_ints(images[i]);
   return f * sizeof(float) + 256;
 }
 
@@ -314,7 +470,7 @@ extern "C" int fo1_hfre_forward(const fo1_hfre_image* images, int32_t n_images, 
   if (n_images == 0) return FO1_OK;
   FO1_CHECK_ARG(p->roi_size >= 1 && p->roi_size <= 32, "fo1_hfre_forward: roi_size %d unsupported", p->roi_size);
   FO1_CHECK_ARG(p->out_dim > 0 && p->out_dim % 4 == 0, "fo1_hfre_forward: out_dim %d must be a positive multiple of 4", p->out_dim);
-  FO1_CHECK_ARG(p->algo == 0 || p->algo == 1, "fo1_hfre_forward: algo %d not available", p->algo);
+  FO1_CHECK_ARG(p->algo >= 0 && p->algo <= 2, "fo1_hfre_forward: algo %d not available", p->algo);
   const size_t need = fo1_hfre_workspace_bytes(images, n_images, p);
   if (workspace == nullptr || workspace_bytes < need) {
     set_error("fo1_hfre_forward: workspace %zu B < required %zu B", workspace_bytes, need);
@@ -322,6 +478,10 @@ extern "C" int fo1_hfre_forward(const fo1_hfre_image* images, int32_t n_images, 
   }
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   float* ws = static_cast<float*>(workspace);
+  size_t total_w = 0;
+  for (int i = 0; i < n_images; ++i) total_w += image_ws_floats(images[i]);
+  int* lists = reinterpret_cast<int*>(ws + total_w);   // region box lists live after all weight records
+  size_t ls_ofs = 0;
 
   size_t ws_ofs = 0;
   for (int base = 0; base < n_images; base += kMaxBatch) {
@@ -331,7 +491,7 @@ extern "C" int fo1_hfre_forward(const fo1_hfre_image* images, int32_t n_images, 
     B.out_dim = p->out_dim;
     B.roi = p->roi_size;
     B.pos = p->apply_pos_embed ? 1 : 0;
-    int max_boxes = 0, max_levels = 0, max_chunks = 0, max_up = 0, max_hw = 0;
+    int max_boxes = 0, max_levels = 0, max_chunks = 0, max_up = 0, max_hw = 0, max_items = 0, max_regions = 0, total_boxes = 0;
     for (int i = 0; i < B.n_images; ++i) {
       const fo1_hfre_image& src = images[base + i];
       ImageDev& d = B.img[i];
@@ -348,7 +508,10 @@ extern "C" int fo1_hfre_forward(const fo1_hfre_image* images, int32_t n_images, 
       d.pos_h = src.pos_img_h;
       d.pos_box_set = src.pos_box_set ? 1 : 0;
       d.ws_ofs = (long long)ws_ofs;
-      int wofs = 0, chunks = 0;
+      int wofs = 0, chunks = 0, lofs = 0, items = 0;
+      d.ls_ofs = (long long)ls_ofs;
+      d.lstride = list_stride(src.n_boxes);
+      total_boxes += src.n_boxes;
       for (int l = 0; l < src.n_levels; ++l) {
         const fo1_hfre_level& sl = src.levels[l];
         FO1_CHECK_ARG(sl.data != nullptr && sl.H > 0 && sl.W > 0 && sl.C > 0, "image %d level %d: bad shape", base + i, l);
@@ -366,12 +529,20 @@ extern "C" int fo1_hfre_forward(const fo1_hfre_image* images, int32_t n_images, 
         dl.wstride = level_wstride(sl);
         wofs += src.n_boxes * dl.wstride;
         chunks += ceil_div(sl.C, kChunk);
+        dl.rh = ceil_div(sl.H, kRegion); dl.rw = ceil_div(sl.W, kRegion);
+        dl.lofs = lofs;
+        lofs += dl.rh * dl.rw * d.lstride;
+        items += dl.rh * dl.rw * ceil_div(sl.C, kSweepCh);
+        max_regions = max_regions > dl.rh * dl.rw ? max_regions : dl.rh * dl.rw;
         max_up = max_up > sl.up_H ? max_up : sl.up_H;
         max_up = max_up > sl.up_W ? max_up : sl.up_W;
         max_hw = max_hw > sl.H + sl.W ? max_hw : sl.H + sl.W;
       }
       d.n_chunks = chunks;
+      d.n_items = items;
+      max_items = max_items > items ? max_items : items;
       ws_ofs += (size_t)wofs;
+      ls_ofs += (size_t)lofs;
       max_boxes = max_boxes > src.n_boxes ? max_boxes : src.n_boxes;
       max_levels = max_levels > src.n_levels ? max_levels : src.n_levels;
       max_chunks = max_chunks > chunks ? max_chunks : chunks;
@@ -388,7 +559,19 @@ extern "C" int fo1_hfre_forward(const fo1_hfre_image* images, int32_t n_images, 
       hfre_pos_init_kernel<<<grid, 256, 0, stream>>>(B);
       FO1_LAUNCH_CHECK();
     }
-    {
+    // algo 0: the sweep wins as soon as boxes overlap (its traffic is the union of the windows, the gather's their sum)
+    const bool sweep = p->algo == 2 || (p->algo == 0 && total_boxes >= 8 * B.n_images);
+    if (sweep) {
+      {
+        dim3 grid(max_regions, max_levels, B.n_images);
+        hfre_region_lists_kernel<<<grid, 32, 0, stream>>>(B, ws, lists);
+        FO1_LAUNCH_CHECK();
+      }
+      dim3 grid(max_items, 1, B.n_images);
+      ProfScope prof("hfre_sweep", 0.0, 0.0, stream);
+      hfre_sweep_kernel<<<grid, kSweepThreads, 0, stream>>>(B, ws, lists);
+      FO1_LAUNCH_CHECK();
+    } else {
       dim3 grid(max_chunks, max_boxes, B.n_images);
       const size_t smem = ((size_t)max_hw + (kGatherThreads / 32) * kChunk) * sizeof(float);
       ProfScope prof("hfre_gather", 0.0, 0.0, stream);

@@ -97,6 +97,22 @@ def bench_hfre(results, B=8, S=896, N=100, algo=0):
     results.append(r)
 
 
+def bench_decode_gemms(results, M=32):
+    """the four per-layer decode GEMMs + lm_head at batch M: weight-streaming, HBM-bound"""
+    shapes = [("qkv", 2560, 2048, False), ("o", 2048, 2048, False), ("gateup", 22016, 2048, True), ("down", 2048, 11008, False),
+              ("lm_head", 151936, 2048, False)]
+    for name, N, K, gated in shapes:
+        a = (torch.randn(M, K, device="cuda") * 0.5).to(torch.bfloat16)
+        w = (torch.randn(N, K, device="cuda") * 0.05).to(torch.bfloat16)
+        fn = (lambda: ops.gemm(a, w, act="silu", gated=True)) if gated else (lambda: ops.gemm(a, w))
+        med, best = timeit(fn, iters=20)
+        byt = 2.0 * (N * K + M * K + M * N)
+        r = {"kind": "decode_gemm", "name": name, "M": M, "N": N, "K": K, "us": med * 1e3, "GBs": byt / med / 1e6,
+             "frac_of_measured_hbm": byt / med / 1e6 / PEAKS["hbm_gbs"]}
+        print(json.dumps(r), flush=True)
+        results.append(r)
+
+
 if __name__ == "__main__":
     tag = sys.argv[1] if len(sys.argv) > 1 else "r1"
     which = sys.argv[2:] or ["gemm", "hfre"]
@@ -109,5 +125,7 @@ if __name__ == "__main__":
         bench_hfre(res, B=8, S=896, N=32, algo=2)
     if "gemm" in which:
         bench_gemm(res)
+    if "decode" in which:
+        bench_decode_gemms(res)
     os.makedirs(os.path.join(REPO, "gpurun_out"), exist_ok=True)
     json.dump(res, open(os.path.join(REPO, "gpurun_out", f"microbench_{tag}.json"), "w"), indent=1)

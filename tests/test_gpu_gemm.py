@@ -64,6 +64,27 @@ def test_gemm_epilogues(act, bias_dtype):
     _check(out, _ref(a, w, bias, act, res), False)
 
 
+@pytest.mark.parametrize("M,N,K", [(32, 2048, 11008), (32, 2560, 2048), (4, 2048, 2048), (1, 2048, 2048), (100, 2048, 5888),
+                                   (32, 2048, 2048), (17, 96, 4096), (32, 151936, 2048)])
+def test_gemm_skinny_splitk(M, N, K):
+    """decode-shaped problems take the narrow-tile / split-K path (partials reduced in-kernel by the last CTA);
+    run twice: the per-tile arrival counters must be self-cleaning."""
+    ops = _ops()
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    a = (torch.randn(M, K, device="cuda", generator=g) * 0.5).to(torch.bfloat16)
+    w = (torch.randn(N, K, device="cuda", generator=g) * 0.05).to(torch.bfloat16)
+    bias = (torch.randn(N, device="cuda", generator=g) * 0.2).to(torch.bfloat16)
+    res = torch.randn(M, N, device="cuda", generator=g).to(torch.bfloat16)
+    ref = _ref(a, w, bias, "gelu", res)
+    for _ in range(2):
+        out = ops.gemm(a, w, bias=bias, act="gelu", residual=res, out_dtype=torch.float32)
+        torch.cuda.synchronize()
+        _check(out, ref, False)
+    out2 = ops.gemm(a, w, bias=bias, act="gelu", residual=res, out_dtype=torch.float32)
+    torch.cuda.synchronize()
+    assert torch.equal(out, out2)      # fixed reduction order -> bitwise reproducible
+
+
 def test_gemm_gated_silu():
     """Qwen2 MLP front half: silu(x Wg^T + bg) * (x Wu^T + bu) with the [32 gate | 32 up] row interleave;
     intermediate size 3420 is zero-padded to 3424 by the host-side weight prep."""

@@ -15,6 +15,10 @@
 // padding beyond 16-byte row pitches.
 #include <cuda.h>
 
+#include <algorithm>
+#include <map>
+#include <mutex>
+
 #include "kernels.cuh"
 #include "ptx.cuh"
 
@@ -33,6 +37,11 @@ struct GemmArgs {
   const __nv_bfloat16* residual; long long ldr;
   int gated;
   int tiles_m, tiles_n;
+  // split-K (skinny problems): work item = (tile, split); partial sums meet in `ws`, the last CTA to arrive on
+  // `counters[tile]` reduces them in split order (deterministic) and runs the epilogue
+  int ksplit, kb_per_split;
+  float* ws;
+  int* counters;
 };
 
 template <int BN>
@@ -120,11 +129,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   uint64_t* tmem_full = bars + 2 * S;        // [2]
   uint64_t* tmem_empty = bars + 2 * S + 2;   // [2]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * S + 4);
+  volatile int* last_flag = reinterpret_cast<volatile int*>(tmem_ptr + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_tiles = g.tiles_m * g.tiles_n;
-  const int num_kb = (g.K + BK - 1) / BK;
+  const int num_tiles = g.tiles_m * g.tiles_n * g.ksplit;   // work items
+  const int num_kb_total = (g.K + BK - 1) / BK;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmA);
@@ -149,10 +159,12 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     // ===================================== TMA producer =====================================
     if (ptx::elect_one()) {
       uint32_t it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int work = blockIdx.x; work < num_tiles; work += gridDim.x) {
+        const int tile = work / g.ksplit, split = work - tile * g.ksplit;
         const int m0 = (tile / g.tiles_n) * BM;
         const int n0 = (tile % g.tiles_n) * BN;
-        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+        const int kb0 = split * g.kb_per_split, kb1 = min(num_kb_total, kb0 + g.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const uint32_t s = it % S, ph = (it / S) & 1;
           ptx::mbar_wait(ptx::smem_u32(empty_bar + s), ph ^ 1);
           const uint32_t fb = ptx::smem_u32(full_bar + s);
@@ -166,12 +178,14 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     // ====================================== MMA issuer ======================================
     constexpr uint32_t idesc = ptx::umma_idesc_bf16(BM, BN);
     uint32_t it = 0, tcount = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
+    for (int work = blockIdx.x; work < num_tiles; work += gridDim.x, ++tcount) {
+      const int split = work % g.ksplit;
+      const int kb0 = split * g.kb_per_split, kb1 = min(num_kb_total, kb0 + g.kb_per_split);
       const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
       ptx::mbar_wait(ptx::smem_u32(tmem_empty + acc), aph ^ 1);  // epilogue has drained this accumulator
       ptx::tc_fence_after();
       const uint32_t tmem_d = tmem_base + acc * BN;
-      for (int kb = 0; kb < num_kb; ++kb, ++it) {
+      for (int kb = kb0; kb < kb1; ++kb, ++it) {
         const uint32_t s = it % S, ph = (it / S) & 1;
         ptx::mbar_wait(ptx::smem_u32(full_bar + s), ph);
         ptx::tc_fence_after();
@@ -182,10 +196,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           for (int k = 0; k < BK / UMMA_K; ++k) {
             const uint64_t da = ptx::umma_desc_k_sw128(a_addr + k * UMMA_K * 2);
             const uint64_t db = ptx::umma_desc_k_sw128(b_addr + k * UMMA_K * 2);
-            ptx::tc_mma_bf16(tmem_d, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            ptx::tc_mma_bf16(tmem_d, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
           ptx::tc_commit(ptx::smem_u32(empty_bar + s));                    // slot free when these MMAs retire
-          if (kb == num_kb - 1) ptx::tc_commit(ptx::smem_u32(tmem_full + acc));  // accumulator complete
+          if (kb == kb1 - 1) ptx::tc_commit(ptx::smem_u32(tmem_full + acc));  // accumulator complete
         }
         __syncwarp();
       }
@@ -194,7 +208,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     // ======================================= epilogue ========================================
     const int quarter = warp & 3;  // TMEM lane quarter this warp may read
     uint32_t tcount = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++tcount) {
+    for (int work = blockIdx.x; work < num_tiles; work += gridDim.x, ++tcount) {
+      const int tile = work / g.ksplit, split = work - tile * g.ksplit;
       const int m0 = (tile / g.tiles_n) * BM;
       const int n0 = (tile % g.tiles_n) * BN;
       const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
@@ -202,6 +217,63 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       ptx::tc_fence_after();
       const int m = m0 + quarter * 32 + lane;
       const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(quarter * 32) << 16);
+      if (g.ksplit > 1) {
+        // ---- split-K: park the fp32 partial, the last split to arrive reduces + finishes the tile ----
+        float* part = g.ws + ((long long)(tile * g.ksplit + split) * BM + quarter * 32 + lane) * BN;
+#pragma unroll 1
+        for (int c = 0; c < BN; c += 32) {
+          uint32_t r[32];
+          ptx::tmem_ld_32x32(taddr + c, r);
+          ptx::tmem_ld_wait();
+          if (m < g.M) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              reinterpret_cast<float4*>(part + c)[q] = make_float4(__uint_as_float(r[q * 4]), __uint_as_float(r[q * 4 + 1]),
+                                                                    __uint_as_float(r[q * 4 + 2]), __uint_as_float(r[q * 4 + 3]));
+          }
+        }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(tmem_empty + acc));   // TMEM is free again: the MMA warp moves on
+        __threadfence();
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (warp == 2 && lane == 0) *last_flag = (atomicAdd(g.counters + tile, 1) == g.ksplit - 1) ? 1 : 0;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (*last_flag) {
+          __threadfence();
+          if (m < g.M) {
+            const float* p0 = g.ws + ((long long)tile * g.ksplit * BM + quarter * 32 + lane) * BN;
+#pragma unroll 1
+            for (int c = 0; c < BN; c += 32) {
+              if (n0 + c >= g.N) break;
+              float v[32];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] = 0.f;
+              for (int sp = 0; sp < g.ksplit; ++sp) {
+                const float4* src = reinterpret_cast<const float4*>(p0 + (long long)sp * BM * BN + c);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                  const float4 t = __ldcg(src + q);
+                  v[q * 4] += t.x; v[q * 4 + 1] += t.y; v[q * 4 + 2] += t.z; v[q * 4 + 3] += t.w;
+                }
+              }
+              if (g.bias != nullptr) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                  if (n0 + c + j < g.N) v[j] += load_bias(g.bias, g.bias_dtype, n0 + c + j);
+              }
+              if (g.act != FO1_EPI_NONE) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], g.act);
+              }
+              store_row32(g, v, m, n0 + c, g.N);
+            }
+          }
+          if (warp == 2 && lane == 0) g.counters[tile] = 0;   // self-cleaning for the next launch
+        }
+        asm volatile("bar.sync 1, 128;" ::: "memory");   // last_flag is reused by the next work item
+        continue;
+      }
       if (!g.gated) {
 #pragma unroll 1
         for (int c = 0; c < BN; c += 32) {
@@ -308,8 +380,33 @@ int device_sm_count() {
   return sms;
 }
 
+// split-K scratch: fp32 partials + per-tile arrival counters, one set per stream (GEMMs on one stream are ordered)
+struct SplitKScratch { float* ws = nullptr; size_t bytes = 0; int* counters = nullptr; };
+static int splitk_scratch(cudaStream_t stream, size_t need_bytes, int need_counters, SplitKScratch** out) {
+  static std::map<cudaStream_t, SplitKScratch> pool;
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lk(mu);
+  SplitKScratch& sc = pool[stream];
+  constexpr int kCounters = 1 << 16;
+  if (need_counters > kCounters) { set_error("split-K: too many tiles (%d)", need_counters); return FO1_ERR_UNSUPPORTED; }
+  if (sc.counters == nullptr) {
+    FO1_CUDA(cudaMalloc(reinterpret_cast<void**>(&sc.counters), kCounters * sizeof(int)));
+    FO1_CUDA(cudaMemset(sc.counters, 0, kCounters * sizeof(int)));
+  }
+  if (need_bytes > sc.bytes) {
+    FO1_CUDA(cudaStreamSynchronize(stream));
+    if (sc.ws) FO1_CUDA(cudaFree(sc.ws));
+    sc.ws = nullptr; sc.bytes = 0;
+    const size_t want = std::max(need_bytes, (size_t)32 << 20);
+    FO1_CUDA(cudaMalloc(reinterpret_cast<void**>(&sc.ws), want));
+    sc.bytes = want;
+  }
+  *out = &sc;
+  return FO1_OK;
+}
+
 template <int BN>
-static int launch_gemm(const fo1_gemm_desc* d, cudaStream_t stream) {
+static int launch_gemm(const fo1_gemm_desc* d, cudaStream_t stream, int ksplit = 1) {
   using Cfg = GemmCfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -328,9 +425,20 @@ static int launch_gemm(const fo1_gemm_desc* d, cudaStream_t stream) {
   g.gated = d->gated;
   g.tiles_m = ceil_div(d->M, BM);
   g.tiles_n = ceil_div(d->N, BN);
-  const int tiles = g.tiles_m * g.tiles_n;
+  const int num_kb = ceil_div(d->K, BK);
+  g.kb_per_split = ceil_div(num_kb, ksplit);
+  g.ksplit = ceil_div(num_kb, g.kb_per_split);   // every split owns at least one k-block
+  g.ws = nullptr; g.counters = nullptr;
+  if (g.ksplit > 1) {
+    SplitKScratch* sc = nullptr;
+    FO1_TRY(splitk_scratch(stream, (size_t)g.tiles_m * g.tiles_n * g.ksplit * BM * BN * sizeof(float), g.tiles_m * g.tiles_n, &sc));
+    g.ws = sc->ws; g.counters = sc->counters;
+  }
+  const int tiles = g.tiles_m * g.tiles_n * g.ksplit;
   const int grid = tiles < device_sm_count() ? tiles : device_sm_count();
-  ProfScope prof(d->M <= 128 ? "gemm_skinny" : "gemm", 2.0 * d->M * (double)d->N * d->K,
+  char tag[96] = "gemm";
+  if (g_prof_on) snprintf(tag, sizeof(tag), "%s:%dx%dx%d%s", d->M <= 128 ? "gemm_skinny" : "gemm", d->M, d->N, d->K, d->gated ? ":gated" : "");
+  ProfScope prof(tag, 2.0 * d->M * (double)d->N * d->K,
                  2.0 * ((double)d->M * d->K + (double)d->N * d->K + (double)d->M * (d->gated ? d->N / 2 : d->N)), stream);
   gemm_bf16_tcgen05_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(tmA, tmW, g);
   FO1_LAUNCH_CHECK();
@@ -360,8 +468,12 @@ int gemm_bf16(const fo1_gemm_desc* d, cudaStream_t stream) {
   if (d->N >= 256 && tm * ceil_div(d->N, 256) >= sms) return launch_gemm<256>(d, stream);
   if (d->N >= 128 && tm * ceil_div(d->N, 128) >= sms) return launch_gemm<128>(d, stream);
   if (d->gated || tm * ceil_div(d->N, 64) >= sms) return launch_gemm<64>(d, stream);
-  // skinny problems (decode: M = batch): narrow tiles so that >= ~half the SMs stream weights, deep ring
-  return launch_gemm<32>(d, stream);
+  // skinny problems (decode: M = batch, weight streaming): narrow tiles, deep ring, and split-K until every SM
+  // pulls weights (>= 8 k-blocks per split so the ring still fills)
+  const long long t32 = tm * ceil_div(d->N, 32);
+  int ks = 1;
+  if (t32 < sms) ks = (int)std::min<long long>(std::min<long long>(8, ceil_div(sms, (int)t32)), std::max(1, ceil_div(d->K, BK) / 8));
+  return launch_gemm<32>(d, stream, ks);
 }
 
 }  // namespace fo1

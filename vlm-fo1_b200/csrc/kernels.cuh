@@ -29,9 +29,10 @@ int vit_rope_table(const int* pos_hw /*[T][2]*/, float* cos_sin /*[T][rot_dim] c
                    float theta, cudaStream_t s);
 // rotate q and k inside a packed qkv buffer [T][3*heads*head_dim] (non-interleaved halves)
 int vit_rope_apply(bf16* qkv, const float* cos_sin, int T, int heads, int head_dim, cudaStream_t s);
-// LLM M-RoPE (modeling_qwen2_5_vl.py:603-624, 643-685): q [T][q_heads*hd], k [T][kv_heads*hd] in a packed row of pitch ld
-int mrope_apply(bf16* q, bf16* k, long long ld, const int* pos3 /*[3][T]*/, int T, int q_heads, int kv_heads, int head_dim,
-                int sec_t, int sec_h, int sec_w, float theta, cudaStream_t s);
+// LLM M-RoPE (modeling_qwen2_5_vl.py:603-624, 643-685): cos/sin table [T][hd/2] x2 from the 3-axis ids, built once per forward
+int mrope_table(const int* pos3 /*[3][T]*/, float* cos_sin, int T, int head_dim, int sec_t, int sec_h, int sec_w, float theta, cudaStream_t s);
+// rotate n_heads consecutive heads (q then k) of every row in place with a [T][hd/2] cos / sin table
+int rope_apply(bf16* x, long long ld, const float* cos_sin, int T, int n_heads, int head_dim, cudaStream_t s);
 
 // ---- attention.cu ----
 // varlen flash attention over packed rows; q/k/v may live in one packed buffer (pitches in elements)

@@ -61,16 +61,21 @@ __global__ void __launch_bounds__(128) kv_append_kernel(const bf16* __restrict__
   }
 }
 
-// Single-query GQA attention over the cache: one block per (sequence, kv head); the G = q_heads/kv_heads
-// query heads that share the K/V stream are processed together so every K/V byte is read once.
-// 8 warps x 4 token slots; a token's 128 dims are split over 8 lanes (16 dims = 32 B each).
+// Single-query GQA attention over the cache, split over the sequence (flash-decoding): one block per
+// (sequence, kv head, split); the G = q_heads/kv_heads query heads that share the K/V stream are processed together
+// so every K/V byte is read once.  8 warps x 4 token slots; a token's 128 dims are split over 8 lanes (16 dims =
+// 32 B each).  Each block writes an un-normalised partial (m, l, acc) per head; decode_attn_combine_kernel merges
+// the splits.  With B = 32, 2 kv heads and 8 splits that is 512 blocks streaming the cache instead of 64.
+constexpr int kDecSplits = 8;
 template <int G>
 __global__ void __launch_bounds__(256) decode_attn_kernel(const bf16* __restrict__ q, long long ldq, const bf16* __restrict__ kc,
                                                           const bf16* __restrict__ vc, const int* __restrict__ cache_len, int cap,
-                                                          int kv_heads, bf16* __restrict__ out, long long ldo, float scale) {
+                                                          int kv_heads, float* __restrict__ part, float scale) {
   constexpr int HD = 128;
-  const int b = blockIdx.x, kvh = blockIdx.y;
+  const int b = blockIdx.x, kvh = blockIdx.y, sp = blockIdx.z;
   const int n = cache_len[b] + 1;  // the step's own K/V was appended at index cache_len[b]
+  const int chunk = ((n + kDecSplits - 1) / kDecSplits + 3) & ~3;
+  const int t_begin = sp * chunk, t_end = min(n, t_begin + chunk);
   const int kv_dim = kv_heads * HD;
   __shared__ float qs[G][HD];
   __shared__ float red_m[8][G], red_l[8][G];
@@ -91,9 +96,9 @@ __global__ void __launch_bounds__(256) decode_attn_kernel(const bf16* __restrict
   }
   const bf16* kb = kc + (long long)b * cap * kv_dim + kvh * HD + sub * 16;
   const bf16* vb = vc + (long long)b * cap * kv_dim + kvh * HD + sub * 16;
-  for (int t0 = warp * 4; t0 < n; t0 += 32) {
+  for (int t0 = t_begin + warp * 4; t0 < t_end; t0 += 32) {
     const int t = t0 + grp;
-    const bool ok = t < n;
+    const bool ok = t < t_end;
     float kf[16], vf[16];
     {
       uint4 k0 = make_uint4(0, 0, 0, 0), k1 = k0, v0 = k0, v1 = k0;
@@ -149,6 +154,7 @@ __global__ void __launch_bounds__(256) decode_attn_kernel(const bf16* __restrict
     }
   }
   __syncthreads();
+  // partial record per (b, kvh, g, split): [m, l, pad, pad, acc[128]]
   for (int i = threadIdx.x; i < G * HD; i += 256) {
     const int g = i / HD, d = i % HD;
     float mm = -INFINITY;
@@ -161,8 +167,30 @@ __global__ void __launch_bounds__(256) decode_attn_kernel(const bf16* __restrict
       num += red_acc[w][g][d] * sc;
       den += red_l[w][g] * sc;
     }
-    out[(long long)b * ldo + (long long)(kvh * G + g) * HD + d] = __float2bfloat16_rn(num / den);
+    float* rec = part + ((((long long)b * kv_heads + kvh) * G + g) * kDecSplits + sp) * (HD + 4);
+    rec[4 + d] = num;
+    if (d == 0) { rec[0] = mm; rec[1] = den; }
   }
+}
+
+// merge the kDecSplits partials of one (sequence, q head): out = sum_s acc_s * 2^(m_s - m) / sum_s l_s * 2^(m_s - m)
+__global__ void __launch_bounds__(128) decode_attn_combine_kernel(const float* __restrict__ part, bf16* __restrict__ out, long long ldo,
+                                                                  int q_heads) {
+  constexpr int HD = 128;
+  const int b = blockIdx.x, h = blockIdx.y, d = threadIdx.x;
+  const float* rec = part + (((long long)b * q_heads + h) * kDecSplits) * (HD + 4);
+  float mm = -INFINITY;
+#pragma unroll
+  for (int s = 0; s < kDecSplits; ++s) mm = fmaxf(mm, rec[s * (HD + 4)]);
+  float num = 0.f, den = 0.f;
+#pragma unroll
+  for (int s = 0; s < kDecSplits; ++s) {
+    const float ms = rec[s * (HD + 4)];
+    const float sc = (ms == -INFINITY) ? 0.f : exp2f(ms - mm);
+    num += rec[s * (HD + 4) + 4 + d] * sc;
+    den += rec[s * (HD + 4) + 1] * sc;
+  }
+  out[(long long)b * ldo + (long long)h * HD + d] = __float2bfloat16_rn(num / den);
 }
 
 // greedy token: lowest index among the maxima of a fp32 logits row
@@ -332,9 +360,9 @@ static int ensure_state(Model* m, int B, int n_stop, DecodeState* st) {
 
 // one decoder layer over `rows` packed rows.  x_in -> x_out (x_mid scratch).  prefill: varlen causal attention
 // + cache fill; decode: cache append + single-query attention.
-struct LayerBuf { bf16 *xn, *qkv, *att, *x_mid, *h; };
+struct LayerBuf { bf16 *xn, *qkv, *att, *x_mid, *h; float* dec_part; };
 
-static int llm_layer(Model* m, int li, const bf16* x_in, bf16* x_out, const LayerBuf& B_, int rows, const int* pos3, bool prefill,
+static int llm_layer(Model* m, int li, const bf16* x_in, bf16* x_out, const LayerBuf& B_, int rows, const float* cs, bool prefill,
                      const int* d_cu, int n_seqs, int max_len, const int* d_row_seq, const int* d_row_t, const DecodeState* st,
                      cudaStream_t s, bool dry) {
   const fo1_model_config& c = m->cfg;
@@ -346,8 +374,7 @@ static int llm_layer(Model* m, int li, const bf16* x_in, bf16* x_out, const Laye
   bf16* vc = static_cast<bf16*>(m->kv_cache) + ((size_t)c.llm_layers + li) * layer_stride;
   FO1_RUN(rmsnorm(x_in, H, L.ln1, B_.xn, H, rows, H, c.rms_eps, s));
   FO1_RUN(linear(B_.xn, H, L.qkv_w, H, B_.qkv, ldq, FO1_BF16, rows, ldq, H, L.qkv_b, FO1_BF16, FO1_EPI_NONE, nullptr, 0, 0, s));
-  FO1_RUN(mrope_apply(B_.qkv, B_.qkv + QD, ldq, pos3, rows, c.llm_heads, c.llm_kv_heads, hd, c.mrope_section[0], c.mrope_section[1],
-                      c.mrope_section[2], c.rope_theta, s));
+  FO1_RUN(rope_apply(B_.qkv, ldq, cs, rows, c.llm_heads + c.llm_kv_heads, hd, s));   // q|k heads are contiguous in the packed row
   if (prefill) {
     if (!dry) {
       kv_store_kernel<<<rows, 128, 0, s>>>(B_.qkv, ldq, QD, KD, d_row_seq, d_row_t, kc, vc, m->kv_cap);
@@ -363,14 +390,16 @@ static int llm_layer(Model* m, int li, const bf16* x_in, bf16* x_out, const Laye
   } else if (!dry) {
     kv_append_kernel<<<rows, 128, 0, s>>>(B_.qkv, ldq, QD, KD, st->cache_len, kc, vc, m->kv_cap);
     FO1_LAUNCH_CHECK();
-    dim3 grid(rows, c.llm_kv_heads);
+    dim3 grid(rows, c.llm_kv_heads, kDecSplits);
     const int G = c.llm_heads / c.llm_kv_heads;
     const float scale = 1.0f / sqrtf((float)hd);
-    if (G == 8) decode_attn_kernel<8><<<grid, 256, 0, s>>>(B_.qkv, ldq, kc, vc, st->cache_len, m->kv_cap, c.llm_kv_heads, B_.att, QD, scale);
-    else if (G == 4) decode_attn_kernel<4><<<grid, 256, 0, s>>>(B_.qkv, ldq, kc, vc, st->cache_len, m->kv_cap, c.llm_kv_heads, B_.att, QD, scale);
-    else if (G == 2) decode_attn_kernel<2><<<grid, 256, 0, s>>>(B_.qkv, ldq, kc, vc, st->cache_len, m->kv_cap, c.llm_kv_heads, B_.att, QD, scale);
-    else if (G == 1) decode_attn_kernel<1><<<grid, 256, 0, s>>>(B_.qkv, ldq, kc, vc, st->cache_len, m->kv_cap, c.llm_kv_heads, B_.att, QD, scale);
+    if (G == 8) decode_attn_kernel<8><<<grid, 256, 0, s>>>(B_.qkv, ldq, kc, vc, st->cache_len, m->kv_cap, c.llm_kv_heads, B_.dec_part, scale);
+    else if (G == 4) decode_attn_kernel<4><<<grid, 256, 0, s>>>(B_.qkv, ldq, kc, vc, st->cache_len, m->kv_cap, c.llm_kv_heads, B_.dec_part, scale);
+    else if (G == 2) decode_attn_kernel<2><<<grid, 256, 0, s>>>(B_.qkv, ldq, kc, vc, st->cache_len, m->kv_cap, c.llm_kv_heads, B_.dec_part, scale);
+    else if (G == 1) decode_attn_kernel<1><<<grid, 256, 0, s>>>(B_.qkv, ldq, kc, vc, st->cache_len, m->kv_cap, c.llm_kv_heads, B_.dec_part, scale);
     else { set_error("decode attention: GQA group %d unsupported", G); return FO1_ERR_UNSUPPORTED; }
+    FO1_LAUNCH_CHECK();
+    decode_attn_combine_kernel<<<dim3(rows, c.llm_heads), 128, 0, s>>>(B_.dec_part, B_.att, QD, c.llm_heads);
     FO1_LAUNCH_CHECK();
   }
   FO1_RUN(linear(B_.att, QD, L.o_w, QD, B_.x_mid, H, FO1_BF16, rows, H, QD, nullptr, 0, FO1_EPI_NONE, x_in, H, 0, s));
@@ -399,6 +428,9 @@ static int llm_generate_impl(Model* m, fo1_generate_desc* d, cudaStream_t s, boo
   buf.att = A.alloc<bf16>((size_t)R * QD);
   buf.x_mid = A.alloc<bf16>((size_t)R * H);
   buf.h = A.alloc<bf16>((size_t)R * Ip);
+  float* cs_pre = A.alloc<float>((size_t)R * hd);
+  float* cs_dec = A.alloc<float>((size_t)B * hd);
+  buf.dec_part = A.alloc<float>((size_t)B * c.llm_heads * kDecSplits * (128 + 4));
   bf16* last = A.alloc<bf16>((size_t)B * H);
   bf16* lastn = A.alloc<bf16>((size_t)B * H);
   float* logits = A.alloc<float>((size_t)B * V);
@@ -428,9 +460,10 @@ static int llm_generate_impl(Model* m, fo1_generate_desc* d, cudaStream_t s, boo
 
   // ---- prefill ----
   const bf16* x = static_cast<const bf16*>(d->inputs_embeds);
+  FO1_RUN(mrope_table(d->position_ids, cs_pre, (int)T, hd, c.mrope_section[0], c.mrope_section[1], c.mrope_section[2], c.rope_theta, s));
   for (int li = 0; li < c.llm_layers; ++li) {
     bf16* xo = (li & 1) ? xb : xa;
-    FO1_TRY(llm_layer(m, li, x, xo, buf, (int)T, d->position_ids, true, d_cu, B, max_len, d_row_seq, d_row_t, nullptr, s, dry));
+    FO1_TRY(llm_layer(m, li, x, xo, buf, (int)T, cs_pre, true, d_cu, B, max_len, d_row_seq, d_row_t, nullptr, s, dry));
     x = xo;
   }
   if (d->all_logits) {
@@ -457,10 +490,11 @@ static int llm_generate_impl(Model* m, fo1_generate_desc* d, cudaStream_t s, boo
   auto enqueue_step = [&]() -> int {
     embed_tokens_kernel<<<B, 256, 0, s>>>(st.cur_tok, m->llm.embed, xa, H);
     FO1_LAUNCH_CHECK();
+    FO1_TRY(mrope_table(st.pos3, cs_dec, B, hd, c.mrope_section[0], c.mrope_section[1], c.mrope_section[2], c.rope_theta, s));
     const bf16* xin = xa;
     for (int li = 0; li < c.llm_layers; ++li) {
       bf16* xo = (li & 1) ? xa : xb;
-      FO1_TRY(llm_layer(m, li, xin, xo, buf, B, st.pos3, false, nullptr, B, 0, nullptr, nullptr, &st, s, false));
+      FO1_TRY(llm_layer(m, li, xin, xo, buf, B, cs_dec, false, nullptr, B, 0, nullptr, nullptr, &st, s, false));
       xin = xo;
     }
     FO1_TRY(rmsnorm(xin, H, m->llm.norm, lastn, H, B, H, c.rms_eps, s));
@@ -478,7 +512,7 @@ static int llm_generate_impl(Model* m, fo1_generate_desc* d, cudaStream_t s, boo
   for (int step = 1; step < d->max_new_tokens; ++step) {
     if (gexec != nullptr) {
       if (cudaGraphLaunch(gexec, s) != cudaSuccess) { set_error("cudaGraphLaunch failed: %s", cudaGetErrorString(cudaGetLastError())); rc = FO1_ERR_CUDA; break; }
-      count_launch((uint64_t)c.llm_layers * 10 + 5);
+      count_launch((uint64_t)c.llm_layers * 11 + 5);
     } else if (want_graph && step == 2) {
       cudaGraph_t graph = nullptr;
       if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {

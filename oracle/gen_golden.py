@@ -411,6 +411,77 @@ def gen_llm() -> None:
 STAGES.update({"llm": gen_llm})
 
 
+def gen_mm_utils() -> None:
+    """Pins the boundary mirror vlm_fo1/mm_utils.py: the REFERENCE's own prepare_inputs / extract_predictions_* /
+    adjust_bbox run on a fabricated byte-level tokenizer + this repo's processors (loaded by file path)."""
+    import importlib.util, json, tempfile
+    from types import SimpleNamespace as NS
+    from PIL import Image
+    if ref_shim.REFERENCE_ROOT not in sys.path:
+        sys.path.insert(0, ref_shim.REFERENCE_ROOT)
+    for k in [k for k in sys.modules if k == "vlm_fo1" or k.startswith("vlm_fo1.")]:
+        del sys.modules[k]
+    import vlm_fo1.mm_utils as RMU            # the reference's
+    from vlm_fo1.task_templates import OD_template, OD_Counting_template
+    assert RMU.__file__.startswith(ref_shim.REFERENCE_ROOT), RMU.__file__
+
+    def load_by_path(name, rel):
+        spec = importlib.util.spec_from_file_location(name, os.path.join(REPO, rel))
+        m = importlib.util.module_from_spec(spec); spec.loader.exec_module(m); return m
+    sys.path.insert(0, REPO)   # for `vlm-fo1_b200` only; `vlm_fo1` is already bound to the reference in sys.modules
+    fo1 = __import__("importlib").import_module("vlm-fo1_b200.fabricate")
+    PR = load_by_path("fo1_processors", "vlm_fo1/processors.py")
+    d = os.path.join(tempfile.mkdtemp(), "VLM-FO1_Qwen2.5-VL-3B-v01"); os.makedirs(d)
+    fo1.write_tokenizer(d)
+    from transformers import AutoTokenizer
+    tok = AutoTokenizer.from_pretrained(d, use_fast=False)
+    procs = (PR.PrimaryImageProcessor(), PR.AuxImageProcessor(768, "dynamic"))
+    model = NS(config=NS(mm_use_region_index_token=True))
+    rng = np.random.default_rng(7)
+    out = {}
+    cases = []
+    img_a = os.path.join(d, "a.png"); Image.fromarray(rng.integers(0, 256, (399, 500, 3), dtype=np.uint8)).save(img_a)
+    img_b = os.path.join(d, "b.png"); Image.fromarray(rng.integers(0, 256, (2300, 1200, 3), dtype=np.uint8)).save(img_b)   # long edge > 2048
+    boxes7 = [[161.0, 11.0, 292.0, 127.0], [268.0, 61.0, 428.0, 226.0], [12.0, 100.0, 140.0, 227.0], [205.0, 188.0, 332.0, 320.0],
+              [326.0, 202.0, 478.0, 357.0], [136.0, 106.0, 269.0, 233.0], [25.0, 206.0, 200.0, 383.0]]
+    boxes_out = [[-5.0, -3.0, 600.0, 500.0], [10.5, 20.25, 30.75, 41.0]]
+    many = [[float(i), float(i), float(i + 20), float(i + 30)] for i in range(130)]
+    specs = [("demo", img_a, boxes7, OD_template.format("orange"), None),
+             ("clamp", img_a, boxes_out, OD_Counting_template.format("cats"), None),
+             ("cap100", img_a, many, OD_template.format("things"), None),
+             ("big", img_b, boxes7, OD_template.format("person"), None),
+             # ("noboxes", ...): the reference itself crashes on a message without bbox_list (torch.tensor(None), mm_utils.py:396)
+             ("system", img_a, boxes7[:2], OD_template.format("x"), "You are terse.")]
+    for tag, img, boxes, text, system in specs:
+        msgs = []
+        if system:
+            msgs.append({"role": "system", "content": system})
+        m = {"role": "user", "content": [{"type": "image_url", "image_url": {"url": img}}, {"type": "text", "text": text}]}
+        if boxes is not None:
+            m["bbox_list"] = [list(b) for b in boxes]
+        msgs.append(m)
+        kw = RMU.prepare_inputs(d, model, procs, tok, msgs, device="cpu", max_tokens=64)
+        out[f"{tag}_inputs"] = kw["inputs"].numpy()
+        out[f"{tag}_grid"] = kw["image_grid_thws"][0].numpy()
+        out[f"{tag}_aux_shape"] = np.array(kw["images_aux"][0].shape)
+        out[f"{tag}_px_sum"] = np.array(float(kw["images"][0].double().sum()))
+        out[f"{tag}_aux_sum"] = np.array(float(kw["images_aux"][0].double().sum()))
+        out[f"{tag}_boxes"] = kw["bbox_list"][0].numpy() if kw["bbox_list"] else np.zeros((0, 4), np.float32)
+        out[f"{tag}_stop"] = np.array([int(k.item()) for k in kw["stopping_criteria"][0].keyword_ids if k.numel() == 1])
+        cases.append(dict(tag=tag, img=os.path.basename(img), boxes=boxes, text=text, system=system))
+    pred = "<ground>orange</ground><objects><region1><region4><region1></objects> and <ground> cat </ground><objects><region0></objects><ground>orange</ground><objects><region6></objects>"
+    idx = RMU.extract_predictions_to_indexes(pred)
+    bxs = RMU.extract_predictions_to_bboxes(pred, boxes7)
+    out["parse_json"] = np.frombuffer(json.dumps({"pred": pred, "indexes": {k: sorted(v) for k, v in idx.items()},
+                                                  "bboxes": {k: sorted(v) for k, v in bxs.items()}}).encode(), dtype=np.uint8)
+    out["cases_json"] = np.frombuffer(json.dumps(cases).encode(), dtype=np.uint8)
+    out["img_a"] = np.asarray(Image.open(img_a)); out["img_b_seed"] = np.array(7)
+    save("mm_utils", **out)
+
+
+STAGES.update({"mm_utils": gen_mm_utils})
+
+
 if __name__ == "__main__":
     torch.set_grad_enabled(False)
     wanted = sys.argv[1:] or list(STAGES)

@@ -27,7 +27,8 @@ namespace fo1 {
 constexpr int BM = 128;
 constexpr int BK = 64;  // 64 bf16 = 128 B = one swizzle atom row
 constexpr int UMMA_K = 16;
-constexpr int kGemmThreads = 192;
+constexpr int kGemmThreads = 320;   // warp 0: TMA, warp 1: MMA, warps 2-9: epilogue (two per TMEM lane quarter)
+constexpr int kEpiThreads = 256;
 
 struct GemmArgs {
   int M, N, K;
@@ -55,6 +56,31 @@ struct GemmCfg {
 __device__ __forceinline__ float load_bias(const void* bias, int dtype, int n) {
   return dtype == FO1_F32 ? __ldg(static_cast<const float*>(bias) + n)
                           : __bfloat162float(__ldg(static_cast<const __nv_bfloat16*>(bias) + n));
+}
+// v[0..31] += bias[n .. n+31]  (16-byte vector loads when the 32 columns are in range, scalar tail otherwise)
+__device__ __forceinline__ void add_bias32(float (&v)[32], const void* bias, int dtype, int n, int n_limit) {
+  if (n + 32 <= n_limit) {
+    if (dtype == FO1_F32) {
+      const float4* b = reinterpret_cast<const float4*>(static_cast<const float*>(bias) + n);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) {
+        const float4 t = __ldg(b + q);
+        v[q * 4] += t.x; v[q * 4 + 1] += t.y; v[q * 4 + 2] += t.z; v[q * 4 + 3] += t.w;
+      }
+    } else {
+      const uint4* b = reinterpret_cast<const uint4*>(static_cast<const __nv_bfloat16*>(bias) + n);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint4 t = __ldg(b + q);
+        v[q * 8 + 0] += bf16_lo(t.x); v[q * 8 + 1] += bf16_hi(t.x); v[q * 8 + 2] += bf16_lo(t.y); v[q * 8 + 3] += bf16_hi(t.y);
+        v[q * 8 + 4] += bf16_lo(t.z); v[q * 8 + 5] += bf16_hi(t.z); v[q * 8 + 6] += bf16_lo(t.w); v[q * 8 + 7] += bf16_hi(t.w);
+      }
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      if (n + j < n_limit) v[j] += load_bias(bias, dtype, n + j);
+  }
 }
 __device__ __forceinline__ float apply_act(float x, int act) {
   if (act == FO1_EPI_GELU) return gelu_erf(x);
@@ -145,7 +171,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(ptx::smem_u32(tmem_full + a), 1);
-      ptx::mbar_init(ptx::smem_u32(tmem_empty + a), 4);  // one arrive per epilogue warp
+      ptx::mbar_init(ptx::smem_u32(tmem_empty + a), kEpiThreads / 32);  // one arrive per epilogue warp
     }
     ptx::mbar_fence_init();
   }
@@ -206,7 +232,13 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     }
   } else {
     // ======================================= epilogue ========================================
-    const int quarter = warp & 3;  // TMEM lane quarter this warp may read
+    const int quarter = warp & 3;          // TMEM lane quarter this warp may read (hardware rule: warp id mod 4)
+    const int half = (warp - 2) >> 2;      // two warps share a quarter: each owns one half of the tile's columns
+    // column range of this warp: plain / split-K work in 32-column units, the gated epilogue in 64-column pairs;
+    // tiles too narrow to split leave the second warp of a quarter idle (it still takes part in the barriers)
+    constexpr bool kSplit32 = BN >= 64, kSplit64 = BN >= 128;
+    const int p_beg = kSplit32 ? half * (BN / 2) : 0, p_end = kSplit32 ? (half + 1) * (BN / 2) : (half == 0 ? BN : 0);
+    const int g_beg = kSplit64 ? half * (BN / 2) : 0, g_end = kSplit64 ? (half + 1) * (BN / 2) : (half == 0 ? BN : 0);
     uint32_t tcount = 0;
     for (int work = blockIdx.x; work < num_tiles; work += gridDim.x, ++tcount) {
       const int tile = work / g.ksplit, split = work - tile * g.ksplit;
@@ -221,7 +253,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         // ---- split-K: park the fp32 partial, the last split to arrive reduces + finishes the tile ----
         float* part = g.ws + ((long long)(tile * g.ksplit + split) * BM + quarter * 32 + lane) * BN;
 #pragma unroll 1
-        for (int c = 0; c < BN; c += 32) {
+        for (int c = p_beg; c < p_end; c += 32) {
           uint32_t r[32];
           ptx::tmem_ld_32x32(taddr + c, r);
           ptx::tmem_ld_wait();
@@ -236,15 +268,15 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         __syncwarp();
         if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(tmem_empty + acc));   // TMEM is free again: the MMA warp moves on
         __threadfence();
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
         if (warp == 2 && lane == 0) *last_flag = (atomicAdd(g.counters + tile, 1) == g.ksplit - 1) ? 1 : 0;
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        asm volatile("bar.sync 1, 256;" ::: "memory");
         if (*last_flag) {
           __threadfence();
           if (m < g.M) {
             const float* p0 = g.ws + ((long long)tile * g.ksplit * BM + quarter * 32 + lane) * BN;
 #pragma unroll 1
-            for (int c = 0; c < BN; c += 32) {
+            for (int c = p_beg; c < p_end; c += 32) {
               if (n0 + c >= g.N) break;
               float v[32];
 #pragma unroll
@@ -257,11 +289,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
                   v[q * 4] += t.x; v[q * 4 + 1] += t.y; v[q * 4 + 2] += t.z; v[q * 4 + 3] += t.w;
                 }
               }
-              if (g.bias != nullptr) {
-#pragma unroll
-                for (int j = 0; j < 32; ++j)
-                  if (n0 + c + j < g.N) v[j] += load_bias(g.bias, g.bias_dtype, n0 + c + j);
-              }
+              if (g.bias != nullptr) add_bias32(v, g.bias, g.bias_dtype, n0 + c, g.N);
               if (g.act != FO1_EPI_NONE) {
 #pragma unroll
                 for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], g.act);
@@ -271,24 +299,26 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           }
           if (warp == 2 && lane == 0) g.counters[tile] = 0;   // self-cleaning for the next launch
         }
-        asm volatile("bar.sync 1, 128;" ::: "memory");   // last_flag is reused by the next work item
+        asm volatile("bar.sync 1, 256;" ::: "memory");   // last_flag is reused by the next work item
         continue;
       }
       if (!g.gated) {
-#pragma unroll 1
-        for (int c = 0; c < BN; c += 32) {
-          if (n0 + c >= g.N) break;  // warp-uniform
-          uint32_t r[32];
-          ptx::tmem_ld_32x32(taddr + c, r);
+        // software pipeline: the TMEM load of chunk c+1 is in flight while chunk c is converted and stored
+        constexpr int NCH = (kSplit32 ? BN / 2 : BN) / 32;
+        uint32_t r[2][32];
+        const int cbeg = p_beg;
+        const bool worker = p_end > p_beg;
+        if (worker && n0 + cbeg < g.N) ptx::tmem_ld_32x32(taddr + cbeg, r[0]);
+#pragma unroll
+        for (int ci = 0; ci < NCH; ++ci) {
+          const int c = cbeg + ci * 32;
+          if (!worker || n0 + c >= g.N) break;  // warp-uniform
           ptx::tmem_ld_wait();
           float v[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
-          if (g.bias != nullptr) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (n0 + c + j < g.N) v[j] += load_bias(g.bias, g.bias_dtype, n0 + c + j);
-          }
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[ci & 1][j]);
+          if (ci + 1 < NCH && n0 + c + 32 < g.N) ptx::tmem_ld_32x32(taddr + c + 32, r[(ci + 1) & 1]);
+          if (g.bias != nullptr) add_bias32(v, g.bias, g.bias_dtype, n0 + c, g.N);
           if (g.act != FO1_EPI_NONE) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], g.act);
@@ -298,22 +328,21 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       } else {
         // W rows interleave [32 gate | 32 up] blocks: out[:, (n0+c)/2 + j] = act(gate_j) * up_j
 #pragma unroll 1
-        for (int c = 0; c < BN; c += 64) {
+        for (int c = g_beg; c < g_end; c += 64) {
           if (n0 + c >= g.N) break;
           uint32_t rg[32], ru[32];
           ptx::tmem_ld_32x32(taddr + c, rg);
           ptx::tmem_ld_32x32(taddr + c + 32, ru);
           ptx::tmem_ld_wait();
-          float v[32];
+          float gt[32], v[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float gt = __uint_as_float(rg[j]), up = __uint_as_float(ru[j]);
-            if (g.bias != nullptr && n0 + c + 32 + j < g.N) {
-              gt += load_bias(g.bias, g.bias_dtype, n0 + c + j);
-              up += load_bias(g.bias, g.bias_dtype, n0 + c + 32 + j);
-            }
-            v[j] = apply_act(gt, g.act) * up;
+          for (int j = 0; j < 32; ++j) { gt[j] = __uint_as_float(rg[j]); v[j] = __uint_as_float(ru[j]); }
+          if (g.bias != nullptr) {
+            add_bias32(gt, g.bias, g.bias_dtype, n0 + c, g.N);
+            add_bias32(v, g.bias, g.bias_dtype, n0 + c + 32, g.N);
           }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = apply_act(gt[j], g.act) * v[j];
           if (m < g.M) store_row32(g, v, m, (n0 + c) >> 1, g.N >> 1);
         }
       }

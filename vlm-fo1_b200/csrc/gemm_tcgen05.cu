@@ -41,6 +41,7 @@ struct GemmArgs {
   // split-K (skinny problems): work item = (tile, split); partial sums meet in `ws`, the last CTA to arrive on
   // `counters[tile]` reduces them in split order (deterministic) and runs the epilogue
   int ksplit, kb_per_split;
+  int stage_tx;   // bytes one ring stage receives (A box rows x 128 B + BN x 128 B): skinny problems load only the live A rows
   float* ws;
   int* counters;
 };
@@ -194,7 +195,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           const uint32_t s = it % S, ph = (it / S) & 1;
           ptx::mbar_wait(ptx::smem_u32(empty_bar + s), ph ^ 1);
           const uint32_t fb = ptx::smem_u32(full_bar + s);
-          ptx::mbar_expect_tx(fb, Cfg::kStageBytes);
+          ptx::mbar_expect_tx(fb, (uint32_t)g.stage_tx);
           ptx::tma_load_2d(ptx::smem_u32(smem_a + s * (BM * BK * 2)), &tmA, fb, kb * BK, m0);
           ptx::tma_load_2d(ptx::smem_u32(smem_b + s * (BN * BK * 2)), &tmW, fb, kb * BK, n0);
         }
@@ -443,7 +444,10 @@ static int launch_gemm(const fo1_gemm_desc* d, cudaStream_t stream, int ksplit =
     attr_set = true;
   }
   CUtensorMap tmA, tmW;
-  FO1_TRY(make_tmap_2d_bf16(&tmA, d->A, (uint64_t)d->K, (uint64_t)d->M, (uint64_t)d->lda, BK, BM));
+  // one m-tile only (decode: M = batch): fetch just the live rows of A, rounded to the 8-row swizzle atom; the UMMA
+  // still multiplies all 128 smem rows, rows >= M hold stale data whose results are never stored
+  const int a_rows = d->M < BM ? ((d->M + 7) & ~7) : BM;
+  FO1_TRY(make_tmap_2d_bf16(&tmA, d->A, (uint64_t)d->K, (uint64_t)d->M, (uint64_t)d->lda, BK, a_rows));
   FO1_TRY(make_tmap_2d_bf16(&tmW, d->W, (uint64_t)d->K, (uint64_t)d->N, (uint64_t)d->ldw, BK, BN));
   GemmArgs g;
   g.M = d->M; g.N = d->N; g.K = d->K;
@@ -454,6 +458,7 @@ static int launch_gemm(const fo1_gemm_desc* d, cudaStream_t stream, int ksplit =
   g.gated = d->gated;
   g.tiles_m = ceil_div(d->M, BM);
   g.tiles_n = ceil_div(d->N, BN);
+  g.stage_tx = (a_rows + BN) * BK * 2;
   const int num_kb = ceil_div(d->K, BK);
   g.kb_per_split = ceil_div(num_kb, ksplit);
   g.ksplit = ceil_div(num_kb, g.kb_per_split);   // every split owns at least one k-block
@@ -501,7 +506,9 @@ int gemm_bf16(const fo1_gemm_desc* d, cudaStream_t stream) {
   // pulls weights (>= 8 k-blocks per split so the ring still fills)
   const long long t32 = tm * ceil_div(d->N, 32);
   int ks = 1;
-  if (t32 < sms) ks = (int)std::min<long long>(std::min<long long>(8, ceil_div(sms, (int)t32)), std::max(1, ceil_div(d->K, BK) / 8));
+  if (t32 * 2 <= sms) {   // split K only while (tiles x splits) still fits one wave: a second round doubles the latency
+    ks = (int)std::min<long long>(std::min<long long>(8, sms / t32), std::max(1, ceil_div(d->K, BK) / 8));
+  }
   return launch_gemm<32>(d, stream, ks);
 }
 

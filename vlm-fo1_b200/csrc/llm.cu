@@ -391,6 +391,7 @@ static int llm_layer(Model* m, int li, const bf16* x_in, bf16* x_out, const Laye
     kv_append_kernel<<<rows, 128, 0, s>>>(B_.qkv, ldq, QD, KD, st->cache_len, kc, vc, m->kv_cap);
     FO1_LAUNCH_CHECK();
     dim3 grid(rows, c.llm_kv_heads, kDecSplits);
+    ProfScope prof("decode_attn", 0.0, 0.0, s);
     const int G = c.llm_heads / c.llm_kv_heads;
     const float scale = 1.0f / sqrtf((float)hd);
     if (G == 8) decode_attn_kernel<8><<<grid, 256, 0, s>>>(B_.qkv, ldq, kc, vc, st->cache_len, m->kv_cap, c.llm_kv_heads, B_.dec_part, scale);

@@ -288,8 +288,14 @@ def main():
     if rank == 0:
         # ---- one extra instrumented step: per-kernel CUDA-event times for the roofline objects ----
         peaks = load_peaks()
+        # (rank-0-only passes must not contain the collective: the other ranks are already at the final barrier)
+        local_step = lambda: pipe.generate(resident, T, stop_ids=[], early_exit_interval=0)
+        pipe.profile_stages = True
+        local_step()
+        line["stage_ms"] = pipe.stage_ms()          # un-instrumented kernels, CUDA events between the stages
+        pipe.profile_stages = False
         L.fo1_profile_enable(1)
-        step(resident)
+        local_step()
         buf = (__import__("ctypes").c_char * (1 << 20))()
         L.fo1_profile_collect(buf, 1 << 20)
         L.fo1_profile_enable(0)

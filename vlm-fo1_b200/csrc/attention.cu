@@ -35,30 +35,31 @@ __device__ __forceinline__ void mma_bf16(float (&c)[4], const uint32_t (&a)[4], 
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-constexpr int kAttnThreads = 128;
-constexpr int kTileM = 64, kTileN = 64;
+constexpr int kTileN = 64;   // keys per iteration; queries per CTA = 16 x WARPS (64 for windows, 128 for long sequences)
 
 // copy `rows_valid` rows of HD bf16 (zero-fill up to 64 rows) into a padded smem tile
-template <int HD>
+template <int HD, int ROWS, int THREADS>
 __device__ __forceinline__ void load_tile_async(bf16* dst, const bf16* src, long long ld, int rows_valid) {
   constexpr int PITCH = HD + 8;
   constexpr int CHUNKS = HD / 8;  // 16-byte chunks per row
-  for (int i = threadIdx.x; i < 64 * CHUNKS; i += kAttnThreads) {
+  for (int i = threadIdx.x; i < ROWS * CHUNKS; i += THREADS) {
     const int r = i / CHUNKS, c = i - r * CHUNKS;
     const bool ok = r < rows_valid;
     cp_async16(dst + r * PITCH + c * 8, src + (long long)(ok ? r : 0) * ld + c * 8, ok);
   }
 }
 
-template <int HD, bool CAUSAL>
-__global__ void __launch_bounds__(kAttnThreads) attn_varlen_kernel(const AttnArgs a) {
+template <int HD, bool CAUSAL, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32) attn_varlen_kernel(const AttnArgs a) {
   constexpr int PITCH = HD + 8;
   constexpr int TILE = 64 * PITCH;
+  constexpr int kTileM = 16 * WARPS, kAttnThreads = WARPS * 32;
+  constexpr int QTILE = kTileM * PITCH;
   constexpr int KC = HD / 16;  // k-chunks of the QK^T contraction == d-tile pairs of the PV product
   extern __shared__ __align__(16) bf16 smem_attn[];
   bf16* sQ = smem_attn;
-  bf16* sK = smem_attn + TILE;      // 2 buffers
-  bf16* sV = smem_attn + 3 * TILE;  // 2 buffers
+  bf16* sK = smem_attn + QTILE;             // 2 buffers
+  bf16* sV = smem_attn + QTILE + 2 * TILE;  // 2 buffers
 
   const int seq = blockIdx.y, head = blockIdx.z;
   const int kvh = head / (a.q_heads / a.kv_heads);
@@ -70,15 +71,15 @@ __global__ void __launch_bounds__(kAttnThreads) attn_varlen_kernel(const AttnArg
   const int g = lane >> 2, t = lane & 3;
 
   int n_kv = (len + kTileN - 1) / kTileN;
-  if (CAUSAL) n_kv = min(n_kv, (int)blockIdx.x + 1);
+  if (CAUSAL) n_kv = min(n_kv, (q0 + kTileM + kTileN - 1) / kTileN);
 
   const bf16* qp = a.q + (long long)(s0 + q0) * a.ldq + (long long)head * HD;
   const bf16* kp = a.k + (long long)s0 * a.ldk + (long long)kvh * HD;
   const bf16* vp = a.v + (long long)s0 * a.ldv + (long long)kvh * HD;
 
-  load_tile_async<HD>(sQ, qp, a.ldq, min(64, len - q0));
-  load_tile_async<HD>(sK, kp, a.ldk, min(64, len));
-  load_tile_async<HD>(sV, vp, a.ldv, min(64, len));
+  load_tile_async<HD, kTileM, kAttnThreads>(sQ, qp, a.ldq, min(kTileM, len - q0));
+  load_tile_async<HD, 64, kAttnThreads>(sK, kp, a.ldk, min(64, len));
+  load_tile_async<HD, 64, kAttnThreads>(sV, vp, a.ldv, min(64, len));
   cp_async_commit();
 
   uint32_t qf[KC][4];
@@ -92,8 +93,8 @@ __global__ void __launch_bounds__(kAttnThreads) attn_varlen_kernel(const AttnArg
     const int buf = j & 1;
     if (j + 1 < n_kv) {
       const int k0 = (j + 1) * kTileN;
-      load_tile_async<HD>(sK + (buf ^ 1) * TILE, kp + (long long)k0 * a.ldk, a.ldk, min(64, len - k0));
-      load_tile_async<HD>(sV + (buf ^ 1) * TILE, vp + (long long)k0 * a.ldv, a.ldv, min(64, len - k0));
+      load_tile_async<HD, 64, kAttnThreads>(sK + (buf ^ 1) * TILE, kp + (long long)k0 * a.ldk, a.ldk, min(64, len - k0));
+      load_tile_async<HD, 64, kAttnThreads>(sV + (buf ^ 1) * TILE, vp + (long long)k0 * a.ldv, a.ldv, min(64, len - k0));
       cp_async_commit();
       cp_async_wait<1>();
     } else {
@@ -214,19 +215,19 @@ __global__ void __launch_bounds__(kAttnThreads) attn_varlen_kernel(const AttnArg
   }
 }
 
-template <int HD>
+template <int HD, int WARPS>
 static int launch_attn(const AttnArgs& a, cudaStream_t s) {
-  constexpr int smem = 5 * 64 * (HD + 8) * 2;
-  dim3 grid(ceil_div(a.max_seqlen, kTileM), a.n_seqs, a.q_heads);
+  constexpr int smem = (16 * WARPS + 4 * 64) * (HD + 8) * 2;
+  dim3 grid(ceil_div(a.max_seqlen, 16 * WARPS), a.n_seqs, a.q_heads);
   ProfScope prof(a.causal ? "attn_causal" : "attn", 0.0, 0.0, s);
   if (a.causal) {
     static bool set = false;
-    if (!set) { FO1_CUDA(cudaFuncSetAttribute(attn_varlen_kernel<HD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); set = true; }
-    attn_varlen_kernel<HD, true><<<grid, kAttnThreads, smem, s>>>(a);
+    if (!set) { FO1_CUDA(cudaFuncSetAttribute(attn_varlen_kernel<HD, true, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); set = true; }
+    attn_varlen_kernel<HD, true, WARPS><<<grid, WARPS * 32, smem, s>>>(a);
   } else {
     static bool set = false;
-    if (!set) { FO1_CUDA(cudaFuncSetAttribute(attn_varlen_kernel<HD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); set = true; }
-    attn_varlen_kernel<HD, false><<<grid, kAttnThreads, smem, s>>>(a);
+    if (!set) { FO1_CUDA(cudaFuncSetAttribute(attn_varlen_kernel<HD, false, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)); set = true; }
+    attn_varlen_kernel<HD, false, WARPS><<<grid, WARPS * 32, smem, s>>>(a);
   }
   FO1_LAUNCH_CHECK();
   return FO1_OK;
@@ -238,10 +239,11 @@ int attention_varlen(const AttnArgs& a, cudaStream_t s) {
   FO1_CHECK_ARG((a.ldq % 8) == 0 && (a.ldk % 8) == 0 && (a.ldv % 8) == 0 && (a.ldo % 8) == 0, "attention: pitches must be multiples of 8");
   if (a.n_seqs == 0 || a.max_seqlen == 0) return FO1_OK;
   FO1_CHECK_ARG(a.n_seqs <= 65535 && a.q_heads <= 65535, "attention: grid too large (%d seqs, %d heads)", a.n_seqs, a.q_heads);
+  const bool long_seq = a.max_seqlen >= 512;   // 128-query tiles halve the K/V re-reads of long sequences
   switch (a.head_dim) {
-    case 32: return launch_attn<32>(a, s);
-    case 80: return launch_attn<80>(a, s);
-    case 128: return launch_attn<128>(a, s);
+    case 32: return launch_attn<32, 4>(a, s);
+    case 80: return long_seq ? launch_attn<80, 8>(a, s) : launch_attn<80, 4>(a, s);
+    case 128: return long_seq ? launch_attn<128, 8>(a, s) : launch_attn<128, 4>(a, s);
     default:
       set_error("attention: head_dim %d unsupported (32, 80, 128)", a.head_dim);
       return FO1_ERR_UNSUPPORTED;

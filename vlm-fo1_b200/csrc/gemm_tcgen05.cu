@@ -41,6 +41,7 @@ struct GemmArgs {
   // split-K (skinny problems): work item = (tile, split); partial sums meet in `ws`, the last CTA to arrive on
   // `counters[tile]` reduces them in split order (deterministic) and runs the epilogue
   int ksplit, kb_per_split;
+  int coalesce;   // 1: epilogue stages rows through shared memory and writes full 128-byte lines (needs 16-byte aligned D / residual rows)
   int stage_tx;   // bytes one ring stage receives (A box rows x 128 B + BN x 128 B): skinny problems load only the live A rows
   float* ws;
   int* counters;
@@ -51,7 +52,8 @@ struct GemmCfg {
   static constexpr int kStageBytes = (BM * BK + BN * BK) * 2;
   static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : (BN == 64 ? 8 : 10));
   static constexpr int kTmemCols = 2 * BN;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kStagingBytes = 8 * 4096;   // epilogue: 32 rows x 128 B per epilogue warp
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + kStagingBytes;
 };
 
 __device__ __forceinline__ float load_bias(const void* bias, int dtype, int n) {
@@ -140,6 +142,77 @@ __device__ __forceinline__ void store_row32(const GemmArgs& g, float (&v)[32], i
   }
 }
 
+
+// ---- coalesced epilogue stores -----------------------------------------------------------------------------
+// tcgen05.ld hands every thread ONE accumulator row (32 consecutive columns): storing from there makes each warp
+// store touch 32 different rows, 16 bytes each -- fine for compute-bound shapes, ruinous for the memory-bound ones
+// (DaViT stage 0: M = 1.6 M rows, K = 256 ran at 0.48 TB/s).  Instead each epilogue warp parks its 32 x 128 B block
+// in shared memory (16-byte slots XOR-swizzled by row, conflict-free both ways) and writes it back row-contiguously:
+// one instruction = 4 rows x 128 B (or 8 rows x 64 B), the residual is read the same way.
+__device__ __forceinline__ void stage_put16(uint8_t* stg, int row, int slot, uint4 v) {
+  *reinterpret_cast<uint4*>(stg + row * 128 + ((slot ^ (row & 7)) << 4)) = v;
+}
+__device__ __forceinline__ uint4 stage_get16(const uint8_t* stg, int row, int slot) {
+  return *reinterpret_cast<const uint4*>(stg + row * 128 + ((slot ^ (row & 7)) << 4));
+}
+// park 32 finished values of this thread's row as bf16 (4 slots) or fp32 (8 slots) starting at slot0
+__device__ __forceinline__ void stage_row32(uint8_t* stg, int lane, int slot0, const float (&v)[32], bool bf16_out) {
+  if (bf16_out) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      stage_put16(stg, lane, slot0 + q, make_uint4(pack_bf16(v[q * 8], v[q * 8 + 1]), pack_bf16(v[q * 8 + 2], v[q * 8 + 3]),
+                                                    pack_bf16(v[q * 8 + 4], v[q * 8 + 5]), pack_bf16(v[q * 8 + 6], v[q * 8 + 7])));
+  } else {
+#pragma unroll
+    for (int q = 0; q < 8; ++q)
+      stage_put16(stg, lane, q, make_uint4(__float_as_uint(v[q * 4]), __float_as_uint(v[q * 4 + 1]), __float_as_uint(v[q * 4 + 2]),
+                                            __float_as_uint(v[q * 4 + 3])));
+  }
+}
+// write `segs` 16-byte slots per row of the parked block to D[m_base + row][col0 ...] (+ residual), n_limit = valid columns
+__device__ __forceinline__ void flush_rows(const GemmArgs& g, const uint8_t* stg, int lane, int segs, int m_base, int col0, int n_limit) {
+  __syncwarp();
+  const bool bf16_out = g.d_dtype == FO1_BF16;
+  const int epp = bf16_out ? 8 : 4;                // elements per 16-byte slot
+  const int rows_per_it = 32 / segs;
+  const int seg = lane % segs, r0 = lane / segs;
+  const int col = col0 + seg * epp;
+  for (int it = 0; it < segs; ++it) {               // segs iterations x rows_per_it rows = 32 rows
+    const int row = it * rows_per_it + r0;
+    const int m = m_base + row;
+    if (m >= g.M || col >= n_limit) continue;
+    uint4 v = stage_get16(stg, row, seg);
+    if (bf16_out) {
+      __nv_bfloat16* dp = static_cast<__nv_bfloat16*>(g.D) + (long long)m * g.ldd + col;
+      if (col + 8 <= n_limit) {
+        if (g.residual != nullptr) {
+          const uint4 r = __ldg(reinterpret_cast<const uint4*>(g.residual + (long long)m * g.ldr + col));
+          v.x = pack_bf16(bf16_lo(v.x) + bf16_lo(r.x), bf16_hi(v.x) + bf16_hi(r.x));
+          v.y = pack_bf16(bf16_lo(v.y) + bf16_lo(r.y), bf16_hi(v.y) + bf16_hi(r.y));
+          v.z = pack_bf16(bf16_lo(v.z) + bf16_lo(r.z), bf16_hi(v.z) + bf16_hi(r.z));
+          v.w = pack_bf16(bf16_lo(v.w) + bf16_lo(r.w), bf16_hi(v.w) + bf16_hi(r.w));
+        }
+        *reinterpret_cast<uint4*>(dp) = v;
+      } else {
+        const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+        for (int j = 0; j < 8 && col + j < n_limit; ++j) {
+          float x = (j & 1) ? bf16_hi(u[j >> 1]) : bf16_lo(u[j >> 1]);
+          if (g.residual != nullptr) x += __bfloat162float(g.residual[(long long)m * g.ldr + col + j]);
+          dp[j] = __float2bfloat16_rn(x);
+        }
+      }
+    } else {
+      float* dp = static_cast<float*>(g.D) + (long long)m * g.ldd + col;
+      float x[4] = {__uint_as_float(v.x), __uint_as_float(v.y), __uint_as_float(v.z), __uint_as_float(v.w)};
+      for (int j = 0; j < 4; ++j)
+        if (g.residual != nullptr && col + j < n_limit) x[j] += __bfloat162float(g.residual[(long long)m * g.ldr + col + j]);
+      if (col + 4 <= n_limit) *reinterpret_cast<float4*>(dp) = make_float4(x[0], x[1], x[2], x[3]);
+      else for (int j = 0; j < 4 && col + j < n_limit; ++j) dp[j] = x[j];
+    }
+  }
+  __syncwarp();
+}
+
 template <int BN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const GemmArgs g) {
@@ -157,6 +230,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   uint64_t* tmem_empty = bars + 2 * S + 2;   // [2]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * S + 4);
   volatile int* last_flag = reinterpret_cast<volatile int*>(tmem_ptr + 1);
+  uint8_t* staging = smem + S * Cfg::kStageBytes + 256;   // [8 epilogue warps][32 rows][128 B]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -306,6 +380,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       if (!g.gated) {
         // software pipeline: the TMEM load of chunk c+1 is in flight while chunk c is converted and stored
         constexpr int NCH = (kSplit32 ? BN / 2 : BN) / 32;
+        uint8_t* stg = staging + (warp - 2) * 4096;
         uint32_t r[2][32];
         const int cbeg = p_beg;
         const bool worker = p_end > p_beg;
@@ -324,7 +399,17 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], g.act);
           }
-          if (m < g.M) store_row32(g, v, m, n0 + c, g.N);
+          if (!g.coalesce) {
+            if (m < g.M) store_row32(g, v, m, n0 + c, g.N);
+          } else if (g.d_dtype == FO1_BF16) {
+            // two 32-column chunks (2 x 64 B) fill a 128-byte row before it is flushed
+            stage_row32(stg, lane, (ci & 1) * 4, v, true);
+            const bool last = (ci + 1 == NCH) || (n0 + c + 32 >= g.N);
+            if ((ci & 1) || last) flush_rows(g, stg, lane, (ci & 1) ? 8 : 4, m0 + quarter * 32, n0 + c - (ci & 1) * 32, g.N);
+          } else {
+            stage_row32(stg, lane, 0, v, false);
+            flush_rows(g, stg, lane, 8, m0 + quarter * 32, n0 + c, g.N);
+          }
         }
       } else {
         // W rows interleave [32 gate | 32 up] blocks: out[:, (n0+c)/2 + j] = act(gate_j) * up_j
@@ -344,7 +429,14 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           }
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = apply_act(gt[j], g.act) * v[j];
-          if (m < g.M) store_row32(g, v, m, (n0 + c) >> 1, g.N >> 1);
+          if (!g.coalesce) {
+            if (m < g.M) store_row32(g, v, m, (n0 + c) >> 1, g.N >> 1);
+          } else {
+            uint8_t* stg = staging + (warp - 2) * 4096;
+            const bool bf = g.d_dtype == FO1_BF16;
+            stage_row32(stg, lane, 0, v, bf);
+            flush_rows(g, stg, lane, bf ? 4 : 8, m0 + quarter * 32, (n0 + c) >> 1, g.N >> 1);
+          }
         }
       }
       ptx::tc_fence_before();
@@ -459,6 +551,12 @@ static int launch_gemm(const fo1_gemm_desc* d, cudaStream_t stream, int ksplit =
   g.tiles_m = ceil_div(d->M, BM);
   g.tiles_n = ceil_div(d->N, BN);
   g.stage_tx = (a_rows + BN) * BK * 2;
+  {
+    const int esz = d->d_dtype == FO1_BF16 ? 2 : 4;
+    const bool d_ok = (reinterpret_cast<uintptr_t>(d->D) & 15) == 0 && (d->ldd * esz) % 16 == 0;
+    const bool r_ok = d->residual == nullptr || ((reinterpret_cast<uintptr_t>(d->residual) & 15) == 0 && (d->ldr * 2) % 16 == 0);
+    g.coalesce = (d_ok && r_ok && getenv("FO1_GEMM_DIRECT_STORE") == nullptr) ? 1 : 0;
+  }
   const int num_kb = ceil_div(d->K, BK);
   g.kb_per_split = ceil_div(num_kb, ksplit);
   g.ksplit = ceil_div(num_kb, g.kb_per_split);   // every split owns at least one k-block
@@ -496,6 +594,7 @@ int gemm_bf16(const fo1_gemm_desc* d, cudaStream_t stream) {
   FO1_CHECK_ARG(!d->gated || d->N % 64 == 0, "fo1_gemm_bf16: gated N=%d must be a multiple of 64", d->N);
   FO1_CHECK_ARG(d->ldd >= n_out, "fo1_gemm_bf16: ldd=%lld < %d", (long long)d->ldd, n_out);
   FO1_CHECK_ARG(d->residual == nullptr || d->ldr >= n_out, "fo1_gemm_bf16: ldr too small");
+  if (skinny_gemm_supported(d)) return skinny_gemm(d, stream);   // M <= 32: weight streaming (skinny_gemm.cu)
   // tile-width choice: widest tile that still yields >= 1 wave of CTAs, else narrower for occupancy
   const int sms = device_sm_count();
   const long long tm = ceil_div(d->M, BM);

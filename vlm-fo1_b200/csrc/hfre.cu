@@ -300,6 +300,24 @@ __global__ void __launch_bounds__(kGatherThreads) hfre_gather_kernel(const Batch
 // channel) at the end.  Per cell and covering box the work is 2 FMA per bf16 pair -- the SIMT FMA
 // rate, not HBM, is then the co-limiter.
 // ------------------------------------------------------------------------------------------------
+// packed fp32x2 helpers: one FFMA2 does the two channels a lane owns (sm_100 `fma.rn.f32x2`; a {w, w} pair becomes
+// the instruction's scalar-broadcast operand)
+__device__ __forceinline__ unsigned long long f2_pack(float lo, float hi) {
+  unsigned long long r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ unsigned long long f2_fma(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ float2 f2_unpack(unsigned long long v) {
+  float2 r;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+  return r;
+}
+
 __global__ void __launch_bounds__(32) hfre_region_lists_kernel(const BatchDev B, const float* __restrict__ ws, int* __restrict__ lists) {
   const ImageDev& im = B.img[blockIdx.z];
   const int lvl = blockIdx.y;
@@ -386,7 +404,7 @@ __global__ void __launch_bounds__(kSweepThreads) hfre_sweep_kernel(const BatchDe
         bool any = false;
         for (int sl = 0; sl < ns; ++sl) any |= ((s_rmask[sl] >> ty) & 1) && ((s_cmask[sl] >> tx) & 1);
         if (!any) continue;  // warp-uniform
-        float vx[8][8], vy[8][8];
+        unsigned long long v2[8][8];   // (channel 0, channel 1) of the 64 cells, packed fp32x2
         const __nv_bfloat16* p0 = L.data + (long long)r_base * rowpitch + (long long)c_base * L.C + cbase;
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
@@ -394,7 +412,7 @@ __global__ void __launch_bounds__(kSweepThreads) hfre_sweep_kernel(const BatchDe
           for (int k = 0; k < 8; ++k) {
             uint32_t u = 0;
             if (r_base + r < L.H && c_base + k < L.W) u = __ldg(reinterpret_cast<const uint32_t*>(p0 + (long long)r * rowpitch + (long long)k * L.C));
-            vx[r][k] = bf16_lo(u); vy[r][k] = bf16_hi(u);
+            v2[r][k] = f2_pack(bf16_lo(u), bf16_hi(u));
           }
         }
         for (int sl = 0; sl < ns; ++sl) {
@@ -403,17 +421,18 @@ __global__ void __launch_bounds__(kSweepThreads) hfre_sweep_kernel(const BatchDe
           const float4 a0 = *reinterpret_cast<const float4*>(&s_wa[sl][ty * 8]), a1 = *reinterpret_cast<const float4*>(&s_wa[sl][ty * 8 + 4]);
           const float wb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
           const float wa[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-          float ax = 0.f, ay = 0.f;
+          unsigned long long a2 = 0ull;
 #pragma unroll
           for (int r = 0; r < 8; ++r) {
-            float tx_ = 0.f, ty_ = 0.f;
+            unsigned long long t2 = 0ull;
 #pragma unroll
-            for (int k = 0; k < 8; ++k) { tx_ = fmaf(wb[k], vx[r][k], tx_); ty_ = fmaf(wb[k], vy[r][k], ty_); }
-            ax = fmaf(wa[r], tx_, ax); ay = fmaf(wa[r], ty_, ay);
+            for (int k = 0; k < 8; ++k) t2 = f2_fma(f2_pack(wb[k], wb[k]), v2[r][k], t2);
+            a2 = f2_fma(f2_pack(wa[r], wa[r]), t2, a2);
           }
+          const float2 part = f2_unpack(a2);
           float2* acc = reinterpret_cast<float2*>(&s_acc[sl][warp * 64 + lane * 2]);  // lane-owned: no atomics
           float2 cur = *acc;
-          cur.x += ax; cur.y += ay;
+          cur.x += part.x; cur.y += part.y;
           *acc = cur;
         }
       }

@@ -35,7 +35,22 @@ class Fo1Pipeline:
         self.ids = dict(image_token_id=image_token_id, vision_start_token_id=vision_start_token_id, video_token_id=video_token_id)
         self.hcfg = HF.HfreConfig(region_dim=engine.cfg.region_dim, vt_mode=vt_mode)
         self.ws = HF.HfreWorkspace()
-        self.timings: Dict[str, float] = {}
+        self.profile_stages = False          # when set, CUDA events bracket every stage (read with stage_ms())
+        self._marks = []
+
+    def _mark(self, name: str) -> None:
+        if self.profile_stages:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            self._marks.append((name, e))
+
+    def stage_ms(self) -> Dict[str, float]:
+        """Milliseconds between consecutive stage marks of the last call (synchronises)."""
+        torch.cuda.synchronize()
+        out: Dict[str, float] = {}
+        for (n0, e0), (n1, e1) in zip(self._marks[:-1], self._marks[1:]):
+            out[n1] = out.get(n1, 0.0) + e0.elapsed_time(e1)
+        return out
 
     # ---- vision side -------------------------------------------------------------------------------------
     def encode(self, samples: Sequence[SampleInputs]):
@@ -43,7 +58,10 @@ class Fo1Pipeline:
         region features fp32 list)."""
         eng, dev = self.eng, self.eng.device
         grids = [s.grid_hw for s in samples]
+        self._marks = []
+        self._mark("start")
         feats, taps = eng.vit_forward([s.pixel_values for s in samples], grids)
+        self._mark("vit")
         B = len(samples)
         H0, W0 = samples[0].image_aux.shape[-2:]
         same_aux = all(s.image_aux.shape[-2:] == (H0, W0) for s in samples)
@@ -56,6 +74,7 @@ class Fo1Pipeline:
             for s in samples:
                 st = eng.davit_forward([s.image_aux])
                 aux.append([st[l][0] for l in range(4)])
+        self._mark("davit")
         tok_off = np.cumsum([0] + [gh * gw for gh, gw in grids])
         hid = eng.cfg.vit["hidden_size"]
         if self.vt_mode == "fpn":
@@ -70,6 +89,7 @@ class Fo1Pipeline:
                     vt.append([pyr[l][0] for l in range(4)])
         else:
             vt = [[taps[t][tok_off[b]:tok_off[b + 1]].view(grids[b][0], grids[b][1], hid) for t in range(len(taps))] for b in range(B)]
+        self._mark("fpn")
         boxes_aux, boxes_vt = [], []
         for b, s in enumerate(samples):
             bx = s.boxes.to(dev, torch.float32)
@@ -82,8 +102,10 @@ class Fo1Pipeline:
             boxes_aux.append(bx)
             boxes_vt.append(bx * scale)                                              # :94-99
         region_f32, region_bf16 = HF.hfre_forward(aux, vt, boxes_aux, boxes_vt, self.hcfg, grids, want_bf16=True, workspace=self.ws)
+        self._mark("hfre")
         counts = [r.shape[0] for r in region_bf16]
         tokens = eng.region_project(torch.cat(region_bf16, 0))
+        self._mark("projector")
         region_tokens = list(torch.split(tokens, counts, 0))
         unit = eng.cfg.vit["spatial_merge_size"] ** 2
         img_off = np.cumsum([0] + [gh * gw // unit for gh, gw in grids])
@@ -109,7 +131,9 @@ class Fo1Pipeline:
         index = torch.from_numpy(np.concatenate(idxs)).to(dev)
         pos = torch.from_numpy(np.concatenate(poss, axis=1)).to(dev)
         embeds = eng.build_embeds(kind, index, feats, torch.cat(region_tokens, 0))
+        self._mark("splice")
         out = eng.generate(embeds, pos, lens, deltas, max_new_tokens, stop_ids, pad_id, want_prefill_logits=want_prefill_logits,
                            early_exit_interval=early_exit_interval)
+        self._mark("llm_prefill_decode")
         out["prompt_lens"] = lens
         return out

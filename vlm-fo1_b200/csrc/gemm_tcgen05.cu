@@ -42,18 +42,21 @@ struct GemmArgs {
   // `counters[tile]` reduces them in split order (deterministic) and runs the epilogue
   int ksplit, kb_per_split;
   int coalesce;   // 1: epilogue stages rows through shared memory and writes full 128-byte lines (needs 16-byte aligned D / residual rows)
+  int stages;     // ring depth actually used (<= kMaxStages): skinny problems trade the unused A rows for more stages in flight
+  int a_stage_bytes, b_stage_bytes;
   int stage_tx;   // bytes one ring stage receives (A box rows x 128 B + BN x 128 B): skinny problems load only the live A rows
   float* ws;
   int* counters;
 };
 
+constexpr int kMaxStages = 24;
 template <int BN>
 struct GemmCfg {
   static constexpr int kStageBytes = (BM * BK + BN * BK) * 2;
   static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : (BN == 64 ? 8 : 10));
   static constexpr int kTmemCols = 2 * BN;
   static constexpr int kStagingBytes = 8 * 4096;   // epilogue: 32 rows x 128 B per epilogue warp
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + kStagingBytes;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 512 /*barriers*/ + kStagingBytes;
 };
 
 __device__ __forceinline__ float load_bias(const void* bias, int dtype, int n) {
@@ -217,20 +220,21 @@ template <int BN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const GemmArgs g) {
   using Cfg = GemmCfg<BN>;
-  constexpr int S = Cfg::kStages;
+  const int S = g.stages;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment: required by the 128B swizzle atoms the UMMA descriptors assume
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
   uint8_t* smem_a = smem;
-  uint8_t* smem_b = smem + S * (BM * BK * 2);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S * Cfg::kStageBytes);
-  uint64_t* full_bar = bars;                 // [S]
-  uint64_t* empty_bar = bars + S;            // [S]
-  uint64_t* tmem_full = bars + 2 * S;        // [2]
-  uint64_t* tmem_empty = bars + 2 * S + 2;   // [2]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * S + 4);
+  uint8_t* smem_b = smem + S * g.a_stage_bytes;
+  uint8_t* tail = smem + S * (g.a_stage_bytes + g.b_stage_bytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tail);
+  uint64_t* full_bar = bars;                          // [S]
+  uint64_t* empty_bar = bars + kMaxStages;            // [S]
+  uint64_t* tmem_full = bars + 2 * kMaxStages;        // [2]
+  uint64_t* tmem_empty = bars + 2 * kMaxStages + 2;   // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
   volatile int* last_flag = reinterpret_cast<volatile int*>(tmem_ptr + 1);
-  uint8_t* staging = smem + S * Cfg::kStageBytes + 256;   // [8 epilogue warps][32 rows][128 B]
+  uint8_t* staging = tail + 512;   // [8 epilogue warps][32 rows][128 B]
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -270,8 +274,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           ptx::mbar_wait(ptx::smem_u32(empty_bar + s), ph ^ 1);
           const uint32_t fb = ptx::smem_u32(full_bar + s);
           ptx::mbar_expect_tx(fb, (uint32_t)g.stage_tx);
-          ptx::tma_load_2d(ptx::smem_u32(smem_a + s * (BM * BK * 2)), &tmA, fb, kb * BK, m0);
-          ptx::tma_load_2d(ptx::smem_u32(smem_b + s * (BN * BK * 2)), &tmW, fb, kb * BK, n0);
+          ptx::tma_load_2d(ptx::smem_u32(smem_a + s * g.a_stage_bytes), &tmA, fb, kb * BK, m0);
+          ptx::tma_load_2d(ptx::smem_u32(smem_b + s * g.b_stage_bytes), &tmW, fb, kb * BK, n0);
         }
       }
     }
@@ -291,8 +295,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         ptx::mbar_wait(ptx::smem_u32(full_bar + s), ph);
         ptx::tc_fence_after();
         if (ptx::elect_one()) {
-          const uint32_t a_addr = ptx::smem_u32(smem_a + s * (BM * BK * 2));
-          const uint32_t b_addr = ptx::smem_u32(smem_b + s * (BN * BK * 2));
+          const uint32_t a_addr = ptx::smem_u32(smem_a + s * g.a_stage_bytes);
+          const uint32_t b_addr = ptx::smem_u32(smem_b + s * g.b_stage_bytes);
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             const uint64_t da = ptx::umma_desc_k_sw128(a_addr + k * UMMA_K * 2);
@@ -551,6 +555,17 @@ static int launch_gemm(const fo1_gemm_desc* d, cudaStream_t stream, int ksplit =
   g.tiles_m = ceil_div(d->M, BM);
   g.tiles_n = ceil_div(d->N, BN);
   g.stage_tx = (a_rows + BN) * BK * 2;
+  // the UMMA reads all 128 A rows of a stage: keep the full 16 KB slot unless only the live rows are loaded AND the
+  // rows beyond them may alias the next stage's data (harmless: those accumulator rows are never stored)
+  g.a_stage_bytes = (a_rows < BM) ? ((a_rows * BK * 2 + 1023) & ~1023) : BM * BK * 2;
+  g.b_stage_bytes = BN * BK * 2;
+  {
+    const int budget = Cfg::kSmemBytes - 1024 - 512 - Cfg::kStagingBytes;
+    int st = budget / (g.a_stage_bytes + g.b_stage_bytes);
+    // the last stage's A slot is read 16 KB deep by the UMMA: keep that window inside the operand area
+    while (st > 2 && st * (g.a_stage_bytes + g.b_stage_bytes) + (BM * BK * 2 - g.a_stage_bytes) > budget) --st;
+    g.stages = st < kMaxStages ? st : kMaxStages;
+  }
   {
     const int esz = d->d_dtype == FO1_BF16 ? 2 : 4;
     const bool d_ok = (reinterpret_cast<uintptr_t>(d->D) & 15) == 0 && (d->ldd * esz) % 16 == 0;
@@ -594,7 +609,6 @@ int gemm_bf16(const fo1_gemm_desc* d, cudaStream_t stream) {
   FO1_CHECK_ARG(!d->gated || d->N % 64 == 0, "fo1_gemm_bf16: gated N=%d must be a multiple of 64", d->N);
   FO1_CHECK_ARG(d->ldd >= n_out, "fo1_gemm_bf16: ldd=%lld < %d", (long long)d->ldd, n_out);
   FO1_CHECK_ARG(d->residual == nullptr || d->ldr >= n_out, "fo1_gemm_bf16: ldr too small");
-  if (skinny_gemm_supported(d)) return skinny_gemm(d, stream);   // M <= 32: weight streaming (skinny_gemm.cu)
   // tile-width choice: widest tile that still yields >= 1 wave of CTAs, else narrower for occupancy
   const int sms = device_sm_count();
   const long long tm = ceil_div(d->M, BM);

@@ -11,9 +11,6 @@ typedef __nv_bfloat16 bf16;
 // ---- gemm_tcgen05.cu ----
 int gemm_bf16(const fo1_gemm_desc* d, cudaStream_t stream);
 int device_sm_count();
-// ---- skinny_gemm.cu ---- (M <= 32 weight-streaming path)
-bool skinny_gemm_supported(const fo1_gemm_desc* d);
-int skinny_gemm(const fo1_gemm_desc* d, cudaStream_t stream);
 // convenience: D = act(A.W^T + bias) + residual, all row-major contiguous unless ld given
 int linear(const bf16* A, long long lda, const bf16* W, long long ldw, void* D, long long ldd, int d_dtype, int M, int N,
            int K, const void* bias, int bias_dtype, int act, const bf16* residual, long long ldr, int gated,

@@ -62,114 +62,92 @@ __global__ void __launch_bounds__(128) kv_append_kernel(const bf16* __restrict__
 }
 
 // Single-query GQA attention over the cache, split over the sequence (flash-decoding): one block per
-// (sequence, kv head, split); the G = q_heads/kv_heads query heads that share the K/V stream are processed together
-// so every K/V byte is read once.  8 warps x 4 token slots; a token's 128 dims are split over 8 lanes (16 dims =
-// 32 B each).  Each block writes an un-normalised partial (m, l, acc) per head; decode_attn_combine_kernel merges
-// the splits.  With B = 32, 2 kv heads and 8 splits that is 512 blocks streaming the cache instead of 64.
+// (sequence, kv head, split); warp g of the block owns query head kvh*G + g, so no cross-warp reduction exists and
+// the register footprint stays small (the G warps re-read the same K/V rows, which the first reader leaves in L1).
+// A token's 128 dims are split over 8 lanes (16 dims = 32 B each), 4 tokens per warp iteration, 2 iterations in
+// flight.  Each warp writes an un-normalised partial (m, l, acc[128]); decode_attn_combine_kernel merges the splits.
 constexpr int kDecSplits = 8;
 template <int G>
-__global__ void __launch_bounds__(256) decode_attn_kernel(const bf16* __restrict__ q, long long ldq, const bf16* __restrict__ kc,
-                                                          const bf16* __restrict__ vc, const int* __restrict__ cache_len, int cap,
-                                                          int kv_heads, float* __restrict__ part, float scale) {
+__global__ void __launch_bounds__(G * 32) decode_attn_kernel(const bf16* __restrict__ q, long long ldq, const bf16* __restrict__ kc,
+                                                             const bf16* __restrict__ vc, const int* __restrict__ cache_len, int cap,
+                                                             int kv_heads, float* __restrict__ part, float scale) {
   constexpr int HD = 128;
   const int b = blockIdx.x, kvh = blockIdx.y, sp = blockIdx.z;
   const int n = cache_len[b] + 1;  // the step's own K/V was appended at index cache_len[b]
   const int chunk = ((n + kDecSplits - 1) / kDecSplits + 3) & ~3;
   const int t_begin = sp * chunk, t_end = min(n, t_begin + chunk);
   const int kv_dim = kv_heads * HD;
-  __shared__ float qs[G][HD];
-  __shared__ float red_m[8][G], red_l[8][G];
-  __shared__ float red_acc[8][G][HD];
-  for (int i = threadIdx.x; i < G * HD; i += 256) {
-    const int g = i / HD, d = i % HD;
-    qs[g][d] = __bfloat162float(q[(long long)b * ldq + (long long)(kvh * G + g) * HD + d]) * scale * 1.4426950408889634f;
-  }
-  __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int grp = lane >> 3, sub = lane & 7;
-  float m[G], l[G], acc[G][16];
+  const int head = kvh * G + g;
+  float qf[16];
+  {
+    const bf16* qp = q + (long long)b * ldq + (long long)head * HD + sub * 16;
+    const uint4 q0 = *reinterpret_cast<const uint4*>(qp), q1 = *reinterpret_cast<const uint4*>(qp + 8);
+    const uint32_t qu[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+    const float sc = scale * 1.4426950408889634f;
 #pragma unroll
-  for (int g = 0; g < G; ++g) {
-    m[g] = -INFINITY; l[g] = 0.f;
-#pragma unroll
-    for (int d = 0; d < 16; ++d) acc[g][d] = 0.f;
+    for (int i = 0; i < 8; ++i) { qf[2 * i] = bf16_lo(qu[i]) * sc; qf[2 * i + 1] = bf16_hi(qu[i]) * sc; }
   }
+  float m = -INFINITY, l = 0.f, acc[16];
+#pragma unroll
+  for (int d = 0; d < 16; ++d) acc[d] = 0.f;
   const bf16* kb = kc + (long long)b * cap * kv_dim + kvh * HD + sub * 16;
   const bf16* vb = vc + (long long)b * cap * kv_dim + kvh * HD + sub * 16;
-  for (int t0 = t_begin + warp * 4; t0 < t_end; t0 += 32) {
-    const int t = t0 + grp;
-    const bool ok = t < t_end;
-    float kf[16], vf[16];
-    {
-      uint4 k0 = make_uint4(0, 0, 0, 0), k1 = k0, v0 = k0, v1 = k0;
-      if (ok) {
-        k0 = *reinterpret_cast<const uint4*>(kb + (long long)t * kv_dim); k1 = *reinterpret_cast<const uint4*>(kb + (long long)t * kv_dim + 8);
-        v0 = *reinterpret_cast<const uint4*>(vb + (long long)t * kv_dim); v1 = *reinterpret_cast<const uint4*>(vb + (long long)t * kv_dim + 8);
-      }
-      const uint32_t ku[8] = {k0.x, k0.y, k0.z, k0.w, k1.x, k1.y, k1.z, k1.w}, vu[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+  for (int t0 = t_begin; t0 < t_end; t0 += 8) {
+    uint4 kk[2][2], vv[2][2];
+    bool ok[2];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { kf[2 * i] = bf16_lo(ku[i]); kf[2 * i + 1] = bf16_hi(ku[i]); vf[2 * i] = bf16_lo(vu[i]); vf[2 * i + 1] = bf16_hi(vu[i]); }
+    for (int u = 0; u < 2; ++u) {
+      const int t = t0 + u * 4 + grp;
+      ok[u] = t < t_end;
+      const long long off = (long long)(ok[u] ? t : t_begin) * kv_dim;
+      kk[u][0] = *reinterpret_cast<const uint4*>(kb + off); kk[u][1] = *reinterpret_cast<const uint4*>(kb + off + 8);
+      vv[u][0] = *reinterpret_cast<const uint4*>(vb + off); vv[u][1] = *reinterpret_cast<const uint4*>(vb + off + 8);
     }
 #pragma unroll
-    for (int g = 0; g < G; ++g) {
+    for (int u = 0; u < 2; ++u) {
+      const uint32_t ku[8] = {kk[u][0].x, kk[u][0].y, kk[u][0].z, kk[u][0].w, kk[u][1].x, kk[u][1].y, kk[u][1].z, kk[u][1].w};
       float s = 0.f;
 #pragma unroll
-      for (int d = 0; d < 16; ++d) s = fmaf(kf[d], qs[g][sub * 16 + d], s);
+      for (int i = 0; i < 8; ++i) { s = fmaf(bf16_lo(ku[i]), qf[2 * i], s); s = fmaf(bf16_hi(ku[i]), qf[2 * i + 1], s); }
       s += __shfl_xor_sync(0xffffffffu, s, 1);
       s += __shfl_xor_sync(0xffffffffu, s, 2);
       s += __shfl_xor_sync(0xffffffffu, s, 4);
-      if (ok) {
-        const float mn = fmaxf(m[g], s);
-        const float a = exp2f(m[g] - mn), p = exp2f(s - mn);  // m = -inf on first use -> a = 0
-        l[g] = l[g] * a + p;
+      if (ok[u]) {
+        const uint32_t vu[8] = {vv[u][0].x, vv[u][0].y, vv[u][0].z, vv[u][0].w, vv[u][1].x, vv[u][1].y, vv[u][1].z, vv[u][1].w};
+        const float mn = fmaxf(m, s);
+        const float a = exp2f(m - mn), p = exp2f(s - mn);  // m = -inf on first use -> a = 0
+        l = l * a + p;
 #pragma unroll
-        for (int d = 0; d < 16; ++d) acc[g][d] = fmaf(p, vf[d], acc[g][d] * a);
-        m[g] = mn;
+        for (int i = 0; i < 8; ++i) {
+          acc[2 * i] = fmaf(p, bf16_lo(vu[i]), acc[2 * i] * a);
+          acc[2 * i + 1] = fmaf(p, bf16_hi(vu[i]), acc[2 * i + 1] * a);
+        }
+        m = mn;
       }
     }
   }
   // combine the 4 token slots of the warp (lanes differing in bits 3 and 4 hold the same dims)
 #pragma unroll
   for (int off = 8; off <= 16; off <<= 1) {
+    const float mo = __shfl_xor_sync(0xffffffffu, m, off), lo = __shfl_xor_sync(0xffffffffu, l, off);
+    const float mn = fmaxf(m, mo);
+    const float a = (m == -INFINITY) ? 0.f : exp2f(m - mn), bsc = (mo == -INFINITY) ? 0.f : exp2f(mo - mn);
 #pragma unroll
-    for (int g = 0; g < G; ++g) {
-      const float mo = __shfl_xor_sync(0xffffffffu, m[g], off), lo = __shfl_xor_sync(0xffffffffu, l[g], off);
-      const float mn = fmaxf(m[g], mo);
-      const float a = (m[g] == -INFINITY) ? 0.f : exp2f(m[g] - mn), bsc = (mo == -INFINITY) ? 0.f : exp2f(mo - mn);
-#pragma unroll
-      for (int d = 0; d < 16; ++d) {
-        const float ao = __shfl_xor_sync(0xffffffffu, acc[g][d], off);
-        acc[g][d] = acc[g][d] * a + ao * bsc;
-      }
-      l[g] = l[g] * a + lo * bsc;
-      m[g] = mn;
+    for (int d = 0; d < 16; ++d) {
+      const float ao = __shfl_xor_sync(0xffffffffu, acc[d], off);
+      acc[d] = acc[d] * a + ao * bsc;
     }
+    l = l * a + lo * bsc;
+    m = mn;
   }
+  // partial record per (b, head, split): [m, l, pad, pad, acc[128]]
   if (grp == 0) {
+    float* rec = part + (((long long)b * kv_heads * G + head) * kDecSplits + sp) * (HD + 4);
+    if (sub == 0) { rec[0] = m; rec[1] = l; }
 #pragma unroll
-    for (int g = 0; g < G; ++g) {
-      if (sub == 0) { red_m[warp][g] = m[g]; red_l[warp][g] = l[g]; }
-#pragma unroll
-      for (int d = 0; d < 16; ++d) red_acc[warp][g][sub * 16 + d] = acc[g][d];
-    }
-  }
-  __syncthreads();
-  // partial record per (b, kvh, g, split): [m, l, pad, pad, acc[128]]
-  for (int i = threadIdx.x; i < G * HD; i += 256) {
-    const int g = i / HD, d = i % HD;
-    float mm = -INFINITY;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) mm = fmaxf(mm, red_m[w][g]);
-    float num = 0.f, den = 0.f;
-#pragma unroll
-    for (int w = 0; w < 8; ++w) {
-      const float sc = (red_m[w][g] == -INFINITY) ? 0.f : exp2f(red_m[w][g] - mm);
-      num += red_acc[w][g][d] * sc;
-      den += red_l[w][g] * sc;
-    }
-    float* rec = part + ((((long long)b * kv_heads + kvh) * G + g) * kDecSplits + sp) * (HD + 4);
-    rec[4 + d] = num;
-    if (d == 0) { rec[0] = mm; rec[1] = den; }
+    for (int d = 0; d < 16; d += 4) *reinterpret_cast<float4*>(rec + 4 + sub * 16 + d) = make_float4(acc[d], acc[d + 1], acc[d + 2], acc[d + 3]);
   }
 }
 
@@ -394,10 +372,10 @@ static int llm_layer(Model* m, int li, const bf16* x_in, bf16* x_out, const Laye
     ProfScope prof("decode_attn", 0.0, 0.0, s);
     const int G = c.llm_heads / c.llm_kv_heads;
     const float scale = 1.0f / sqrtf((float)hd);
-    if (G == 8) decode_attn_kernel<8><<<grid, 256, 0, s>>>(B_.qkv, ldq, kc, vc, st->cache_len, m->kv_cap, c.llm_kv_heads, B_.dec_part, scale);
-    else if (G == 4) decode_attn_kernel<4><<<grid, 256, 0, s>>>(B_.qkv, ldq, kc, vc, st->cache_len, m->kv_cap, c.llm_kv_heads, B_.dec_part, scale);
-    else if (G == 2) decode_attn_kernel<2><<<grid, 256, 0, s>>>(B_.qkv, ldq, kc, vc, st->cache_len, m->kv_cap, c.llm_kv_heads, B_.dec_part, scale);
-    else if (G == 1) decode_attn_kernel<1><<<grid, 256, 0, s>>>(B_.qkv, ldq, kc, vc, st->cache_len, m->kv_cap, c.llm_kv_heads, B_.dec_part, scale);
+    if (G == 8) decode_attn_kernel<8><<<grid, 8 * 32, 0, s>>>(B_.qkv, ldq, kc, vc, st->cache_len, m->kv_cap, c.llm_kv_heads, B_.dec_part, scale);
+    else if (G == 4) decode_attn_kernel<4><<<grid, 4 * 32, 0, s>>>(B_.qkv, ldq, kc, vc, st->cache_len, m->kv_cap, c.llm_kv_heads, B_.dec_part, scale);
+    else if (G == 2) decode_attn_kernel<2><<<grid, 2 * 32, 0, s>>>(B_.qkv, ldq, kc, vc, st->cache_len, m->kv_cap, c.llm_kv_heads, B_.dec_part, scale);
+    else if (G == 1) decode_attn_kernel<1><<<grid, 1 * 32, 0, s>>>(B_.qkv, ldq, kc, vc, st->cache_len, m->kv_cap, c.llm_kv_heads, B_.dec_part, scale);
     else { set_error("decode attention: GQA group %d unsupported", G); return FO1_ERR_UNSUPPORTED; }
     FO1_LAUNCH_CHECK();
     decode_attn_combine_kernel<<<dim3(rows, c.llm_heads), 128, 0, s>>>(B_.dec_part, B_.att, QD, c.llm_heads);

@@ -53,10 +53,11 @@ constexpr int kMaxStages = 24;
 template <int BN>
 struct GemmCfg {
   static constexpr int kStageBytes = (BM * BK + BN * BK) * 2;
-  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : (BN == 64 ? 8 : 10));
+  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : (BN == 64 ? 8 : 9));   // sets the smem budget; the ring depth is planned per launch
   static constexpr int kTmemCols = 2 * BN;
   static constexpr int kStagingBytes = 8 * 4096;   // epilogue: 32 rows x 128 B per epilogue warp
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 512 /*barriers*/ + kStagingBytes;
+  static_assert(kSmemBytes <= 232448, "exceeds the 227 KB of shared memory a CTA may opt into");
 };
 
 __device__ __forceinline__ float load_bias(const void* bias, int dtype, int n) {

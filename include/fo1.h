@@ -120,6 +120,8 @@ typedef struct {
   const void* residual; int64_t ldr; /* optional bf16 [M][N] added after act */
   int32_t gated;                   /* 1: W rows interleave [32 gate | 32 up] blocks -> D[M][N/2] =
                                       act(gate)*up  (Qwen2MLP, modeling_qwen2_5_vl.py:84-85,638-640) */
+  int32_t tile_n;                  /* 0 = library heuristic; 32 / 64 / 128 / 256 pins the tile width (tuning, tests) */
+  int32_t split_k;                 /* with tile_n != 0: number of K splits reduced in-kernel (>= 1); 0 = 1 */
 } fo1_gemm_desc;
 
 int fo1_gemm_bf16(const fo1_gemm_desc* d, void* stream);

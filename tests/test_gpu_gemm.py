@@ -85,6 +85,49 @@ def test_gemm_skinny_splitk(M, N, K):
     assert torch.equal(out, out2)      # fixed reduction order -> bitwise reproducible
 
 
+@pytest.mark.parametrize("tile_n,split_k", [(32, 1), (32, 4), (64, 3), (128, 8), (256, 5), (128, 1)])
+@pytest.mark.parametrize("M", [32, 130])
+def test_gemm_pinned_tile_and_split(tile_n, split_k, M):
+    """every tile width x split-K variant the descriptor can pin: cooperative reduction by the last CTA of a tile,
+    bias / activation / residual applied after the reduction, bit-reproducible"""
+    ops = _ops()
+    N, K = 1000, 2112        # ragged N tile, 33 k-blocks (uneven splits)
+    g = torch.Generator(device="cuda").manual_seed(tile_n + split_k + M)
+    a = (torch.randn(M, K, device="cuda", generator=g) * 0.5).to(torch.bfloat16)
+    w = (torch.randn(N, K, device="cuda", generator=g) * 0.05).to(torch.bfloat16)
+    bias = (torch.randn(N, device="cuda", generator=g) * 0.2).to(torch.float32)
+    res = torch.randn(M, N, device="cuda", generator=g).to(torch.bfloat16)
+    ref = _ref(a, w, bias, "silu", res)
+    outs = []
+    for dt in (torch.float32, torch.bfloat16, torch.float32):
+        out = ops.gemm(a, w, bias=bias, act="silu", residual=res, out_dtype=dt, tile_n=tile_n, split_k=split_k)
+        torch.cuda.synchronize()
+        _check(out, ref, dt == torch.bfloat16)
+        outs.append(out)
+    assert torch.equal(outs[0], outs[2])
+
+
+@pytest.mark.parametrize("tile_n,split_k", [(64, 1), (64, 3), (128, 4), (256, 2), (256, 7)])
+def test_gemm_gated_split(tile_n, split_k):
+    """the gated epilogue after a split-K reduction (decode gate/up projection)"""
+    ops = _ops()
+    M, K, I = 32, 2048, 1000
+    g = torch.Generator(device="cuda").manual_seed(tile_n * 3 + split_k)
+    x = torch.randn(M, K, device="cuda", generator=g).to(torch.bfloat16)
+    wg = (torch.randn(I, K, device="cuda", generator=g) * 0.03).to(torch.bfloat16)
+    wu = (torch.randn(I, K, device="cuda", generator=g) * 0.03).to(torch.bfloat16)
+    bg = (torch.randn(I, device="cuda", generator=g) * 0.1).to(torch.bfloat16)
+    bu = (torch.randn(I, device="cuda", generator=g) * 0.1).to(torch.bfloat16)
+    w = ops.interleave_gate_up(wg, wu); b = ops.interleave_gate_up(bg, bu)
+    ref = torch.nn.functional.silu(x.float() @ wg.float().t() + bg.float()) * (x.float() @ wu.float().t() + bu.float())
+    for dt in (torch.float32, torch.bfloat16):
+        out = ops.gemm(x, w, bias=b, act="silu", gated=True, out_dtype=dt, tile_n=tile_n, split_k=split_k)
+        torch.cuda.synchronize()
+        assert out.shape == (M, 1024)
+        _check(out[:, :I], ref, dt == torch.bfloat16)
+        assert out[:, I:].abs().max().item() == 0.0
+
+
 def test_gemm_gated_silu():
     """Qwen2 MLP front half: silu(x Wg^T + bg) * (x Wu^T + bu) with the [32 gate | 32 up] row interleave;
     intermediate size 3420 is zero-padded to 3424 by the host-side weight prep."""

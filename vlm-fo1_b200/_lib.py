@@ -40,7 +40,7 @@ class GemmDesc(C.Structure):
                 ("A", C.c_void_p), ("lda", C.c_int64), ("W", C.c_void_p), ("ldw", C.c_int64),
                 ("D", C.c_void_p), ("ldd", C.c_int64), ("d_dtype", C.c_int32),
                 ("bias", C.c_void_p), ("bias_dtype", C.c_int32), ("act", C.c_int32),
-                ("residual", C.c_void_p), ("ldr", C.c_int64), ("gated", C.c_int32)]
+                ("residual", C.c_void_p), ("ldr", C.c_int64), ("gated", C.c_int32), ("tile_n", C.c_int32), ("split_k", C.c_int32)]
 
 
 class AttnDesc(C.Structure):

@@ -42,6 +42,7 @@ struct GemmArgs {
   // `counters[tile]` reduces them in split order (deterministic) and runs the epilogue
   int ksplit, kb_per_split;
   int coalesce;   // 1: epilogue stages rows through shared memory and writes full 128-byte lines (needs 16-byte aligned D / residual rows)
+  int debug_skip_a;   // tuning experiment only (env FO1_GEMM_SKIP_A): do not fetch A (results are garbage)
   int stages;     // ring depth actually used (<= kMaxStages): skinny problems trade the unused A rows for more stages in flight
   int a_stage_bytes, b_stage_bytes;
   int stage_tx;   // bytes one ring stage receives (A box rows x 128 B + BN x 128 B): skinny problems load only the live A rows
@@ -144,6 +145,65 @@ __device__ __forceinline__ void store_row32(const GemmArgs& g, float (&v)[32], i
         if (n + j < n_limit) dp[j] = v[j];
     }
   }
+}
+
+
+// 4-column variants for the cooperative split-K reduction
+__device__ __forceinline__ void add_bias4(float (&v)[4], const void* bias, int dtype, int n, int n_limit) {
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    if (n + j < n_limit) v[j] += load_bias(bias, dtype, n + j);
+}
+__device__ __forceinline__ void store_row4(const GemmArgs& g, float (&v)[4], int m, int n, int n_limit) {
+  const bool full = (n + 4 <= n_limit);
+  if (g.residual != nullptr) {
+    const __nv_bfloat16* rp = g.residual + (long long)m * g.ldr + n;
+    if (full && ((g.ldr & 3) == 0)) {
+      const uint2 rv = __ldg(reinterpret_cast<const uint2*>(rp));
+      v[0] += bf16_lo(rv.x); v[1] += bf16_hi(rv.x); v[2] += bf16_lo(rv.y); v[3] += bf16_hi(rv.y);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (n + j < n_limit) v[j] += __bfloat162float(rp[j]);
+    }
+  }
+  if (g.d_dtype == FO1_BF16) {
+    __nv_bfloat16* dp = static_cast<__nv_bfloat16*>(g.D) + (long long)m * g.ldd + n;
+    if (full && ((g.ldd & 3) == 0)) {
+      *reinterpret_cast<uint2*>(dp) = make_uint2(pack_bf16(v[0], v[1]), pack_bf16(v[2], v[3]));
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (n + j < n_limit) dp[j] = __float2bfloat16_rn(v[j]);
+    }
+  } else {
+    float* dp = static_cast<float*>(g.D) + (long long)m * g.ldd + n;
+    if (full && ((g.ldd & 3) == 0)) {
+      *reinterpret_cast<float4*>(dp) = make_float4(v[0], v[1], v[2], v[3]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (n + j < n_limit) dp[j] = v[j];
+    }
+  }
+}
+// sum of the ksplit parked partials of 4 consecutive columns (fixed order: deterministic), 4 loads in flight
+__device__ __forceinline__ void sum_splits4(float (&v)[4], const float* src, long long sstride, int ksplit) {
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+  int sp = 0;
+  for (; sp + 4 <= ksplit; sp += 4) {
+    const float4 t0 = __ldcg(reinterpret_cast<const float4*>(src + (long long)sp * sstride));
+    const float4 t1 = __ldcg(reinterpret_cast<const float4*>(src + (long long)(sp + 1) * sstride));
+    const float4 t2 = __ldcg(reinterpret_cast<const float4*>(src + (long long)(sp + 2) * sstride));
+    const float4 t3 = __ldcg(reinterpret_cast<const float4*>(src + (long long)(sp + 3) * sstride));
+    a.x += (t0.x + t1.x) + (t2.x + t3.x); a.y += (t0.y + t1.y) + (t2.y + t3.y);
+    a.z += (t0.z + t1.z) + (t2.z + t3.z); a.w += (t0.w + t1.w) + (t2.w + t3.w);
+  }
+  for (; sp < ksplit; ++sp) {
+    const float4 t = __ldcg(reinterpret_cast<const float4*>(src + (long long)sp * sstride));
+    a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
+  }
+  v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
 }
 
 
@@ -275,7 +335,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           ptx::mbar_wait(ptx::smem_u32(empty_bar + s), ph ^ 1);
           const uint32_t fb = ptx::smem_u32(full_bar + s);
           ptx::mbar_expect_tx(fb, (uint32_t)g.stage_tx);
-          ptx::tma_load_2d(ptx::smem_u32(smem_a + s * g.a_stage_bytes), &tmA, fb, kb * BK, m0);
+          if (!g.debug_skip_a) ptx::tma_load_2d(ptx::smem_u32(smem_a + s * g.a_stage_bytes), &tmA, fb, kb * BK, m0);
           ptx::tma_load_2d(ptx::smem_u32(smem_b + s * g.b_stage_bytes), &tmW, fb, kb * BK, n0);
         }
       }
@@ -353,28 +413,43 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         asm volatile("bar.sync 1, 256;" ::: "memory");
         if (*last_flag) {
           __threadfence();
-          if (m < g.M) {
-            const float* p0 = g.ws + ((long long)tile * g.ksplit * BM + quarter * 32 + lane) * BN;
-#pragma unroll 1
-            for (int c = p_beg; c < p_end; c += 32) {
-              if (n0 + c >= g.N) break;
-              float v[32];
-#pragma unroll
-              for (int j = 0; j < 32; ++j) v[j] = 0.f;
-              for (int sp = 0; sp < g.ksplit; ++sp) {
-                const float4* src = reinterpret_cast<const float4*>(p0 + (long long)sp * BM * BN + c);
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                  const float4 t = __ldcg(src + q);
-                  v[q * 4] += t.x; v[q * 4 + 1] += t.y; v[q * 4 + 2] += t.z; v[q * 4 + 3] += t.w;
-                }
-              }
-              if (g.bias != nullptr) add_bias32(v, g.bias, g.bias_dtype, n0 + c, g.N);
+          // all 256 epilogue threads share the tile: thread -> (row, 4 columns), row-major, so the partial reads and the
+          // output stores are coalesced and the ksplit loads of a thread are independent
+          const int et = threadIdx.x - 64;
+          const int rows_live = min(BM, g.M - m0);
+          const float* p0 = g.ws + (long long)tile * g.ksplit * BM * BN;
+          constexpr long long sstride = (long long)BM * BN;
+          if (!g.gated) {
+            constexpr int UPR = BN / 4;
+            for (int u = et; u < rows_live * UPR; u += kEpiThreads) {
+              const int r = u / UPR, c = (u % UPR) * 4;
+              if (n0 + c >= g.N) continue;
+              float v[4];
+              sum_splits4(v, p0 + r * BN + c, sstride, g.ksplit);
+              if (g.bias != nullptr) add_bias4(v, g.bias, g.bias_dtype, n0 + c, g.N);
               if (g.act != FO1_EPI_NONE) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], g.act);
+                for (int j = 0; j < 4; ++j) v[j] = apply_act(v[j], g.act);
               }
-              store_row32(g, v, m, n0 + c, g.N);
+              store_row4(g, v, m0 + r, n0 + c, g.N);
+            }
+          } else if constexpr (BN >= 64) {
+            // gate and up columns of a 64-column pair: out[:, (n0 + c) / 2 + j] = act(gate_j) * up_j
+            constexpr int UPR = BN / 8;
+            for (int u = et; u < rows_live * UPR; u += kEpiThreads) {
+              const int r = u / UPR, q = u % UPR;
+              const int c = (q >> 3) * 64 + (q & 7) * 4;   // gate column inside the tile; up = +32
+              if (n0 + c >= g.N) continue;
+              float gt[4], v[4];
+              sum_splits4(gt, p0 + r * BN + c, sstride, g.ksplit);
+              sum_splits4(v, p0 + r * BN + c + 32, sstride, g.ksplit);
+              if (g.bias != nullptr) {
+                add_bias4(gt, g.bias, g.bias_dtype, n0 + c, g.N);
+                add_bias4(v, g.bias, g.bias_dtype, n0 + c + 32, g.N);
+              }
+#pragma unroll
+              for (int j = 0; j < 4; ++j) v[j] = apply_act(gt[j], g.act) * v[j];
+              store_row4(g, v, m0 + r, ((n0 + (c & ~63)) >> 1) + (c & 31), g.N >> 1);
             }
           }
           if (warp == 2 && lane == 0) g.counters[tile] = 0;   // self-cleaning for the next launch
@@ -555,7 +630,9 @@ static int launch_gemm(const fo1_gemm_desc* d, cudaStream_t stream, int ksplit =
   g.gated = d->gated;
   g.tiles_m = ceil_div(d->M, BM);
   g.tiles_n = ceil_div(d->N, BN);
-  g.stage_tx = (a_rows + BN) * BK * 2;
+  static const bool tune_skip_a = getenv("FO1_GEMM_SKIP_A") != nullptr;
+  g.debug_skip_a = tune_skip_a ? 1 : 0;
+  g.stage_tx = ((tune_skip_a ? 0 : a_rows) + BN) * BK * 2;
   // the UMMA reads all 128 A rows of a stage: keep the full 16 KB slot unless only the live rows are loaded AND the
   // rows beyond them may alias the next stage's data (harmless: those accumulator rows are never stored)
   g.a_stage_bytes = (a_rows < BM) ? ((a_rows * BK * 2 + 1023) & ~1023) : BM * BK * 2;
@@ -610,6 +687,18 @@ int gemm_bf16(const fo1_gemm_desc* d, cudaStream_t stream) {
   FO1_CHECK_ARG(!d->gated || d->N % 64 == 0, "fo1_gemm_bf16: gated N=%d must be a multiple of 64", d->N);
   FO1_CHECK_ARG(d->ldd >= n_out, "fo1_gemm_bf16: ldd=%lld < %d", (long long)d->ldd, n_out);
   FO1_CHECK_ARG(d->residual == nullptr || d->ldr >= n_out, "fo1_gemm_bf16: ldr too small");
+  if (d->tile_n != 0) {   // pinned by the caller (tuning sweeps, tests of the split-K / tile variants)
+    const int ks = d->split_k > 0 ? d->split_k : 1;
+    FO1_CHECK_ARG(!d->gated || d->tile_n >= 64, "fo1_gemm_bf16: gated needs tile_n >= 64");
+    FO1_CHECK_ARG(ks == 1 || (long long)ceil_div(d->M, BM) * ceil_div(d->N, d->tile_n) <= (1 << 16), "fo1_gemm_bf16: too many tiles for split_k");
+    switch (d->tile_n) {
+      case 32: return launch_gemm<32>(d, stream, ks);
+      case 64: return launch_gemm<64>(d, stream, ks);
+      case 128: return launch_gemm<128>(d, stream, ks);
+      case 256: return launch_gemm<256>(d, stream, ks);
+      default: set_error("fo1_gemm_bf16: tile_n=%d unsupported (32, 64, 128, 256)", d->tile_n); return FO1_ERR_INVALID_ARG;
+    }
+  }
   // tile-width choice: widest tile that still yields >= 1 wave of CTAs, else narrower for occupancy
   const int sms = device_sm_count();
   const long long tm = ceil_div(d->M, BM);

@@ -61,93 +61,142 @@ __global__ void __launch_bounds__(128) kv_append_kernel(const bf16* __restrict__
   }
 }
 
-// Single-query GQA attention over the cache, split over the sequence (flash-decoding): one block per
-// (sequence, kv head, split); warp g of the block owns query head kvh*G + g, so no cross-warp reduction exists and
-// the register footprint stays small (the G warps re-read the same K/V rows, which the first reader leaves in L1).
-// A token's 128 dims are split over 8 lanes (16 dims = 32 B each), 4 tokens per warp iteration, 2 iterations in
-// flight.  Each warp writes an un-normalised partial (m, l, acc[128]); decode_attn_combine_kernel merges the splits.
+// Single-query GQA attention over the cache, split over the sequence (flash-decoding) and run on the tensor pipe:
+// one block per (sequence, kv head, split).  The G <= 8 query heads of the kv head are the rows of an m16n8k16 tile
+// (rows G..15 are zero), so K and V are read ONCE per kv head instead of once per query head.  Every warp owns
+// 16-key tiles of the split and loads its operands straight from global memory into mma fragments with 16-byte loads:
+// the contraction index of an mma is a free permutation, so lane (g, t) feeds dims [c*32 + t*8, +8) of key g as the
+// k-slots of two consecutive k-steps (Q uses the same permutation), and for P.V the two keys a B register pairs up are
+// transposed out of two row loads with one PRMT each; the output dims come out permuted and are un-permuted on the
+// smem write.  The block merges its warps' (m, l, acc) and writes one un-normalised partial per (head, split);
+// decode_attn_combine_kernel merges the splits.
 constexpr int kDecSplits = 8;
-template <int G>
-__global__ void __launch_bounds__(G * 32) decode_attn_kernel(const bf16* __restrict__ q, long long ldq, const bf16* __restrict__ kc,
-                                                             const bf16* __restrict__ vc, const int* __restrict__ cache_len, int cap,
-                                                             int kv_heads, float* __restrict__ part, float scale) {
+constexpr int kDecWarps = 4;
+__device__ __forceinline__ void mma_m16n8k16(float (&c)[4], uint32_t a0, uint32_t a2, uint32_t b0, uint32_t b1) {
+  // rows 8..15 of A (a1, a3) are zero: only the G query heads in rows 0..7 carry data
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%5}, {%7,%8}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a0), "r"(0u), "r"(a2), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
+  uint32_t r;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
+  return r;
+}
+__device__ __forceinline__ uint32_t pack2_bf16(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+__global__ void __launch_bounds__(kDecWarps * 32) decode_attn_kernel(const bf16* __restrict__ q, long long ldq, const bf16* __restrict__ kc,
+                                                                     const bf16* __restrict__ vc, const int* __restrict__ cache_len, int cap,
+                                                                     int kv_heads, int G, float* __restrict__ part, float scale) {
   constexpr int HD = 128;
+  __shared__ float sm_o[kDecWarps][8][HD];
+  __shared__ float sm_m[kDecWarps][8], sm_l[kDecWarps][8];
   const int b = blockIdx.x, kvh = blockIdx.y, sp = blockIdx.z;
   const int n = cache_len[b] + 1;  // the step's own K/V was appended at index cache_len[b]
-  const int chunk = ((n + kDecSplits - 1) / kDecSplits + 3) & ~3;
+  const int chunk = ((n + kDecSplits - 1) / kDecSplits + 15) & ~15;
   const int t_begin = sp * chunk, t_end = min(n, t_begin + chunk);
   const int kv_dim = kv_heads * HD;
-  const int g = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int grp = lane >> 3, sub = lane & 7;
-  const int head = kvh * G + g;
-  float qf[16];
-  {
-    const bf16* qp = q + (long long)b * ldq + (long long)head * HD + sub * 16;
-    const uint4 q0 = *reinterpret_cast<const uint4*>(qp), q1 = *reinterpret_cast<const uint4*>(qp + 8);
-    const uint32_t qu[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
-    const float sc = scale * 1.4426950408889634f;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  uint4 qa[4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { qf[2 * i] = bf16_lo(qu[i]) * sc; qf[2 * i + 1] = bf16_hi(qu[i]) * sc; }
+  for (int c = 0; c < 4; ++c) qa[c] = make_uint4(0u, 0u, 0u, 0u);
+  if (g < G) {
+    const bf16* qp = q + (long long)b * ldq + (long long)(kvh * G + g) * HD + t * 8;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) qa[c] = *reinterpret_cast<const uint4*>(qp + c * 32);
   }
-  float m = -INFINITY, l = 0.f, acc[16];
+  const float sc = scale * 1.4426950408889634f;
+  float m = -INFINITY, l = 0.f, o[16][4];
 #pragma unroll
-  for (int d = 0; d < 16; ++d) acc[d] = 0.f;
-  const bf16* kb = kc + (long long)b * cap * kv_dim + kvh * HD + sub * 16;
-  const bf16* vb = vc + (long long)b * cap * kv_dim + kvh * HD + sub * 16;
-  for (int t0 = t_begin; t0 < t_end; t0 += 8) {
-    uint4 kk[2][2], vv[2][2];
-    bool ok[2];
+  for (int j = 0; j < 16; ++j) { o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f; }
+  const bf16* kb = kc + (long long)b * cap * kv_dim + kvh * HD + t * 8;
+  const bf16* vb = vc + (long long)b * cap * kv_dim + kvh * HD + g * 8;
+  for (int t0 = t_begin + w * 16; t0 < t_end; t0 += kDecWarps * 16) {
+    uint4 kq[2][4], vq[4][2];
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const int t = t0 + u * 4 + grp;
-      ok[u] = t < t_end;
-      const long long off = (long long)(ok[u] ? t : t_begin) * kv_dim;
-      kk[u][0] = *reinterpret_cast<const uint4*>(kb + off); kk[u][1] = *reinterpret_cast<const uint4*>(kb + off + 8);
-      vv[u][0] = *reinterpret_cast<const uint4*>(vb + off); vv[u][1] = *reinterpret_cast<const uint4*>(vb + off + 8);
+    for (int i = 0; i < 2; ++i) {
+      const bf16* kp = kb + (long long)min(t0 + i * 8 + g, t_end - 1) * kv_dim;   // clamped rows are masked below
+#pragma unroll
+      for (int c = 0; c < 4; ++c) kq[i][c] = *reinterpret_cast<const uint4*>(kp + c * 32);
     }
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const uint32_t ku[8] = {kk[u][0].x, kk[u][0].y, kk[u][0].z, kk[u][0].w, kk[u][1].x, kk[u][1].y, kk[u][1].z, kk[u][1].w};
-      float s = 0.f;
+    for (int j = 0; j < 4; ++j) {
+      const bf16* vp = vb + (long long)min(t0 + (j >> 1) * 8 + 2 * t + (j & 1), t_end - 1) * kv_dim;  // finite data, weight 0
+      vq[j][0] = *reinterpret_cast<const uint4*>(vp);
+      vq[j][1] = *reinterpret_cast<const uint4*>(vp + 64);
+    }
+    float s[2][4];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { s = fmaf(bf16_lo(ku[i]), qf[2 * i], s); s = fmaf(bf16_hi(ku[i]), qf[2 * i + 1], s); }
-      s += __shfl_xor_sync(0xffffffffu, s, 1);
-      s += __shfl_xor_sync(0xffffffffu, s, 2);
-      s += __shfl_xor_sync(0xffffffffu, s, 4);
-      if (ok[u]) {
-        const uint32_t vu[8] = {vv[u][0].x, vv[u][0].y, vv[u][0].z, vv[u][0].w, vv[u][1].x, vv[u][1].y, vv[u][1].z, vv[u][1].w};
-        const float mn = fmaxf(m, s);
-        const float a = exp2f(m - mn), p = exp2f(s - mn);  // m = -inf on first use -> a = 0
-        l = l * a + p;
+    for (int i = 0; i < 2; ++i) {
+      s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          acc[2 * i] = fmaf(p, bf16_lo(vu[i]), acc[2 * i] * a);
-          acc[2 * i + 1] = fmaf(p, bf16_hi(vu[i]), acc[2 * i + 1] * a);
+      for (int c = 0; c < 4; ++c) {
+        mma_m16n8k16(s[i], qa[c].x, qa[c].y, kq[i][c].x, kq[i][c].y);
+        mma_m16n8k16(s[i], qa[c].z, qa[c].w, kq[i][c].z, kq[i][c].w);
+      }
+    }
+    float tmax = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        s[i][e] = (t0 + i * 8 + 2 * t + e < t_end) ? s[i][e] * sc : -INFINITY;
+        tmax = fmaxf(tmax, s[i][e]);
+      }
+    tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, 1));
+    tmax = fmaxf(tmax, __shfl_xor_sync(0xffffffffu, tmax, 2));
+    const float mn = fmaxf(m, tmax);            // key t0 is always valid: mn is finite
+    const float alpha = exp2f(m - mn);          // m = -inf on the first tile -> 0
+    const float p00 = exp2f(s[0][0] - mn), p01 = exp2f(s[0][1] - mn), p10 = exp2f(s[1][0] - mn), p11 = exp2f(s[1][1] - mn);
+    l = l * alpha + (p00 + p01) + (p10 + p11);
+    m = mn;
+    const uint32_t pa0 = pack2_bf16(p00, p01), pa2 = pack2_bf16(p10, p11);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const uint32_t ra[4] = {vq[0][h].x, vq[0][h].y, vq[0][h].z, vq[0][h].w}, rb[4] = {vq[1][h].x, vq[1][h].y, vq[1][h].z, vq[1][h].w};
+      const uint32_t rc[4] = {vq[2][h].x, vq[2][h].y, vq[2][h].z, vq[2][h].w}, rd[4] = {vq[3][h].x, vq[3][h].y, vq[3][h].z, vq[3][h].w};
+#pragma unroll
+      for (int p4 = 0; p4 < 4; ++p4) {
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int j = h * 8 + p4 * 2 + u;
+          const uint32_t sel = u ? 0x7632u : 0x5410u;
+          o[j][0] *= alpha; o[j][1] *= alpha;
+          mma_m16n8k16(o[j], pa0, pa2, prmt(ra[p4], rb[p4], sel), prmt(rc[p4], rd[p4], sel));
         }
-        m = mn;
       }
     }
   }
-  // combine the 4 token slots of the warp (lanes differing in bits 3 and 4 hold the same dims)
+  l += __shfl_xor_sync(0xffffffffu, l, 1);
+  l += __shfl_xor_sync(0xffffffffu, l, 2);
+  // accumulator column 2t+e of n-tile j = h*8+u is output dim h*64 + (2t+e)*8 + u
+  if (t == 0) { sm_m[w][g] = m; sm_l[w][g] = l; }
 #pragma unroll
-  for (int off = 8; off <= 16; off <<= 1) {
-    const float mo = __shfl_xor_sync(0xffffffffu, m, off), lo = __shfl_xor_sync(0xffffffffu, l, off);
-    const float mn = fmaxf(m, mo);
-    const float a = (m == -INFINITY) ? 0.f : exp2f(m - mn), bsc = (mo == -INFINITY) ? 0.f : exp2f(mo - mn);
-#pragma unroll
-    for (int d = 0; d < 16; ++d) {
-      const float ao = __shfl_xor_sync(0xffffffffu, acc[d], off);
-      acc[d] = acc[d] * a + ao * bsc;
-    }
-    l = l * a + lo * bsc;
-    m = mn;
+  for (int j = 0; j < 16; ++j) {
+    sm_o[w][g][(j >> 3) * 64 + (2 * t) * 8 + (j & 7)] = o[j][0];
+    sm_o[w][g][(j >> 3) * 64 + (2 * t + 1) * 8 + (j & 7)] = o[j][1];
   }
-  // partial record per (b, head, split): [m, l, pad, pad, acc[128]]
-  if (grp == 0) {
-    float* rec = part + (((long long)b * kv_heads * G + head) * kDecSplits + sp) * (HD + 4);
-    if (sub == 0) { rec[0] = m; rec[1] = l; }
+  __syncthreads();
+  const int d = threadIdx.x;   // kDecWarps * 32 == HD
+  for (int r = 0; r < G; ++r) {
+    float mm = -INFINITY;
 #pragma unroll
-    for (int d = 0; d < 16; d += 4) *reinterpret_cast<float4*>(rec + 4 + sub * 16 + d) = make_float4(acc[d], acc[d + 1], acc[d + 2], acc[d + 3]);
+    for (int ww = 0; ww < kDecWarps; ++ww) mm = fmaxf(mm, sm_m[ww][r]);
+    float num = 0.f, den = 0.f;
+#pragma unroll
+    for (int ww = 0; ww < kDecWarps; ++ww) {
+      const float f = (sm_m[ww][r] == -INFINITY) ? 0.f : exp2f(sm_m[ww][r] - mm);
+      num += sm_o[ww][r][d] * f;
+      den += sm_l[ww][r] * f;
+    }
+    // partial record per (b, head, split): [m, l, pad, pad, acc[128]]
+    float* rec = part + (((long long)b * kv_heads * G + kvh * G + r) * kDecSplits + sp) * (HD + 4);
+    if (d == 0) { rec[0] = mm; rec[1] = den; }
+    rec[4 + d] = num;
   }
 }
 
@@ -372,11 +421,8 @@ static int llm_layer(Model* m, int li, const bf16* x_in, bf16* x_out, const Laye
     ProfScope prof("decode_attn", 0.0, 0.0, s);
     const int G = c.llm_heads / c.llm_kv_heads;
     const float scale = 1.0f / sqrtf((float)hd);
-    if (G == 8) decode_attn_kernel<8><<<grid, 8 * 32, 0, s>>>(B_.qkv, ldq, kc, vc, st->cache_len, m->kv_cap, c.llm_kv_heads, B_.dec_part, scale);
-    else if (G == 4) decode_attn_kernel<4><<<grid, 4 * 32, 0, s>>>(B_.qkv, ldq, kc, vc, st->cache_len, m->kv_cap, c.llm_kv_heads, B_.dec_part, scale);
-    else if (G == 2) decode_attn_kernel<2><<<grid, 2 * 32, 0, s>>>(B_.qkv, ldq, kc, vc, st->cache_len, m->kv_cap, c.llm_kv_heads, B_.dec_part, scale);
-    else if (G == 1) decode_attn_kernel<1><<<grid, 1 * 32, 0, s>>>(B_.qkv, ldq, kc, vc, st->cache_len, m->kv_cap, c.llm_kv_heads, B_.dec_part, scale);
-    else { set_error("decode attention: GQA group %d unsupported", G); return FO1_ERR_UNSUPPORTED; }
+    if (G > 8 || hd != 128) { set_error("decode attention: GQA group %d / head_dim %d unsupported (group <= 8, head_dim 128)", G, hd); return FO1_ERR_UNSUPPORTED; }
+    decode_attn_kernel<<<grid, kDecWarps * 32, 0, s>>>(B_.qkv, ldq, kc, vc, st->cache_len, m->kv_cap, c.llm_kv_heads, G, B_.dec_part, scale);
     FO1_LAUNCH_CHECK();
     decode_attn_combine_kernel<<<dim3(rows, c.llm_heads), 128, 0, s>>>(B_.dec_part, B_.att, QD, c.llm_heads);
     FO1_LAUNCH_CHECK();

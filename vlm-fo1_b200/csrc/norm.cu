@@ -80,6 +80,90 @@ __global__ void __launch_bounds__(256) rownorm_kernel(const bf16* __restrict__ x
   }
 }
 
+// few rows (the decode step: one row per sequence): one BLOCK per row so a single 16-byte load per thread covers the
+// row and the whole GPU shares the work instead of rows/8 SMs.  Same arithmetic as rownorm_kernel.
+template <int MAXV, bool RMS>
+__global__ void __launch_bounds__(256) rownorm_block_kernel(const bf16* __restrict__ x, long long ldx, const bf16* __restrict__ gamma,
+                                                            const bf16* __restrict__ beta, bf16* __restrict__ y, long long ldy,
+                                                            int cols, float eps) {
+  __shared__ float red[2][8];
+  const bf16* xr = x + (long long)blockIdx.x * ldx;
+  bf16* yr = y + (long long)blockIdx.x * ldy;
+  const int nvec = cols >> 3, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  uint4 v[MAXV], g[MAXV], bt[MAXV];
+  float sum = 0.f, sq = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int vi = tid + i * 256;
+    g[i] = make_uint4(0x3f803f80u, 0x3f803f80u, 0x3f803f80u, 0x3f803f80u);
+    bt[i] = make_uint4(0, 0, 0, 0);
+    if (vi < nvec) {
+      v[i] = *reinterpret_cast<const uint4*>(xr + vi * 8);
+      if (gamma) g[i] = *reinterpret_cast<const uint4*>(gamma + vi * 8);
+      if (beta) bt[i] = *reinterpret_cast<const uint4*>(beta + vi * 8);
+      const uint32_t u[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float a = bf16_lo(u[j]), b = bf16_hi(u[j]);
+        sum += a + b;
+        sq += a * a + b * b;
+      }
+    }
+  }
+  auto block_sum2 = [&](float& a, float& b) {
+    a = warp_sum(a); b = warp_sum(b);
+    __syncthreads();
+    if (lane == 0) { red[0][warp] = a; red[1][warp] = b; }
+    __syncthreads();
+    a = 0.f; b = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { a += red[0][k]; b += red[1][k]; }
+  };
+  block_sum2(sum, sq);
+  const float inv_n = 1.0f / (float)cols;
+  float mean = 0.f, rstd;
+  if (RMS) {
+    rstd = rsqrtf(sq * inv_n + eps);
+  } else {
+    mean = sum * inv_n;
+    float var = 0.f, dummy = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+      if (tid + i * 256 < nvec) {
+        const uint32_t u[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float a = bf16_lo(u[j]) - mean, b = bf16_hi(u[j]) - mean;
+          var += a * a + b * b;
+        }
+      }
+    }
+    block_sum2(var, dummy);
+    rstd = rsqrtf(var * inv_n + eps);
+  }
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int vi = tid + i * 256;
+    if (vi < nvec) {
+      const uint32_t u[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+      const uint32_t gu[4] = {g[i].x, g[i].y, g[i].z, g[i].w}, bu[4] = {bt[i].x, bt[i].y, bt[i].z, bt[i].w};
+      uint32_t o[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float a = (bf16_lo(u[j]) - mean) * rstd, b = (bf16_hi(u[j]) - mean) * rstd;
+        if (RMS) {
+          a = __bfloat162float(__float2bfloat16_rn(a));
+          b = __bfloat162float(__float2bfloat16_rn(b));
+        }
+        a = a * bf16_lo(gu[j]) + bf16_lo(bu[j]);
+        b = b * bf16_hi(gu[j]) + bf16_hi(bu[j]);
+        o[j] = pack_bf16(a, b);
+      }
+      *reinterpret_cast<uint4*>(yr + vi * 8) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+  }
+}
+
 template <bool RMS>
 static int launch_rownorm(const bf16* x, long long ldx, const bf16* g, const bf16* b, bf16* y, long long ldy, int rows, int cols,
                           float eps, cudaStream_t s) {
@@ -87,6 +171,12 @@ static int launch_rownorm(const bf16* x, long long ldx, const bf16* g, const bf1
   FO1_CHECK_ARG(cols <= 8 * 32 * 32, "rownorm: cols=%d too large", cols);
   if (rows == 0) return FO1_OK;
   const int nvec = cols / 8;
+  if (rows <= 592 && nvec <= 512) {   // fewer rows than 4 per SM: spread each row over a block
+    if (nvec <= 256) rownorm_block_kernel<1, RMS><<<rows, 256, 0, s>>>(x, ldx, g, b, y, ldy, cols, eps);
+    else rownorm_block_kernel<2, RMS><<<rows, 256, 0, s>>>(x, ldx, g, b, y, ldy, cols, eps);
+    FO1_LAUNCH_CHECK();
+    return FO1_OK;
+  }
   const int maxv = ceil_div(nvec, 32);
   dim3 grid(ceil_div(rows, 8));
 #define FO1_RN(MV)                                                                              \

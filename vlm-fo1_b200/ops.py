@@ -26,9 +26,10 @@ def _require_cuda(*ts) -> None:
 
 def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, act: Optional[str] = None,
          residual: Optional[torch.Tensor] = None, out_dtype: torch.dtype = torch.bfloat16, gated: bool = False,
-         out: Optional[torch.Tensor] = None) -> torch.Tensor:
+         out: Optional[torch.Tensor] = None, tile_n: int = 0, split_k: int = 0) -> torch.Tensor:
     """out[M, N] = act(a[M, K] @ w[N, K]^T + bias) + residual   (nn.Linear semantics).
-    ``gated``: w/bias rows interleave [32 gate | 32 up] blocks -> out[M, N/2] = act(gate) * up."""
+    ``gated``: w/bias rows interleave [32 gate | 32 up] blocks -> out[M, N/2] = act(gate) * up.
+    ``tile_n`` / ``split_k`` pin the tile width and the in-kernel K split (0 = the library's choice)."""
     _require_cuda(a, w, bias, residual)
     assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16 and a.dim() == 2 and w.dim() == 2
     assert a.stride(1) == 1 and w.stride(1) == 1 and a.shape[1] == w.shape[1]
@@ -51,6 +52,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor] = None, 
         assert residual.dtype == torch.bfloat16 and residual.shape == (M, n_out) and residual.stride(1) == 1
         d.residual, d.ldr = residual.data_ptr(), residual.stride(0)
     d.gated = 1 if gated else 0
+    d.tile_n, d.split_k = int(tile_n), int(split_k)
     check(lib().fo1_gemm_bf16(C.byref(d), C.c_void_p(_stream())), "fo1_gemm_bf16")
     return out
 

@@ -61,12 +61,38 @@ struct ProfScope {
   ~ProfScope();
 };
 
+// ---- programmatic dependent launch (decode loop) ----------------------------------------------------
+// Inside a PdlScope every launch_k() carries cudaLaunchAttributeProgrammaticStreamSerialization: the kernel may start
+// while its predecessor on the stream is still draining.  Kernels launched this way call griddep_wait() before they
+// touch anything a predecessor wrote (and before they write anything a predecessor may still read) and
+// griddep_launch() as early as possible; both are no-ops for ordinary launches.
+extern thread_local bool t_pdl;
+struct PdlScope {
+  bool prev;
+  explicit PdlScope(bool on) : prev(t_pdl) { t_pdl = on; }
+  ~PdlScope() { t_pdl = prev; }
+};
+#ifdef __CUDACC__
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = t_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+#endif
+
 inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // ---- device helpers ---------------------------------------------------------------------------
 #ifdef __CUDACC__
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {

@@ -320,17 +320,36 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  griddep_launch();   // programmatic dependent launch: the next kernel of the stream may begin its own prologue now
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================
     if (ptx::elect_one()) {
       uint32_t it = 0;
+      bool first = true;
       for (int work = blockIdx.x; work < num_tiles; work += gridDim.x) {
         const int tile = work / g.ksplit, split = work - tile * g.ksplit;
         const int m0 = (tile / g.tiles_n) * BM;
         const int n0 = (tile % g.tiles_n) * BN;
         const int kb0 = split * g.kb_per_split, kb1 = min(num_kb_total, kb0 + g.kb_per_split);
-        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+        int kb = kb0;
+        if (first) {
+          // W never depends on the previous kernel of the stream: fill the ring with weight tiles BEFORE waiting for
+          // it to finish, then add the A tiles to the same barriers (all slots are free on the first lap)
+          first = false;
+          const int pre = min(S, kb1 - kb0);
+          for (int i = 0; i < pre; ++i) {
+            const uint32_t fb = ptx::smem_u32(full_bar + i);
+            ptx::mbar_expect_tx(fb, (uint32_t)g.stage_tx);
+            ptx::tma_load_2d(ptx::smem_u32(smem_b + i * g.b_stage_bytes), &tmW, fb, (kb0 + i) * BK, n0);
+          }
+          griddep_wait();
+          if (!g.debug_skip_a)
+            for (int i = 0; i < pre; ++i)
+              ptx::tma_load_2d(ptx::smem_u32(smem_a + i * g.a_stage_bytes), &tmA, ptx::smem_u32(full_bar + i), (kb0 + i) * BK, m0);
+          it = pre; kb = kb0 + pre;
+        }
+        for (; kb < kb1; ++kb, ++it) {
           const uint32_t s = it % S, ph = (it / S) & 1;
           ptx::mbar_wait(ptx::smem_u32(empty_bar + s), ph ^ 1);
           const uint32_t fb = ptx::smem_u32(full_bar + s);
@@ -380,6 +399,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     const int p_beg = kSplit32 ? half * (BN / 2) : 0, p_end = kSplit32 ? (half + 1) * (BN / 2) : (half == 0 ? BN : 0);
     const int g_beg = kSplit64 ? half * (BN / 2) : 0, g_end = kSplit64 ? (half + 1) * (BN / 2) : (half == 0 ? BN : 0);
     uint32_t tcount = 0;
+    griddep_wait();   // residual reads / output writes are ordered after the previous kernel
     for (int work = blockIdx.x; work < num_tiles; work += gridDim.x, ++tcount) {
       const int tile = work / g.ksplit, split = work - tile * g.ksplit;
       const int m0 = (tile / g.tiles_n) * BM;
@@ -665,7 +685,7 @@ static int launch_gemm(const fo1_gemm_desc* d, cudaStream_t stream, int ksplit =
   if (g_prof_on) snprintf(tag, sizeof(tag), "%s:%dx%dx%d%s", d->M <= 128 ? "gemm_skinny" : "gemm", d->M, d->N, d->K, d->gated ? ":gated" : "");
   ProfScope prof(tag, 2.0 * d->M * (double)d->N * d->K,
                  2.0 * ((double)d->M * d->K + (double)d->N * d->K + (double)d->M * (d->gated ? d->N / 2 : d->N)), stream);
-  gemm_bf16_tcgen05_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(tmA, tmW, g);
+  launch_k(gemm_bf16_tcgen05_kernel<BN>, dim3(grid), dim3(kGemmThreads), Cfg::kSmemBytes, stream, tmA, tmW, g);
   FO1_LAUNCH_CHECK();
   return FO1_OK;
 }
@@ -705,14 +725,14 @@ int gemm_bf16(const fo1_gemm_desc* d, cudaStream_t stream) {
   if (d->N >= 256 && tm * ceil_div(d->N, 256) >= sms) return launch_gemm<256>(d, stream);
   if (d->N >= 128 && tm * ceil_div(d->N, 128) >= sms) return launch_gemm<128>(d, stream);
   if (d->gated || tm * ceil_div(d->N, 64) >= sms) return launch_gemm<64>(d, stream);
-  // skinny problems (decode: M = batch, weight streaming): narrow tiles, deep ring, and split-K until every SM
-  // pulls weights (>= 8 k-blocks per split so the ring still fills)
-  const long long t32 = tm * ceil_div(d->N, 32);
+  // skinny problems (decode: M = batch, weight streaming): 64-wide tiles (the activation tile every CTA re-reads is
+  // half the weight tile) and split-K until one wave of CTAs pulls weights, >= 8 k-blocks per split so the ring
+  // still fills (measured: scripts/sweep_skinny.py, profiles/r01_sweep_skinny.json)
+  const int bn = d->N >= 512 ? 64 : 32;
+  const long long t = tm * ceil_div(d->N, bn);
   int ks = 1;
-  if (t32 * 2 <= sms) {   // split K only while (tiles x splits) still fits one wave: a second round doubles the latency
-    ks = (int)std::min<long long>(std::min<long long>(8, sms / t32), std::max(1, ceil_div(d->K, BK) / 8));
-  }
-  return launch_gemm<32>(d, stream, ks);
+  if (t * 2 <= sms) ks = (int)std::min<long long>(std::min<long long>(8, sms / t), std::max(1, ceil_div(d->K, BK) / 8));
+  return bn == 64 ? launch_gemm<64>(d, stream, ks) : launch_gemm<32>(d, stream, ks);
 }
 
 }  // namespace fo1

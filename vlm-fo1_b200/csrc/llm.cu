@@ -31,6 +31,8 @@ __global__ void __launch_bounds__(256) build_embeds_kernel(const int* __restrict
 // x[b] = table[tok[b]]
 __global__ void __launch_bounds__(256) embed_tokens_kernel(const int* __restrict__ tok, const bf16* __restrict__ table,
                                                            bf16* __restrict__ out, int H) {
+  griddep_launch();
+  griddep_wait();
   const bf16* src = table + (long long)tok[blockIdx.x] * H;
   bf16* dst = out + (long long)blockIdx.x * H;
   for (int c = threadIdx.x * 8; c < H; c += blockDim.x * 8) *reinterpret_cast<uint4*>(dst + c) = *reinterpret_cast<const uint4*>(src + c);
@@ -48,19 +50,6 @@ __global__ void __launch_bounds__(128) kv_store_kernel(const bf16* __restrict__ 
     *reinterpret_cast<uint4*>(vc + slot + c) = *reinterpret_cast<const uint4*>(kp + kv_dim + c);
   }
 }
-// decode: append row b at index cache_len[b]
-__global__ void __launch_bounds__(128) kv_append_kernel(const bf16* __restrict__ qkv, long long ld, int q_dim, int kv_dim,
-                                                        const int* __restrict__ cache_len, bf16* __restrict__ kc,
-                                                        bf16* __restrict__ vc, int cap) {
-  const int b = blockIdx.x;
-  const long long slot = ((long long)b * cap + cache_len[b]) * kv_dim;
-  const bf16* kp = qkv + (long long)b * ld + q_dim;
-  for (int c = threadIdx.x * 8; c < kv_dim; c += blockDim.x * 8) {
-    *reinterpret_cast<uint4*>(kc + slot + c) = *reinterpret_cast<const uint4*>(kp + c);
-    *reinterpret_cast<uint4*>(vc + slot + c) = *reinterpret_cast<const uint4*>(kp + kv_dim + c);
-  }
-}
-
 // Single-query GQA attention over the cache, split over the sequence (flash-decoding) and run on the tensor pipe:
 // one block per (sequence, kv head, split).  The G <= 8 query heads of the kv head are the rows of an m16n8k16 tile
 // (rows G..15 are zero), so K and V are read ONCE per kv head instead of once per query head.  Every warp owns
@@ -95,6 +84,8 @@ __global__ void __launch_bounds__(kDecWarps * 32) decode_attn_kernel(const bf16*
   __shared__ float sm_o[kDecWarps][8][HD];
   __shared__ float sm_m[kDecWarps][8], sm_l[kDecWarps][8];
   const int b = blockIdx.x, kvh = blockIdx.y, sp = blockIdx.z;
+  griddep_launch();
+  griddep_wait();
   const int n = cache_len[b] + 1;  // the step's own K/V was appended at index cache_len[b]
   const int chunk = ((n + kDecSplits - 1) / kDecSplits + 15) & ~15;
   const int t_begin = sp * chunk, t_end = min(n, t_begin + chunk);
@@ -205,6 +196,8 @@ __global__ void __launch_bounds__(128) decode_attn_combine_kernel(const float* _
                                                                   int q_heads) {
   constexpr int HD = 128;
   const int b = blockIdx.x, h = blockIdx.y, d = threadIdx.x;
+  griddep_launch();
+  griddep_wait();
   const float* rec = part + (((long long)b * q_heads + h) * kDecSplits) * (HD + 4);
   float mm = -INFINITY;
 #pragma unroll
@@ -222,6 +215,8 @@ __global__ void __launch_bounds__(128) decode_attn_combine_kernel(const float* _
 
 // greedy token: lowest index among the maxima of a fp32 logits row
 __global__ void __launch_bounds__(1024) argmax_kernel(const float* __restrict__ logits, int V, int* __restrict__ out) {
+  griddep_launch();
+  griddep_wait();
   const float* row = logits + (long long)blockIdx.x * V;
   float best = -INFINITY;
   int bi = 0x7fffffff;
@@ -277,6 +272,8 @@ __global__ void decode_init_kernel(DecodeState st, const int* __restrict__ seq_l
 __global__ void __launch_bounds__(1024) decode_update_kernel(DecodeState st, int n_stop, int pad_id, int max_new,
                                                              int* __restrict__ out_tokens, int* __restrict__ out_lens, int B,
                                                              int advance_cache) {
+  griddep_launch();
+  griddep_wait();
   const int step = *st.step;
   __syncthreads();
   for (int b = threadIdx.x; b < B; b += blockDim.x) {
@@ -401,8 +398,8 @@ static int llm_layer(Model* m, int li, const bf16* x_in, bf16* x_out, const Laye
   bf16* vc = static_cast<bf16*>(m->kv_cache) + ((size_t)c.llm_layers + li) * layer_stride;
   FO1_RUN(rmsnorm(x_in, H, L.ln1, B_.xn, H, rows, H, c.rms_eps, s));
   FO1_RUN(linear(B_.xn, H, L.qkv_w, H, B_.qkv, ldq, FO1_BF16, rows, ldq, H, L.qkv_b, FO1_BF16, FO1_EPI_NONE, nullptr, 0, 0, s));
-  FO1_RUN(rope_apply(B_.qkv, ldq, cs, rows, c.llm_heads + c.llm_kv_heads, hd, s));   // q|k heads are contiguous in the packed row
   if (prefill) {
+    FO1_RUN(rope_apply(B_.qkv, ldq, cs, rows, c.llm_heads + c.llm_kv_heads, hd, s));   // q|k heads are contiguous in the packed row
     if (!dry) {
       kv_store_kernel<<<rows, 128, 0, s>>>(B_.qkv, ldq, QD, KD, d_row_seq, d_row_t, kc, vc, m->kv_cap);
       FO1_LAUNCH_CHECK();
@@ -415,16 +412,15 @@ static int llm_layer(Model* m, int li, const bf16* x_in, bf16* x_out, const Laye
     a.scale = 1.0f / sqrtf((float)hd); a.causal = 1;
     FO1_RUN(attention_varlen(a, s));
   } else if (!dry) {
-    kv_append_kernel<<<rows, 128, 0, s>>>(B_.qkv, ldq, QD, KD, st->cache_len, kc, vc, m->kv_cap);
-    FO1_LAUNCH_CHECK();
+    FO1_RUN(rope_kv_append(B_.qkv, ldq, cs, rows, c.llm_heads, c.llm_kv_heads, hd, st->cache_len, kc, vc, m->kv_cap, s));
     dim3 grid(rows, c.llm_kv_heads, kDecSplits);
     ProfScope prof("decode_attn", 0.0, 0.0, s);
     const int G = c.llm_heads / c.llm_kv_heads;
     const float scale = 1.0f / sqrtf((float)hd);
     if (G > 8 || hd != 128) { set_error("decode attention: GQA group %d / head_dim %d unsupported (group <= 8, head_dim 128)", G, hd); return FO1_ERR_UNSUPPORTED; }
-    decode_attn_kernel<<<grid, kDecWarps * 32, 0, s>>>(B_.qkv, ldq, kc, vc, st->cache_len, m->kv_cap, c.llm_kv_heads, G, B_.dec_part, scale);
+    launch_k(decode_attn_kernel, grid, dim3(kDecWarps * 32), 0, s, B_.qkv, (long long)ldq, kc, vc, st->cache_len, m->kv_cap, c.llm_kv_heads, G, B_.dec_part, scale);
     FO1_LAUNCH_CHECK();
-    decode_attn_combine_kernel<<<dim3(rows, c.llm_heads), 128, 0, s>>>(B_.dec_part, B_.att, QD, c.llm_heads);
+    launch_k(decode_attn_combine_kernel, dim3(rows, c.llm_heads), dim3(128), 0, s, B_.dec_part, B_.att, (long long)QD, c.llm_heads);
     FO1_LAUNCH_CHECK();
   }
   FO1_RUN(linear(B_.att, QD, L.o_w, QD, B_.x_mid, H, FO1_BF16, rows, H, QD, nullptr, 0, FO1_EPI_NONE, x_in, H, 0, s));
@@ -512,8 +508,11 @@ static int llm_generate_impl(Model* m, fo1_generate_desc* d, cudaStream_t s, boo
   // ---- greedy decode: every step is the SAME launch sequence reading its state from device memory; the first
   // step runs eagerly (warms every kernel), the second is captured into a CUDA graph that is replayed afterwards ----
   LlmState* ls = static_cast<LlmState*>(m->llm_state);
+  // programmatic dependent launch: each kernel of the step starts (prologue, weight prefetch) while its predecessor drains
+  const bool use_pdl = getenv("FO1_NO_PDL") == nullptr;
   auto enqueue_step = [&]() -> int {
-    embed_tokens_kernel<<<B, 256, 0, s>>>(st.cur_tok, m->llm.embed, xa, H);
+    PdlScope pdl(use_pdl);
+    launch_k(embed_tokens_kernel, dim3(B), dim3(256), 0, s, st.cur_tok, m->llm.embed, xa, H);
     FO1_LAUNCH_CHECK();
     FO1_TRY(mrope_table(st.pos3, cs_dec, B, hd, c.mrope_section[0], c.mrope_section[1], c.mrope_section[2], c.rope_theta, s));
     const bf16* xin = xa;
@@ -524,9 +523,9 @@ static int llm_generate_impl(Model* m, fo1_generate_desc* d, cudaStream_t s, boo
     }
     FO1_TRY(rmsnorm(xin, H, m->llm.norm, lastn, H, B, H, c.rms_eps, s));
     FO1_TRY(linear(lastn, H, m->llm.lm_head, H, logits, V, FO1_F32, B, V, H, nullptr, 0, FO1_EPI_NONE, nullptr, 0, 0, s));
-    argmax_kernel<<<B, 1024, 0, s>>>(logits, V, st.new_tok);
+    launch_k(argmax_kernel, dim3(B), dim3(1024), 0, s, logits, V, st.new_tok);
     FO1_LAUNCH_CHECK();
-    decode_update_kernel<<<1, upd_threads, 0, s>>>(st, d->n_stop_ids, d->pad_id, d->max_new_tokens, d->out_tokens, d->out_lens, B, 1);
+    launch_k(decode_update_kernel, dim3(1), dim3(upd_threads), 0, s, st, d->n_stop_ids, d->pad_id, d->max_new_tokens, d->out_tokens, d->out_lens, B, 1);
     FO1_LAUNCH_CHECK();
     return FO1_OK;
   };
@@ -537,7 +536,7 @@ static int llm_generate_impl(Model* m, fo1_generate_desc* d, cudaStream_t s, boo
   for (int step = 1; step < d->max_new_tokens; ++step) {
     if (gexec != nullptr) {
       if (cudaGraphLaunch(gexec, s) != cudaSuccess) { set_error("cudaGraphLaunch failed: %s", cudaGetErrorString(cudaGetLastError())); rc = FO1_ERR_CUDA; break; }
-      count_launch((uint64_t)c.llm_layers * 11 + 5);
+      count_launch((uint64_t)c.llm_layers * 9 + 6);
     } else if (want_graph && step == 2) {
       cudaGraph_t graph = nullptr;
       if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {

@@ -87,6 +87,8 @@ __global__ void __launch_bounds__(256) rownorm_block_kernel(const bf16* __restri
                                                             const bf16* __restrict__ beta, bf16* __restrict__ y, long long ldy,
                                                             int cols, float eps) {
   __shared__ float red[2][8];
+  griddep_launch();
+  griddep_wait();
   const bf16* xr = x + (long long)blockIdx.x * ldx;
   bf16* yr = y + (long long)blockIdx.x * ldy;
   const int nvec = cols >> 3, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -172,8 +174,8 @@ static int launch_rownorm(const bf16* x, long long ldx, const bf16* g, const bf1
   if (rows == 0) return FO1_OK;
   const int nvec = cols / 8;
   if (rows <= 592 && nvec <= 512) {   // fewer rows than 4 per SM: spread each row over a block
-    if (nvec <= 256) rownorm_block_kernel<1, RMS><<<rows, 256, 0, s>>>(x, ldx, g, b, y, ldy, cols, eps);
-    else rownorm_block_kernel<2, RMS><<<rows, 256, 0, s>>>(x, ldx, g, b, y, ldy, cols, eps);
+    if (nvec <= 256) launch_k(rownorm_block_kernel<1, RMS>, dim3(rows), dim3(256), 0, s, x, ldx, g, b, y, ldy, cols, eps);
+    else launch_k(rownorm_block_kernel<2, RMS>, dim3(rows), dim3(256), 0, s, x, ldx, g, b, y, ldy, cols, eps);
     FO1_LAUNCH_CHECK();
     return FO1_OK;
   }

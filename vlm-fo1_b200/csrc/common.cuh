@@ -116,8 +116,29 @@ __device__ __forceinline__ uint4 ldg_nc_v4(const void* p) {
                : "l"(p));
   return r;
 }
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
-__device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float ex2_approx(float x) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+// exact-erf GELU, x * Phi(x), with ONE special-function op per element (the GEMM epilogues are issue/MUFU-bound on
+// erff): erfc(z) = 2^P(z) on z = |x|/sqrt(2) in [0, 4], P the degree-7 Chebyshev fit of log2(erfc) (relative error
+// 4.3e-6, clamped beyond z = 4 where erfc < 1.6e-8); Phi(x) = erfc(z)/2 for x < 0, 1 - erfc(z)/2 otherwise.
+// |gelu_erf(x) - x*Phi(x)| <= 7e-7 absolute, 4.2e-6 relative over [-8, 8] (fp32 evaluation, checked against scipy).
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float z = fminf(fabsf(x) * 0.70710678118654752440f, 4.0f);
+  float p = -2.1777637812192552e-05f;
+  p = fmaf(p, z, 0.0005068330792710185f);
+  p = fmaf(p, z, -0.005339398048818111f);
+  p = fmaf(p, z, 0.03423144668340683f);
+  p = fmaf(p, z, -0.15289084613323212f);
+  p = fmaf(p, z, -0.9167589545249939f);
+  p = fmaf(p, z, -1.6281543970108032f);
+  p = fmaf(p, z, 6.178960575198289e-06f);
+  const float q = 0.5f * ex2_approx(p);
+  return x * (x < 0.f ? q : 1.0f - q);
+}
+__device__ __forceinline__ float silu(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 #endif
 
 }  // namespace fo1

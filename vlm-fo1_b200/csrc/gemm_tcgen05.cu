@@ -95,6 +95,16 @@ __device__ __forceinline__ float apply_act(float x, int act) {
   if (act == FO1_EPI_SILU) return silu(x);
   return x;
 }
+// 32 values of one accumulator row: the activation switch is taken once, not per element
+__device__ __forceinline__ void apply_act32(float (&v)[32], int act) {
+  if (act == FO1_EPI_GELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = gelu_erf(v[j]);
+  } else if (act == FO1_EPI_SILU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = silu(v[j]);
+  }
+}
 
 // residual add + store of 32 consecutive output columns of one row
 __device__ __forceinline__ void store_row32(const GemmArgs& g, float (&v)[32], int m, int n, int n_limit) {
@@ -277,9 +287,54 @@ __device__ __forceinline__ void flush_rows(const GemmArgs& g, const uint8_t* stg
   __syncwarp();
 }
 
+// Split-K: the last CTA to park its partial reduces the tile.  Kept out of line so that its registers do not weigh
+// on the allocation of the main epilogue (the kernel runs at the 168-register cap of 3 warps per SM sub-partition).
+template <int BN>
+__device__ __noinline__ void splitk_finish(const GemmArgs& g, int tile, int m0, int n0) {
+  // all 256 epilogue threads share the tile: thread -> (row, 4 columns), row-major, so the partial reads and the
+  // output stores are coalesced and the ksplit loads of a thread are independent
+  const int et = threadIdx.x - 64;
+  const int rows_live = min(BM, g.M - m0);
+  const float* p0 = g.ws + (long long)tile * g.ksplit * BM * BN;
+  constexpr long long sstride = (long long)BM * BN;
+  if (!g.gated) {
+    constexpr int UPR = BN / 4;
+    for (int u = et; u < rows_live * UPR; u += kEpiThreads) {
+      const int r = u / UPR, c = (u % UPR) * 4;
+      if (n0 + c >= g.N) continue;
+      float v[4];
+      sum_splits4(v, p0 + r * BN + c, sstride, g.ksplit);
+      if (g.bias != nullptr) add_bias4(v, g.bias, g.bias_dtype, n0 + c, g.N);
+      if (g.act != FO1_EPI_NONE) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v[j] = apply_act(v[j], g.act);
+      }
+      store_row4(g, v, m0 + r, n0 + c, g.N);
+    }
+  } else if constexpr (BN >= 64) {
+    // gate and up columns of a 64-column pair: out[:, (n0 + c) / 2 + j] = act(gate_j) * up_j
+    constexpr int UPR = BN / 8;
+    for (int u = et; u < rows_live * UPR; u += kEpiThreads) {
+      const int r = u / UPR, q = u % UPR;
+      const int c = (q >> 3) * 64 + (q & 7) * 4;   // gate column inside the tile; up = +32
+      if (n0 + c >= g.N) continue;
+      float gt[4], v[4];
+      sum_splits4(gt, p0 + r * BN + c, sstride, g.ksplit);
+      sum_splits4(v, p0 + r * BN + c + 32, sstride, g.ksplit);
+      if (g.bias != nullptr) {
+        add_bias4(gt, g.bias, g.bias_dtype, n0 + c, g.N);
+        add_bias4(v, g.bias, g.bias_dtype, n0 + c + 32, g.N);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = apply_act(gt[j], g.act) * v[j];
+      store_row4(g, v, m0 + r, ((n0 + (c & ~63)) >> 1) + (c & 31), g.N >> 1);
+    }
+  }
+}
+
 template <int BN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
-gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const GemmArgs g) {
+gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const __grid_constant__ GemmArgs g) {
   using Cfg = GemmCfg<BN>;
   const int S = g.stages;
   extern __shared__ uint8_t smem_raw[];
@@ -433,45 +488,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         asm volatile("bar.sync 1, 256;" ::: "memory");
         if (*last_flag) {
           __threadfence();
-          // all 256 epilogue threads share the tile: thread -> (row, 4 columns), row-major, so the partial reads and the
-          // output stores are coalesced and the ksplit loads of a thread are independent
-          const int et = threadIdx.x - 64;
-          const int rows_live = min(BM, g.M - m0);
-          const float* p0 = g.ws + (long long)tile * g.ksplit * BM * BN;
-          constexpr long long sstride = (long long)BM * BN;
-          if (!g.gated) {
-            constexpr int UPR = BN / 4;
-            for (int u = et; u < rows_live * UPR; u += kEpiThreads) {
-              const int r = u / UPR, c = (u % UPR) * 4;
-              if (n0 + c >= g.N) continue;
-              float v[4];
-              sum_splits4(v, p0 + r * BN + c, sstride, g.ksplit);
-              if (g.bias != nullptr) add_bias4(v, g.bias, g.bias_dtype, n0 + c, g.N);
-              if (g.act != FO1_EPI_NONE) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) v[j] = apply_act(v[j], g.act);
-              }
-              store_row4(g, v, m0 + r, n0 + c, g.N);
-            }
-          } else if constexpr (BN >= 64) {
-            // gate and up columns of a 64-column pair: out[:, (n0 + c) / 2 + j] = act(gate_j) * up_j
-            constexpr int UPR = BN / 8;
-            for (int u = et; u < rows_live * UPR; u += kEpiThreads) {
-              const int r = u / UPR, q = u % UPR;
-              const int c = (q >> 3) * 64 + (q & 7) * 4;   // gate column inside the tile; up = +32
-              if (n0 + c >= g.N) continue;
-              float gt[4], v[4];
-              sum_splits4(gt, p0 + r * BN + c, sstride, g.ksplit);
-              sum_splits4(v, p0 + r * BN + c + 32, sstride, g.ksplit);
-              if (g.bias != nullptr) {
-                add_bias4(gt, g.bias, g.bias_dtype, n0 + c, g.N);
-                add_bias4(v, g.bias, g.bias_dtype, n0 + c + 32, g.N);
-              }
-#pragma unroll
-              for (int j = 0; j < 4; ++j) v[j] = apply_act(gt[j], g.act) * v[j];
-              store_row4(g, v, m0 + r, ((n0 + (c & ~63)) >> 1) + (c & 31), g.N >> 1);
-            }
-          }
+          splitk_finish<BN>(g, tile, m0, n0);
           if (warp == 2 && lane == 0) g.counters[tile] = 0;   // self-cleaning for the next launch
         }
         asm volatile("bar.sync 1, 256;" ::: "memory");   // last_flag is reused by the next work item
@@ -495,10 +512,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[ci & 1][j]);
           if (ci + 1 < NCH && n0 + c + 32 < g.N) ptx::tmem_ld_32x32(taddr + c + 32, r[(ci + 1) & 1]);
           if (g.bias != nullptr) add_bias32(v, g.bias, g.bias_dtype, n0 + c, g.N);
-          if (g.act != FO1_EPI_NONE) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], g.act);
-          }
+          apply_act32(v, g.act);
           if (!g.coalesce) {
             if (m < g.M) store_row32(g, v, m, n0 + c, g.N);
           } else if (g.d_dtype == FO1_BF16) {
@@ -527,8 +541,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             add_bias32(gt, g.bias, g.bias_dtype, n0 + c, g.N);
             add_bias32(v, g.bias, g.bias_dtype, n0 + c + 32, g.N);
           }
+          apply_act32(gt, g.act);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = apply_act(gt[j], g.act) * v[j];
+          for (int j = 0; j < 32; ++j) v[j] = gt[j] * v[j];
           if (!g.coalesce) {
             if (m < g.M) store_row32(g, v, m, (n0 + c) >> 1, g.N >> 1);
           } else {

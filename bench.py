@@ -154,6 +154,7 @@ def cpu_arm(args, CK, E, cfg, steps):
 
 
 def main():
+    out = _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -201,7 +202,7 @@ def main():
                                  "sample": CPU_SAMPLE_NOTE.format(tok=args.cpu_tokens, T=args.tokens),
                                  "stage_seconds": detail},
                 "e2e": {"value": ips, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        print(json.dumps(line), file=out, flush=True)
         return
 
     # ------------------------------------------------------------------ fo1 arm
@@ -262,7 +263,7 @@ def main():
             step(resident)
         ms = timed(lambda: step(resident), args.steps)
         if rank == 0:
-            print(json.dumps({"profile_run": True, "ms_per_step": ms / args.steps, "launches": int(L.fo1_launch_count())}))
+            print(json.dumps({"profile_run": True, "ms_per_step": ms / args.steps, "launches": int(L.fo1_launch_count())}), file=out, flush=True)
         return
     for _ in range(max(args.warmup, 3)):
         step(resident)
@@ -344,10 +345,20 @@ def main():
                                         "sample": CPU_SAMPLE_NOTE.format(tok=args.cpu_tokens, T=args.tokens), "stage_seconds": detail}
             except Exception as exc:  # the baseline is a report, never a reason to lose the GPU number
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {exc!r}"}
-        print(json.dumps(line))
+        print(json.dumps(line), file=out, flush=True)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def _claim_stdout():
+    """stdout carries exactly ONE JSON line: libraries that print from C (NCCL's version banner) go to stderr instead.
+    Returns a text handle on the original stdout."""
+    sys.stdout.flush()
+    real = os.dup(1)
+    os.dup2(2, 1)
+    sys.stdout = os.fdopen(os.dup(2), "w", buffering=1)
+    return os.fdopen(real, "w", buffering=1)
 
 
 if __name__ == "__main__":

@@ -320,7 +320,7 @@ def main():
                                 "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": ach / peaks["tflops"], "traffic": None,
                                 "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['source']})",
                                 "launches": g["launches"], "ms_per_launch": g["ms"] / g["launches"], "share_of_step": g["ms"] / (ms / args.steps)}
-        h = prof.get("hfre_sweep") or prof.get("hfre_gather")
+        h = prof.get("hfre_sweep_mma") or prof.get("hfre_sweep") or prof.get("hfre_gather")
         if h and h["ms"] > 0:
             tot = 0
             for s in host:
@@ -334,7 +334,7 @@ def main():
                 ups = [H0 // sh[0] for sh in shapes[:4]] + [1] * 4
                 tot += HF.algorithmic_bytes(shapes, bl, scales, ups, s.boxes.shape[0], cfg.region_dim)["unique_bytes"]
             ach = tot / h["ms"] / 1e6
-            line["roofline_hfre"] = {"kernel": "hfre_sweep_kernel" if "hfre_sweep" in prof else "hfre_gather_kernel", "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+            line["roofline_hfre"] = {"kernel": "hfre_sweep_mma_kernel" if "hfre_sweep_mma" in prof else ("hfre_sweep_kernel" if "hfre_sweep" in prof else "hfre_gather_kernel"), "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                                      "frac": ach / peaks["hbm_gbs"], "traffic": None, "algorithmic_bytes": tot, "ms": h["ms"],
                                      "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peaks['source']})"}
         # ---- CPU baseline (rank 0, N = 1 only) ----

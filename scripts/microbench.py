@@ -119,10 +119,10 @@ if __name__ == "__main__":
     res = []
     print("device", torch.cuda.get_device_name(0), "cpus", os.cpu_count(), flush=True)
     if "hfre" in which:
-        for algo in (1, 2):
+        for algo in (1, 2, 3):
             bench_hfre(res, algo=algo)
-        bench_hfre(res, B=8, S=896, N=32, algo=1)     # COCO-like box count (mean 31.5)
-        bench_hfre(res, B=8, S=896, N=32, algo=2)
+        for algo in (1, 2, 3):
+            bench_hfre(res, B=8, S=896, N=32, algo=algo)     # COCO-like box count (mean 31.5)
     if "gemm" in which:
         bench_gemm(res)
     if "decode" in which:

@@ -16,7 +16,7 @@ def _nerr(got, ref):
     return float((got - ref).abs().max() / ref.abs().max())
 
 
-@pytest.mark.parametrize("algo", [1, 2])
+@pytest.mark.parametrize("algo", [1, 2, 3])
 @pytest.mark.parametrize("tag", ["small", "rect"])
 def test_hfre_matches_reference_goldens(golden_dir, tag, algo):
     import fo1_b200  # noqa: F401
@@ -39,7 +39,7 @@ def test_hfre_matches_reference_goldens(golden_dir, tag, algo):
     np.testing.assert_allclose(out_a.cpu().numpy(), z["out_concat"], rtol=1e-3, atol=2e-4)
 
 
-@pytest.mark.parametrize("algo", [1, 2])
+@pytest.mark.parametrize("algo", [1, 2, 3])
 @pytest.mark.parametrize("S,N", [(448, 37), (896, 100)])
 def test_hfre_matches_oracle_full_shapes(S, N, algo):
     """DaViT-large / SimpleFPN shaped maps at real resolution, batch of 2 images, ragged box counts."""

@@ -25,6 +25,8 @@ constexpr int kRegion = 32;            // sweep: a CTA owns a kRegion x kRegion 
 constexpr int kSweepCh = 256;          // sweep: channels per CTA (4 warps x 32 lanes x 2 channels)
 constexpr int kSlots = 32;             // sweep: boxes accumulated concurrently per pass over the region
 constexpr int kSweepThreads = 128;
+constexpr int kMmaRows = 16;           // tensor sweep: region = kMmaRows x kRegion cells, one 16-box m-tile per pass
+constexpr int kMmaSlots = 16;
 
 struct LevelDev {
   const __nv_bfloat16* data;
@@ -55,6 +57,7 @@ struct ImageDev {
 struct BatchDev {
   ImageDev img[kMaxBatch];
   int n_images;
+  int rrows;     // region height in cells used by the region lists / sweep of this launch (kRegion or kMmaRows)
   int out_dim;
   int roi;
   int pos;
@@ -326,7 +329,7 @@ __global__ void __launch_bounds__(32) hfre_region_lists_kernel(const BatchDev B,
   const int reg = blockIdx.x;
   if (reg >= L.rh * L.rw) return;
   const int ry = reg / L.rw, rx = reg % L.rw;
-  const int row0 = ry * kRegion, row1 = min(row0 + kRegion, L.H) - 1;
+  const int row0 = ry * B.rrows, row1 = min(row0 + B.rrows, L.H) - 1;
   const int col0 = rx * kRegion, col1 = min(col0 + kRegion, L.W) - 1;
   int* out = lists + im.ls_ofs + L.lofs + (long long)reg * im.lstride;
   int count = 0;
@@ -447,6 +450,156 @@ __global__ void __launch_bounds__(kSweepThreads) hfre_sweep_kernel(const BatchDe
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Kernel 3'' (algo 3, map sweep on the tensor pipe).  At C2's box density every cell is covered by ~7 boxes, i.e.
+// ~7.5 FLOP per loaded byte: with the bf16 -> fp32 unpacking the SIMT sweep is issue-bound at ~1/8 of the HBM roofline
+// (profiles/: FMA pipe 26 %, 488 M warp instructions for 1.3 GB).  The reduction is a contraction,
+//     out[box][c] += sum_y a_y[box] * ( sum_x b_x[box] * L[y][x][c] ),
+// so the inner sum over a region row runs as mma.sync m16n8k16 (A = b_x of 16 boxes, B = 16 cells x 8 channels of
+// the bf16 map, fp32 accumulate) and only the per-row scaling by a_y stays on the FMA pipe (1 FMA per 32 MACs).
+// The fp32 weights are fed as hi + lo bf16 halves (two MMAs): the map is bf16 already, so products are exact and
+// the weights keep 16 mantissa bits -- inside the 1e-3 parity budget with three orders of margin.
+// Same work split as the SIMT sweep: CTA = (level, 32 x 32 cell region, 256 channels), warp = 64 channels, a pass
+// accumulates 32 boxes (2 m-tiles); A fragments depend on the boxes only and are built once per pass; B fragments
+// come straight from global memory (16-byte loads of 8 channels of one cell; the two cells an mma B register pairs
+// are transposed out of two loads with one PRMT each).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t prmt_b32(uint32_t a, uint32_t b, uint32_t sel) {
+  uint32_t r;
+  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
+  return r;
+}
+// w0, w1 -> packed bf16 pairs of their high parts and of the remainders
+__device__ __forceinline__ void split_pair(float w0, float w1, uint32_t& hi, uint32_t& lo) {
+  const __nv_bfloat16 h0 = __float2bfloat16_rn(w0), h1 = __float2bfloat16_rn(w1);
+  hi = pack_bf16(__bfloat162float(h0), __bfloat162float(h1));
+  lo = pack_bf16(w0 - __bfloat162float(h0), w1 - __bfloat162float(h1));
+}
+
+__global__ void __launch_bounds__(kSweepThreads, 4) hfre_sweep_mma_kernel(const BatchDev B, const float* __restrict__ ws, const int* __restrict__ lists) {
+  const ImageDev& im = B.img[blockIdx.z];
+  if ((int)blockIdx.x >= im.n_items) return;
+  int lvl = 0, item = blockIdx.x;
+  for (; lvl < im.n_levels; ++lvl) {
+    const int n = im.lv[lvl].rh * im.lv[lvl].rw * ((im.lv[lvl].C + kSweepCh - 1) / kSweepCh);
+    if (item < n) break;
+    item -= n;
+  }
+  const LevelDev& L = im.lv[lvl];
+  const int n_reg = L.rh * L.rw;
+  const int cgroup = item / n_reg, reg = item % n_reg;
+  const int* list = lists + im.ls_ofs + L.lofs + (long long)reg * im.lstride;
+  const int n_list = list[0];
+  if (n_list == 0) return;  // no box touches this region: its cells are never read
+  const int ry = reg / L.rw, rx = reg % L.rw;
+  const int row0 = ry * kMmaRows, col0 = rx * kRegion;
+
+  __shared__ __align__(16) float s_acc[kMmaSlots][kSweepCh];
+  __shared__ __align__(16) float s_wa[kMmaSlots][kMmaRows];
+  __shared__ __align__(16) float s_wb[kMmaSlots][kRegion];
+  __shared__ int s_box[kMmaSlots];
+  __shared__ unsigned s_rows, s_cols;   // region rows / column halves on which some box of the pass has a non-zero weight
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int cbase = cgroup * kSweepCh + warp * 64;        // this warp's 64 channels
+  const bool ch_ok = cbase + g * 8 < L.C;                 // this lane's 8-channel vector exists (C % 8 == 0)
+  const long long rowpitch = (long long)L.W * L.C;
+  const __nv_bfloat16* gbase = L.data + cbase + g * 8;
+
+  for (int base = 0; base < n_list; base += kMmaSlots) {
+    const int ns = min(kMmaSlots, n_list - base);
+    if (threadIdx.x < kMmaSlots) s_box[threadIdx.x] = threadIdx.x < ns ? list[1 + base + threadIdx.x] : -1;
+    if (threadIdx.x == 0) { s_rows = 0u; s_cols = 0u; }
+    __syncthreads();
+    for (int i = threadIdx.x; i < kMmaSlots * (kMmaRows + kRegion); i += kSweepThreads) {
+      const int sl = i / (kMmaRows + kRegion), j = i % (kMmaRows + kRegion);
+      const int axis = j >= kMmaRows, k = axis ? j - kMmaRows : j;
+      float w = 0.0f;
+      if (sl < ns) {
+        const float* rec = ws + im.ws_ofs + L.wofs + (long long)s_box[sl] * L.wstride;
+        const int* hdr = reinterpret_cast<const int*>(rec);
+        const int start = hdr[axis * 2], len = hdr[axis * 2 + 1];
+        const int idx = (axis ? col0 : row0) + k - start;
+        if (idx >= 0 && idx < len) w = rec[4 + (axis ? L.H : 0) + idx];
+      }
+      if (axis) s_wb[sl][k] = w; else s_wa[sl][k] = w;
+      if (w != 0.0f) atomicOr(axis ? &s_cols : &s_rows, axis ? (1u << (k >> 4)) : (1u << k));
+    }
+    __syncthreads();
+
+    // A fragments: rows = boxes (g, g+8), k-slots (2t, 2t+1 | 2t+8, 2t+9) = columns of the half; built once per pass
+    uint32_t ahi[2][4], alo[2][4];
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const float* wb = &s_wb[g + 8 * h][ks * 16 + 2 * t];
+        split_pair(wb[0], wb[1], ahi[ks][h], alo[ks][h]);
+        split_pair(wb[8], wb[9], ahi[ks][2 + h], alo[ks][2 + h]);
+      }
+    float acc[8][4];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e][0] = acc[e][1] = acc[e][2] = acc[e][3] = 0.f;
+
+    unsigned rows_any = s_rows;        // rows beyond the map carry zero weights and are never selected
+    const unsigned cols_any = s_cols;
+    while (rows_any) {
+      const int y = __ffs(rows_any) - 1;
+      rows_any &= rows_any - 1;
+      const __nv_bfloat16* prow = gbase + (long long)(row0 + y) * rowpitch;
+      uint32_t cell[2][4][4];   // [column half][cell 2t, 2t+1, 2t+8, 2t+9][channel pair]
+#pragma unroll
+      for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int x = col0 + ks * 16 + (j >> 1) * 8 + 2 * t + (j & 1);
+          uint4 v = make_uint4(0u, 0u, 0u, 0u);
+          if (((cols_any >> ks) & 1u) && ch_ok && x < L.W) v = __ldg(reinterpret_cast<const uint4*>(prow + (long long)x * L.C));
+          cell[ks][j][0] = v.x; cell[ks][j][1] = v.y; cell[ks][j][2] = v.z; cell[ks][j][3] = v.w;
+        }
+      const float wa0 = s_wa[g][y], wa1 = s_wa[g + 8][y];
+#pragma unroll
+      for (int p4 = 0; p4 < 4; ++p4) {
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int e = p4 * 2 + u;
+          const uint32_t sel = u ? 0x7632u : 0x5410u;
+          float t0[4] = {0.f, 0.f, 0.f, 0.f}, t1[4] = {0.f, 0.f, 0.f, 0.f};   // hi and lo halves accumulate independently
+#pragma unroll
+          for (int ks = 0; ks < 2; ++ks) {
+            if (!((cols_any >> ks) & 1u)) continue;   // warp-uniform
+            const uint32_t b0 = prmt_b32(cell[ks][0][p4], cell[ks][1][p4], sel), b1 = prmt_b32(cell[ks][2][p4], cell[ks][3][p4], sel);
+            mma_bf16_16816(t0, ahi[ks], b0, b1);
+            mma_bf16_16816(t1, alo[ks], b0, b1);
+          }
+          acc[e][0] = fmaf(wa0, t0[0] + t1[0], acc[e][0]); acc[e][1] = fmaf(wa0, t0[1] + t1[1], acc[e][1]);
+          acc[e][2] = fmaf(wa1, t0[2] + t1[2], acc[e][2]); acc[e][3] = fmaf(wa1, t0[3] + t1[3], acc[e][3]);
+        }
+      }
+    }
+    // accumulator column (2t + i) of n-tile e is channel (2t + i) * 8 + e of the warp's 64
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float* r0 = &s_acc[g][warp * 64];
+      float* r1 = &s_acc[g + 8][warp * 64];
+      r0[(2 * t) * 8 + e] = acc[e][0]; r0[(2 * t + 1) * 8 + e] = acc[e][1];
+      r1[(2 * t) * 8 + e] = acc[e][2]; r1[(2 * t + 1) * 8 + e] = acc[e][3];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < ns * kSweepCh; i += kSweepThreads) {
+      const int sl = i / kSweepCh, c = cgroup * kSweepCh + (i % kSweepCh);
+      if (c < L.C) atomicAdd(im.out + (long long)s_box[sl] * B.out_dim + L.out_off + c, s_acc[sl][i % kSweepCh]);
+    }
+    __syncthreads();
+  }
+}
+
 // Kernel 4: optional bf16 copy of the region features (the reference casts to the tower dtype
 // before mm_projector_aux, omchat_qwen2_5_vl.py:106).
 __global__ void __launch_bounds__(256) hfre_to_bf16_kernel(const BatchDev B) {
@@ -469,7 +622,7 @@ static int list_stride(int n_boxes) { return (1 + n_boxes + 3) & ~3; }
 static size_t image_list_ints(const fo1_hfre_image& im) {
   size_t n = 0;
   for (int l = 0; l < im.n_levels; ++l)
-    n += (size_t)ceil_div(im.levels[l].H, kRegion) * ceil_div(im.levels[l].W, kRegion) * list_stride(im.n_boxes);
+    n += (size_t)ceil_div(im.levels[l].H, kMmaRows) * ceil_div(im.levels[l].W, kRegion) * list_stride(im.n_boxes);   // finest region grid of any algo
   return n;
 }
 
@@ -489,7 +642,7 @@ extern "C" int fo1_hfre_forward(const fo1_hfre_image* images, int32_t n_images, 
   if (n_images == 0) return FO1_OK;
   FO1_CHECK_ARG(p->roi_size >= 1 && p->roi_size <= 32, "fo1_hfre_forward: roi_size %d unsupported", p->roi_size);
   FO1_CHECK_ARG(p->out_dim > 0 && p->out_dim % 4 == 0, "fo1_hfre_forward: out_dim %d must be a positive multiple of 4", p->out_dim);
-  FO1_CHECK_ARG(p->algo >= 0 && p->algo <= 2, "fo1_hfre_forward: algo %d not available", p->algo);
+  FO1_CHECK_ARG(p->algo >= 0 && p->algo <= 3, "fo1_hfre_forward: algo %d not available", p->algo);
   const size_t need = fo1_hfre_workspace_bytes(images, n_images, p);
   if (workspace == nullptr || workspace_bytes < need) {
     set_error("fo1_hfre_forward: workspace %zu B < required %zu B", workspace_bytes, need);
@@ -510,7 +663,14 @@ extern "C" int fo1_hfre_forward(const fo1_hfre_image* images, int32_t n_images, 
     B.out_dim = p->out_dim;
     B.roi = p->roi_size;
     B.pos = p->apply_pos_embed ? 1 : 0;
-    int max_boxes = 0, max_levels = 0, max_chunks = 0, max_up = 0, max_hw = 0, max_items = 0, max_regions = 0, total_boxes = 0;
+    int batch_boxes = 0;
+    for (int i = 0; i < B.n_images; ++i) batch_boxes += images[base + i].n_boxes > 0 ? images[base + i].n_boxes : 0;
+    // algo 0: a sweep wins as soon as boxes overlap (its traffic is the union of the windows, the gather's their sum),
+    // and the tensor-pipe sweep beats the SIMT one at every density measured (profiles/r01_microbench_hfre_*.json)
+    const bool sweep = p->algo == 2 || p->algo == 3 || (p->algo == 0 && batch_boxes >= 8 * B.n_images);
+    const bool tensor = p->algo == 3 || (p->algo == 0 && sweep);
+    B.rrows = tensor ? kMmaRows : kRegion;
+    int max_boxes = 0, max_levels = 0, max_chunks = 0, max_up = 0, max_hw = 0, max_items = 0, max_regions = 0;
     for (int i = 0; i < B.n_images; ++i) {
       const fo1_hfre_image& src = images[base + i];
       ImageDev& d = B.img[i];
@@ -530,7 +690,6 @@ extern "C" int fo1_hfre_forward(const fo1_hfre_image* images, int32_t n_images, 
       int wofs = 0, chunks = 0, lofs = 0, items = 0;
       d.ls_ofs = (long long)ls_ofs;
       d.lstride = list_stride(src.n_boxes);
-      total_boxes += src.n_boxes;
       for (int l = 0; l < src.n_levels; ++l) {
         const fo1_hfre_level& sl = src.levels[l];
         FO1_CHECK_ARG(sl.data != nullptr && sl.H > 0 && sl.W > 0 && sl.C > 0, "image %d level %d: bad shape", base + i, l);
@@ -548,7 +707,7 @@ extern "C" int fo1_hfre_forward(const fo1_hfre_image* images, int32_t n_images, 
         dl.wstride = level_wstride(sl);
         wofs += src.n_boxes * dl.wstride;
         chunks += ceil_div(sl.C, kChunk);
-        dl.rh = ceil_div(sl.H, kRegion); dl.rw = ceil_div(sl.W, kRegion);
+        dl.rh = ceil_div(sl.H, B.rrows); dl.rw = ceil_div(sl.W, kRegion);
         dl.lofs = lofs;
         lofs += dl.rh * dl.rw * d.lstride;
         items += dl.rh * dl.rw * ceil_div(sl.C, kSweepCh);
@@ -578,8 +737,6 @@ extern "C" int fo1_hfre_forward(const fo1_hfre_image* images, int32_t n_images, 
       hfre_pos_init_kernel<<<grid, 256, 0, stream>>>(B);
       FO1_LAUNCH_CHECK();
     }
-    // algo 0: the sweep wins as soon as boxes overlap (its traffic is the union of the windows, the gather's their sum)
-    const bool sweep = p->algo == 2 || (p->algo == 0 && total_boxes >= 8 * B.n_images);
     if (sweep) {
       {
         dim3 grid(max_regions, max_levels, B.n_images);
@@ -587,8 +744,9 @@ extern "C" int fo1_hfre_forward(const fo1_hfre_image* images, int32_t n_images, 
         FO1_LAUNCH_CHECK();
       }
       dim3 grid(max_items, 1, B.n_images);
-      ProfScope prof("hfre_sweep", 0.0, 0.0, stream);
-      hfre_sweep_kernel<<<grid, kSweepThreads, 0, stream>>>(B, ws, lists);
+      ProfScope prof(tensor ? "hfre_sweep_mma" : "hfre_sweep", 0.0, 0.0, stream);
+      if (tensor) hfre_sweep_mma_kernel<<<grid, kSweepThreads, 0, stream>>>(B, ws, lists);
+      else hfre_sweep_kernel<<<grid, kSweepThreads, 0, stream>>>(B, ws, lists);
       FO1_LAUNCH_CHECK();
     } else {
       dim3 grid(max_chunks, max_boxes, B.n_images);

@@ -25,7 +25,7 @@ constexpr int kRegion = 32;            // sweep: a CTA owns a kRegion x kRegion 
 constexpr int kSweepCh = 256;          // sweep: channels per CTA (4 warps x 32 lanes x 2 channels)
 constexpr int kSlots = 32;             // sweep: boxes accumulated concurrently per pass over the region
 constexpr int kSweepThreads = 128;
-constexpr int kMmaRows = 16;           // tensor sweep: region = kMmaRows x kRegion cells, one 16-box m-tile per pass
+constexpr int kMmaRows = 8;            // tensor sweep: region = kMmaRows x kRegion cells, one 16-box m-tile per pass
 constexpr int kMmaSlots = 16;
 
 struct LevelDev {
@@ -348,6 +348,54 @@ __global__ void __launch_bounds__(32) hfre_region_lists_kernel(const BatchDev B,
   if (threadIdx.x == 0) out[0] = count;
 }
 
+// Tensor sweep variant of the region lists: besides the ids, every listed box gets its weights over the region's rows
+// and columns as one contiguous 48-word record (word 0 = box id, words 4..4+kMmaRows-1 = a_y, words 12..43 = b_x), so a
+// sweep pass stages its 16 boxes with ONE round of coalesced loads instead of the id -> header -> weights chain.
+constexpr int kRecWords = 48;
+static_assert(kMmaRows <= 8 && kRegion == 32, "record layout: words 4..11 = a_y, words 12..43 = b_x");
+__global__ void __launch_bounds__(128) hfre_region_records_kernel(const BatchDev B, const float* __restrict__ ws, int* __restrict__ lists) {
+  const ImageDev& im = B.img[blockIdx.z];
+  const int lvl = blockIdx.y;
+  if (lvl >= im.n_levels) return;
+  const LevelDev& L = im.lv[lvl];
+  const int reg = blockIdx.x;
+  if (reg >= L.rh * L.rw) return;
+  const int ry = reg / L.rw, rx = reg % L.rw;
+  const int row0 = ry * kMmaRows, row1 = min(row0 + kMmaRows, L.H) - 1;
+  const int col0 = rx * kRegion, col1 = min(col0 + kRegion, L.W) - 1;
+  int* out = lists + im.ls_ofs + L.lofs + (long long)reg * im.lstride;
+  __shared__ int s_count;
+  if (threadIdx.x < 32) {
+    int count = 0;
+    for (int b0 = 0; b0 < im.n_boxes; b0 += 32) {
+      const int b = b0 + threadIdx.x;
+      bool hit = false;
+      if (b < im.n_boxes) {
+        const int* hdr = reinterpret_cast<const int*>(ws + im.ws_ofs + L.wofs + (long long)b * L.wstride);
+        const int r0 = hdr[0], r1 = hdr[0] + hdr[1] - 1, c0 = hdr[2], c1 = hdr[2] + hdr[3] - 1;
+        hit = r0 <= row1 && r1 >= row0 && c0 <= col1 && c1 >= col0;
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, hit);
+      if (hit) out[4 + (count + __popc(m & ((1u << threadIdx.x) - 1u))) * kRecWords] = b;
+      count += __popc(m);
+    }
+    if (threadIdx.x == 0) { out[0] = count; s_count = count; }
+  }
+  __syncthreads();   // block-scope visibility of the ids written above
+  const int count = s_count;
+  float* fout = reinterpret_cast<float*>(out);
+  for (int i = threadIdx.x; i < count * (kMmaRows + kRegion); i += blockDim.x) {
+    const int sl = i / (kMmaRows + kRegion), j = i % (kMmaRows + kRegion);
+    const int axis = j >= kMmaRows, k = axis ? j - kMmaRows : j;
+    const int b = out[4 + sl * kRecWords];
+    const float* rec = ws + im.ws_ofs + L.wofs + (long long)b * L.wstride;
+    const int* hdr = reinterpret_cast<const int*>(rec);
+    const int start = hdr[axis * 2], len = hdr[axis * 2 + 1];
+    const int idx = (axis ? col0 : row0) + k - start;
+    fout[4 + sl * kRecWords + (axis ? 12 + k : 4 + k)] = (idx >= 0 && idx < len) ? rec[4 + (axis ? L.H : 0) + idx] : 0.0f;
+  }
+}
+
 __global__ void __launch_bounds__(kSweepThreads) hfre_sweep_kernel(const BatchDev B, const float* __restrict__ ws, const int* __restrict__ lists) {
   const ImageDev& im = B.img[blockIdx.z];
   if ((int)blockIdx.x >= im.n_items) return;
@@ -481,6 +529,20 @@ __device__ __forceinline__ void split_pair(float w0, float w1, uint32_t& hi, uin
   lo = pack_bf16(w0 - __bfloat162float(h0), w1 - __bfloat162float(h1));
 }
 
+__device__ __forceinline__ void cp_async16_zfill(uint32_t dst_smem, const void* src, bool valid) {
+  const int sz = valid ? 16 : 0;  // src-size 0 -> 16 bytes of zeros
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+constexpr int kMmaStages = 3;                                   // per-warp ring of region rows (cp.async)
+constexpr int kMmaRowBytes = kRegion * 128;                     // 32 cells x 64 channels x 2 B
+constexpr int kMmaRingBytes = (kSweepThreads / 32) * kMmaStages * kMmaRowBytes;
+constexpr int kMmaAccPitch = kSweepCh + 4;                      // floats; the flush staging aliases the ring
+constexpr int kMmaSmemBytes = kMmaRingBytes + kMmaSlots * (kMmaRows + kRegion) * 4 + kMmaSlots * 4 + 16;
+static_assert(kMmaSlots * kMmaAccPitch * 4 <= kMmaRingBytes, "flush staging must fit in the ring it aliases");
+
 __global__ void __launch_bounds__(kSweepThreads, 4) hfre_sweep_mma_kernel(const BatchDev B, const float* __restrict__ ws, const int* __restrict__ lists) {
   const ImageDev& im = B.img[blockIdx.z];
   if ((int)blockIdx.x >= im.n_items) return;
@@ -499,37 +561,38 @@ __global__ void __launch_bounds__(kSweepThreads, 4) hfre_sweep_mma_kernel(const 
   const int ry = reg / L.rw, rx = reg % L.rw;
   const int row0 = ry * kMmaRows, col0 = rx * kRegion;
 
-  __shared__ __align__(16) float s_acc[kMmaSlots][kSweepCh];
-  __shared__ __align__(16) float s_wa[kMmaSlots][kMmaRows];
-  __shared__ __align__(16) float s_wb[kMmaSlots][kRegion];
-  __shared__ int s_box[kMmaSlots];
-  __shared__ unsigned s_rows, s_cols;   // region rows / column halves on which some box of the pass has a non-zero weight
+  extern __shared__ __align__(128) uint8_t s_dyn[];
+  float* s_acc = reinterpret_cast<float*>(s_dyn);                                   // [kMmaSlots][kMmaAccPitch], aliases the ring
+  float (*s_wa)[kMmaRows] = reinterpret_cast<float (*)[kMmaRows]>(s_dyn + kMmaRingBytes);
+  float (*s_wb)[kRegion] = reinterpret_cast<float (*)[kRegion]>(s_dyn + kMmaRingBytes + kMmaSlots * kMmaRows * 4);
+  int* s_box = reinterpret_cast<int*>(s_dyn + kMmaRingBytes + kMmaSlots * (kMmaRows + kRegion) * 4);
+  unsigned* s_mask = reinterpret_cast<unsigned*>(s_box + kMmaSlots);                // [0] rows, [1] column halves
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
   const int cbase = cgroup * kSweepCh + warp * 64;        // this warp's 64 channels
-  const bool ch_ok = cbase + g * 8 < L.C;                 // this lane's 8-channel vector exists (C % 8 == 0)
   const long long rowpitch = (long long)L.W * L.C;
-  const __nv_bfloat16* gbase = L.data + cbase + g * 8;
+  const uint32_t ring = (uint32_t)__cvta_generic_to_shared(s_dyn) + warp * kMmaStages * kMmaRowBytes;
+  // cp.async: instruction i moves 16-byte chunk (cell = 4i + lane/8, channels 8*(lane%8) ..); 16-byte chunks of a cell row
+  // are XOR-swizzled by (cell & 7) so the transposing ldmatrix reads below are bank-conflict-free
+  const int cp_cell = lane >> 3, cp_chunk = lane & 7;
+  const bool cp_ch_ok = cbase + cp_chunk * 8 < L.C;       // C % 8 == 0
+  const __nv_bfloat16* cp_src = L.data + cbase + cp_chunk * 8;
+  // ldmatrix.x4.trans: lane -> row (cell (m&1)*8 + r of the 16-cell k-step) of matrix m = lane/8; matrices 0,1 = n-tile 2p, 2,3 = 2p+1
+  const int lm_cell = ((lane >> 3) & 1) * 8 + (lane & 7), lm_half = lane >> 4;
 
   for (int base = 0; base < n_list; base += kMmaSlots) {
     const int ns = min(kMmaSlots, n_list - base);
-    if (threadIdx.x < kMmaSlots) s_box[threadIdx.x] = threadIdx.x < ns ? list[1 + base + threadIdx.x] : -1;
-    if (threadIdx.x == 0) { s_rows = 0u; s_cols = 0u; }
+    const int* recs = list + 4 + (long long)base * kRecWords;
+    if (threadIdx.x < kMmaSlots) s_box[threadIdx.x] = threadIdx.x < ns ? recs[threadIdx.x * kRecWords] : -1;
+    if (threadIdx.x < 2) s_mask[threadIdx.x] = 0u;
     __syncthreads();
     for (int i = threadIdx.x; i < kMmaSlots * (kMmaRows + kRegion); i += kSweepThreads) {
       const int sl = i / (kMmaRows + kRegion), j = i % (kMmaRows + kRegion);
       const int axis = j >= kMmaRows, k = axis ? j - kMmaRows : j;
-      float w = 0.0f;
-      if (sl < ns) {
-        const float* rec = ws + im.ws_ofs + L.wofs + (long long)s_box[sl] * L.wstride;
-        const int* hdr = reinterpret_cast<const int*>(rec);
-        const int start = hdr[axis * 2], len = hdr[axis * 2 + 1];
-        const int idx = (axis ? col0 : row0) + k - start;
-        if (idx >= 0 && idx < len) w = rec[4 + (axis ? L.H : 0) + idx];
-      }
+      const float w = sl < ns ? __int_as_float(recs[sl * kRecWords + (axis ? 12 + k : 4 + k)]) : 0.0f;
       if (axis) s_wb[sl][k] = w; else s_wa[sl][k] = w;
-      if (w != 0.0f) atomicOr(axis ? &s_cols : &s_rows, axis ? (1u << (k >> 4)) : (1u << k));
+      if (w != 0.0f) atomicOr(&s_mask[axis], axis ? (1u << (k >> 4)) : (1u << k));
     }
     __syncthreads();
 
@@ -547,54 +610,73 @@ __global__ void __launch_bounds__(kSweepThreads, 4) hfre_sweep_mma_kernel(const 
 #pragma unroll
     for (int e = 0; e < 8; ++e) acc[e][0] = acc[e][1] = acc[e][2] = acc[e][3] = 0.f;
 
-    unsigned rows_any = s_rows;        // rows beyond the map carry zero weights and are never selected
-    const unsigned cols_any = s_cols;
-    while (rows_any) {
-      const int y = __ffs(rows_any) - 1;
-      rows_any &= rows_any - 1;
-      const __nv_bfloat16* prow = gbase + (long long)(row0 + y) * rowpitch;
-      uint32_t cell[2][4][4];   // [column half][cell 2t, 2t+1, 2t+8, 2t+9][channel pair]
+    const unsigned rows_any = s_mask[0];      // rows beyond the map carry zero weights and are never selected
+    const unsigned cols_any = s_mask[1];
+    unsigned pending = rows_any, todo = rows_any;
+    int issued = 0, done = 0;
+    auto issue_row = [&]() {                  // next active row -> ring stage issued % kMmaStages (always commits a group)
+      if (pending) {
+        const int y = __ffs(pending) - 1;
+        pending &= pending - 1;
+        const uint32_t stage = ring + (issued % kMmaStages) * kMmaRowBytes;
+        const __nv_bfloat16* prow = cp_src + (long long)(row0 + y) * rowpitch;
 #pragma unroll
-      for (int ks = 0; ks < 2; ++ks)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int x = col0 + ks * 16 + (j >> 1) * 8 + 2 * t + (j & 1);
-          uint4 v = make_uint4(0u, 0u, 0u, 0u);
-          if (((cols_any >> ks) & 1u) && ch_ok && x < L.W) v = __ldg(reinterpret_cast<const uint4*>(prow + (long long)x * L.C));
-          cell[ks][j][0] = v.x; cell[ks][j][1] = v.y; cell[ks][j][2] = v.z; cell[ks][j][3] = v.w;
+        for (int i = 0; i < 8; ++i) {
+          if (!((cols_any >> (i >> 2)) & 1u)) continue;    // column half without weights: neither loaded nor multiplied
+          const int cell = i * 4 + cp_cell, x = col0 + cell;
+          const bool ok = cp_ch_ok && x < L.W;
+          cp_async16_zfill(stage + cell * 128 + ((cp_chunk ^ (cell & 7)) << 4), prow + (long long)(ok ? x : 0) * L.C, ok);
         }
+        ++issued;
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    issue_row();
+    issue_row();
+    while (todo) {
+      const int y = __ffs(todo) - 1;
+      todo &= todo - 1;
+      issue_row();                                            // two rows stay in flight behind the one being reduced
+      asm volatile("cp.async.wait_group 2;" ::: "memory");
+      __syncwarp();
+      const uint32_t stage = ring + (done % kMmaStages) * kMmaRowBytes;
       const float wa0 = s_wa[g][y], wa1 = s_wa[g + 8][y];
 #pragma unroll
-      for (int p4 = 0; p4 < 4; ++p4) {
+      for (int p = 0; p < 4; ++p) {
+        float th[2][4], tl[2][4];
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          const int e = p4 * 2 + u;
-          const uint32_t sel = u ? 0x7632u : 0x5410u;
-          float t0[4] = {0.f, 0.f, 0.f, 0.f}, t1[4] = {0.f, 0.f, 0.f, 0.f};   // hi and lo halves accumulate independently
+        for (int q = 0; q < 2; ++q) { th[q][0] = th[q][1] = th[q][2] = th[q][3] = 0.f; tl[q][0] = tl[q][1] = tl[q][2] = tl[q][3] = 0.f; }
 #pragma unroll
-          for (int ks = 0; ks < 2; ++ks) {
-            if (!((cols_any >> ks) & 1u)) continue;   // warp-uniform
-            const uint32_t b0 = prmt_b32(cell[ks][0][p4], cell[ks][1][p4], sel), b1 = prmt_b32(cell[ks][2][p4], cell[ks][3][p4], sel);
-            mma_bf16_16816(t0, ahi[ks], b0, b1);
-            mma_bf16_16816(t1, alo[ks], b0, b1);
-          }
-          acc[e][0] = fmaf(wa0, t0[0] + t1[0], acc[e][0]); acc[e][1] = fmaf(wa0, t0[1] + t1[1], acc[e][1]);
-          acc[e][2] = fmaf(wa1, t0[2] + t1[2], acc[e][2]); acc[e][3] = fmaf(wa1, t0[3] + t1[3], acc[e][3]);
+        for (int ks = 0; ks < 2; ++ks) {
+          if (!((cols_any >> ks) & 1u)) continue;   // warp-uniform
+          const int cell = ks * 16 + lm_cell;
+          uint32_t bf[4];
+          ldsm_x4_t(bf, stage + cell * 128 + (((2 * p + lm_half) ^ (cell & 7)) << 4));
+          mma_bf16_16816(th[0], ahi[ks], bf[0], bf[1]); mma_bf16_16816(tl[0], alo[ks], bf[0], bf[1]);
+          mma_bf16_16816(th[1], ahi[ks], bf[2], bf[3]); mma_bf16_16816(tl[1], alo[ks], bf[2], bf[3]);
+        }
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          float* a4 = acc[2 * p + q];
+          a4[0] = fmaf(wa0, th[q][0] + tl[q][0], a4[0]); a4[1] = fmaf(wa0, th[q][1] + tl[q][1], a4[1]);
+          a4[2] = fmaf(wa1, th[q][2] + tl[q][2], a4[2]); a4[3] = fmaf(wa1, th[q][3] + tl[q][3], a4[3]);
         }
       }
+      __syncwarp();                                           // the stage may be refilled by the next issue_row()
+      ++done;
     }
-    // accumulator column (2t + i) of n-tile e is channel (2t + i) * 8 + e of the warp's 64
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();                                          // every warp is done with its ring: reuse it as the flush staging
+    // accumulator columns (2t, 2t+1) of n-tile e are channels e*8 + 2t, +1 of the warp's 64
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
-      float* r0 = &s_acc[g][warp * 64];
-      float* r1 = &s_acc[g + 8][warp * 64];
-      r0[(2 * t) * 8 + e] = acc[e][0]; r0[(2 * t + 1) * 8 + e] = acc[e][1];
-      r1[(2 * t) * 8 + e] = acc[e][2]; r1[(2 * t + 1) * 8 + e] = acc[e][3];
+      *reinterpret_cast<float2*>(&s_acc[g * kMmaAccPitch + warp * 64 + e * 8 + 2 * t]) = make_float2(acc[e][0], acc[e][1]);
+      *reinterpret_cast<float2*>(&s_acc[(g + 8) * kMmaAccPitch + warp * 64 + e * 8 + 2 * t]) = make_float2(acc[e][2], acc[e][3]);
     }
     __syncthreads();
     for (int i = threadIdx.x; i < ns * kSweepCh; i += kSweepThreads) {
       const int sl = i / kSweepCh, c = cgroup * kSweepCh + (i % kSweepCh);
-      if (c < L.C) atomicAdd(im.out + (long long)s_box[sl] * B.out_dim + L.out_off + c, s_acc[sl][i % kSweepCh]);
+      if (c < L.C) atomicAdd(im.out + (long long)s_box[sl] * B.out_dim + L.out_off + c, s_acc[sl * kMmaAccPitch + (i % kSweepCh)]);
     }
     __syncthreads();
   }
@@ -618,11 +700,12 @@ static size_t image_ws_floats(const fo1_hfre_image& im) {
   for (int l = 0; l < im.n_levels; ++l) f += (size_t)im.n_boxes * level_wstride(im.levels[l]);
   return f;
 }
-static int list_stride(int n_boxes) { return (1 + n_boxes + 3) & ~3; }
+static int list_stride(int n_boxes) { return (1 + n_boxes + 3) & ~3; }                 // SIMT sweep: count + ids
+static int record_stride(int n_boxes) { return 4 + n_boxes * kRecWords; }             // tensor sweep: count + 48-word records
 static size_t image_list_ints(const fo1_hfre_image& im) {
   size_t n = 0;
   for (int l = 0; l < im.n_levels; ++l)
-    n += (size_t)ceil_div(im.levels[l].H, kMmaRows) * ceil_div(im.levels[l].W, kRegion) * list_stride(im.n_boxes);   // finest region grid of any algo
+    n += (size_t)ceil_div(im.levels[l].H, kMmaRows) * ceil_div(im.levels[l].W, kRegion) * record_stride(im.n_boxes);   // finest region grid / widest list of any algo
   return n;
 }
 
@@ -689,7 +772,7 @@ extern "C" int fo1_hfre_forward(const fo1_hfre_image* images, int32_t n_images, 
       d.ws_ofs = (long long)ws_ofs;
       int wofs = 0, chunks = 0, lofs = 0, items = 0;
       d.ls_ofs = (long long)ls_ofs;
-      d.lstride = list_stride(src.n_boxes);
+      d.lstride = tensor ? record_stride(src.n_boxes) : list_stride(src.n_boxes);
       for (int l = 0; l < src.n_levels; ++l) {
         const fo1_hfre_level& sl = src.levels[l];
         FO1_CHECK_ARG(sl.data != nullptr && sl.H > 0 && sl.W > 0 && sl.C > 0, "image %d level %d: bad shape", base + i, l);
@@ -740,12 +823,20 @@ extern "C" int fo1_hfre_forward(const fo1_hfre_image* images, int32_t n_images, 
     if (sweep) {
       {
         dim3 grid(max_regions, max_levels, B.n_images);
-        hfre_region_lists_kernel<<<grid, 32, 0, stream>>>(B, ws, lists);
+        if (tensor) hfre_region_records_kernel<<<grid, 128, 0, stream>>>(B, ws, lists);
+        else hfre_region_lists_kernel<<<grid, 32, 0, stream>>>(B, ws, lists);
         FO1_LAUNCH_CHECK();
       }
       dim3 grid(max_items, 1, B.n_images);
       ProfScope prof(tensor ? "hfre_sweep_mma" : "hfre_sweep", 0.0, 0.0, stream);
-      if (tensor) hfre_sweep_mma_kernel<<<grid, kSweepThreads, 0, stream>>>(B, ws, lists);
+      if (tensor) {
+        static bool attr_set = false;
+        if (!attr_set) {
+          FO1_CUDA(cudaFuncSetAttribute(hfre_sweep_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMmaSmemBytes));
+          attr_set = true;
+        }
+        hfre_sweep_mma_kernel<<<grid, kSweepThreads, kMmaSmemBytes, stream>>>(B, ws, lists);
+      }
       else hfre_sweep_kernel<<<grid, kSweepThreads, 0, stream>>>(B, ws, lists);
       FO1_LAUNCH_CHECK();
     } else {

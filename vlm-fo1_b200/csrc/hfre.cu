@@ -643,23 +643,23 @@ __global__ void __launch_bounds__(kSweepThreads, 4) hfre_sweep_mma_kernel(const 
       const float wa0 = s_wa[g][y], wa1 = s_wa[g + 8][y];
 #pragma unroll
       for (int p = 0; p < 4; ++p) {
-        float th[2][4], tl[2][4];
+        float tq[2][4];   // row sums of the pair's two n-tiles; the hi and lo weight halves accumulate into the same registers
 #pragma unroll
-        for (int q = 0; q < 2; ++q) { th[q][0] = th[q][1] = th[q][2] = th[q][3] = 0.f; tl[q][0] = tl[q][1] = tl[q][2] = tl[q][3] = 0.f; }
+        for (int q = 0; q < 2; ++q) { tq[q][0] = tq[q][1] = tq[q][2] = tq[q][3] = 0.f; }
 #pragma unroll
         for (int ks = 0; ks < 2; ++ks) {
           if (!((cols_any >> ks) & 1u)) continue;   // warp-uniform
           const int cell = ks * 16 + lm_cell;
           uint32_t bf[4];
           ldsm_x4_t(bf, stage + cell * 128 + (((2 * p + lm_half) ^ (cell & 7)) << 4));
-          mma_bf16_16816(th[0], ahi[ks], bf[0], bf[1]); mma_bf16_16816(tl[0], alo[ks], bf[0], bf[1]);
-          mma_bf16_16816(th[1], ahi[ks], bf[2], bf[3]); mma_bf16_16816(tl[1], alo[ks], bf[2], bf[3]);
+          mma_bf16_16816(tq[0], ahi[ks], bf[0], bf[1]); mma_bf16_16816(tq[1], ahi[ks], bf[2], bf[3]);
+          mma_bf16_16816(tq[0], alo[ks], bf[0], bf[1]); mma_bf16_16816(tq[1], alo[ks], bf[2], bf[3]);
         }
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
           float* a4 = acc[2 * p + q];
-          a4[0] = fmaf(wa0, th[q][0] + tl[q][0], a4[0]); a4[1] = fmaf(wa0, th[q][1] + tl[q][1], a4[1]);
-          a4[2] = fmaf(wa1, th[q][2] + tl[q][2], a4[2]); a4[3] = fmaf(wa1, th[q][3] + tl[q][3], a4[3]);
+          a4[0] = fmaf(wa0, tq[q][0], a4[0]); a4[1] = fmaf(wa0, tq[q][1], a4[1]);
+          a4[2] = fmaf(wa1, tq[q][2], a4[2]); a4[3] = fmaf(wa1, tq[q][3], a4[3]);
         }
       }
       __syncwarp();                                           // the stage may be refilled by the next issue_row()

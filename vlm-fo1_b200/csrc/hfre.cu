@@ -577,7 +577,15 @@ __global__ void __launch_bounds__(kSweepThreads, 4) hfre_sweep_mma_kernel(const 
   // are XOR-swizzled by (cell & 7) so the transposing ldmatrix reads below are bank-conflict-free
   const int cp_cell = lane >> 3, cp_chunk = lane & 7;
   const bool cp_ch_ok = cbase + cp_chunk * 8 < L.C;       // C % 8 == 0
-  const __nv_bfloat16* cp_src = L.data + cbase + cp_chunk * 8;
+  // everything about the 8 copies of a row that does not depend on the row is computed once: source column pointer
+  // (cell i*4 + cp_cell is i * 4C elements further), validity bits, the two swizzled destinations (even / odd i)
+  const __nv_bfloat16* cp_src = L.data + (cp_ch_ok ? cbase + cp_chunk * 8 : 0) + (long long)min(col0 + cp_cell, L.W - 1) * L.C;
+  const long long cp_step = 4LL * L.C;
+  unsigned cp_ok = 0u;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) cp_ok |= (cp_ch_ok && col0 + i * 4 + cp_cell < L.W) ? (1u << i) : 0u;
+  const uint32_t cp_dst_even = ring + cp_cell * 128 + ((cp_chunk ^ cp_cell) << 4);
+  const uint32_t cp_dst_odd = ring + (cp_cell + 4) * 128 + ((cp_chunk ^ (cp_cell + 4)) << 4);
   // ldmatrix.x4.trans: lane -> row (cell (m&1)*8 + r of the 16-cell k-step) of matrix m = lane/8; matrices 0,1 = n-tile 2p, 2,3 = 2p+1
   const int lm_cell = ((lane >> 3) & 1) * 8 + (lane & 7), lm_half = lane >> 4;
 
@@ -613,21 +621,19 @@ __global__ void __launch_bounds__(kSweepThreads, 4) hfre_sweep_mma_kernel(const 
     const unsigned rows_any = s_mask[0];      // rows beyond the map carry zero weights and are never selected
     const unsigned cols_any = s_mask[1];
     unsigned pending = rows_any, todo = rows_any;
-    int issued = 0, done = 0;
-    auto issue_row = [&]() {                  // next active row -> ring stage issued % kMmaStages (always commits a group)
+    uint32_t st_issue = 0, st_done = 0;       // ring stage offsets (bytes) of the next row to fetch / to reduce
+    auto issue_row = [&]() {                  // next active row -> next ring stage (always commits a group)
       if (pending) {
         const int y = __ffs(pending) - 1;
         pending &= pending - 1;
-        const uint32_t stage = ring + (issued % kMmaStages) * kMmaRowBytes;
         const __nv_bfloat16* prow = cp_src + (long long)(row0 + y) * rowpitch;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           if (!((cols_any >> (i >> 2)) & 1u)) continue;    // column half without weights: neither loaded nor multiplied
-          const int cell = i * 4 + cp_cell, x = col0 + cell;
-          const bool ok = cp_ch_ok && x < L.W;
-          cp_async16_zfill(stage + cell * 128 + ((cp_chunk ^ (cell & 7)) << 4), prow + (long long)(ok ? x : 0) * L.C, ok);
+          const bool ok = (cp_ok >> i) & 1u;               // off-map cells / channels: zero-filled, source pointer stays in range
+          cp_async16_zfill(((i & 1) ? cp_dst_odd + (i - 1) * 512 : cp_dst_even + i * 512) + st_issue, ok ? prow + i * cp_step : prow, ok);
         }
-        ++issued;
+        st_issue = (st_issue == (kMmaStages - 1) * kMmaRowBytes) ? 0u : st_issue + kMmaRowBytes;
       }
       asm volatile("cp.async.commit_group;" ::: "memory");
     };
@@ -639,7 +645,7 @@ __global__ void __launch_bounds__(kSweepThreads, 4) hfre_sweep_mma_kernel(const 
       issue_row();                                            // two rows stay in flight behind the one being reduced
       asm volatile("cp.async.wait_group 2;" ::: "memory");
       __syncwarp();
-      const uint32_t stage = ring + (done % kMmaStages) * kMmaRowBytes;
+      const uint32_t stage = ring + st_done;
       const float wa0 = s_wa[g][y], wa1 = s_wa[g + 8][y];
 #pragma unroll
       for (int p = 0; p < 4; ++p) {
@@ -663,7 +669,7 @@ __global__ void __launch_bounds__(kSweepThreads, 4) hfre_sweep_mma_kernel(const 
         }
       }
       __syncwarp();                                           // the stage may be refilled by the next issue_row()
-      ++done;
+      st_done = (st_done == (kMmaStages - 1) * kMmaRowBytes) ? 0u : st_done + kMmaRowBytes;
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
     __syncthreads();                                          // every warp is done with its ring: reuse it as the flush staging

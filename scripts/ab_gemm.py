@@ -16,14 +16,14 @@ class GemmDesc(C.Structure):
                 ("residual", C.c_void_p), ("ldr", C.c_int64), ("gated", C.c_int32), ("tile_n", C.c_int32), ("split_k", C.c_int32)]
 
 
-SHAPES = [(100352, 4096, 1024, 1, 0), (100352, 4096, 1024, 0, 0), (401408, 2048, 512, 1, 0), (1605632, 1024, 256, 1, 0),
-          (131072, 3840, 1280, 0, 0), (131072, 1280, 1280, 0, 0), (131072, 6848, 1280, 2, 1), (38240, 22016, 2048, 2, 1)]
+SHAPES = [(100352, 4096, 1024, 1, 0, 0), (131072, 3840, 1280, 0, 0, 0), (131072, 1280, 1280, 0, 0, 1), (38240, 2048, 2048, 0, 0, 1),
+          (38240, 2048, 11008, 0, 0, 1), (131072, 1280, 3424, 0, 0, 1), (131072, 6848, 1280, 2, 1, 0), (100352, 1024, 4096, 0, 0, 1)]
 
 
 def main():
     libs = [(p, C.CDLL(p)) for p in sys.argv[1:]]
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-    for M, N, K, act, gated in SHAPES:
+    for M, N, K, act, gated, resid in SHAPES:
         a = (torch.randn(M, K, device="cuda") * 0.5).to(torch.bfloat16)
         w = (torch.randn(N, K, device="cuda") * 0.05).to(torch.bfloat16)
         bias = torch.randn(N, device="cuda").to(torch.bfloat16)
@@ -32,7 +32,10 @@ def main():
         d.M, d.N, d.K = M, N, K
         d.A, d.lda, d.W, d.ldw, d.D, d.ldd, d.d_dtype = a.data_ptr(), K, w.data_ptr(), K, out.data_ptr(), out.shape[1], 0
         d.bias, d.bias_dtype, d.act, d.gated = bias.data_ptr(), 0, act, gated
-        row = {"M": M, "N": N, "K": K, "act": act, "gated": gated}
+        if resid:
+            res = torch.randn_like(out)
+            d.residual, d.ldr = res.data_ptr(), out.shape[1]
+        row = {"M": M, "N": N, "K": K, "act": act, "gated": gated, "resid": resid}
         for path, lib in libs:
             lib.fo1_gemm_bf16.restype = C.c_int
             st = C.c_void_p(torch.cuda.current_stream().cuda_stream)

@@ -49,8 +49,10 @@ __device__ __forceinline__ void load_tile_async(bf16* dst, const bf16* src, long
   }
 }
 
+// two resident CTAs per SM when the accumulators leave room (head_dim <= 80): with one 8-warp CTA the tensor pipe sat at
+// 38 % with the warps waiting on fixed-latency dependencies (ncu, profiles/)
 template <int HD, bool CAUSAL, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32) attn_varlen_kernel(const AttnArgs a) {
+__global__ void __launch_bounds__(WARPS * 32, (HD <= 80 ? 2 : 1)) attn_varlen_kernel(const AttnArgs a) {
   constexpr int PITCH = HD + 8;
   constexpr int TILE = 64 * PITCH;
   constexpr int kTileM = 16 * WARPS, kAttnThreads = WARPS * 32;

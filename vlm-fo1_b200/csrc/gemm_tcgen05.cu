@@ -251,6 +251,33 @@ __device__ __forceinline__ void flush_rows(const GemmArgs& g, const uint8_t* stg
   const int rows_per_it = 32 / segs;
   const int seg = lane % segs, r0 = lane / segs;
   const int col = col0 + seg * epp;
+  if (bf16_out && g.residual != nullptr && col + 8 <= n_limit) {
+    // residual fast path: all residual rows of the block are requested first (up to 8 independent 16-byte loads in
+    // flight per lane), then added and stored -- a load -> add -> store chain per row left the K <= 2048 GEMMs with a
+    // residual at 720-950 TFLOP/s
+    uint4 rr[8];
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int m = m_base + it * rows_per_it + r0;
+      rr[it] = make_uint4(0u, 0u, 0u, 0u);
+      if (it < segs && m < g.M) rr[it] = __ldg(reinterpret_cast<const uint4*>(g.residual + (long long)m * g.ldr + col));
+    }
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int row = it * rows_per_it + r0;
+      const int m = m_base + row;
+      if (it >= segs || m >= g.M) continue;
+      uint4 v = stage_get16(stg, row, seg);
+      const uint4 r = rr[it];
+      v.x = pack_bf16(bf16_lo(v.x) + bf16_lo(r.x), bf16_hi(v.x) + bf16_hi(r.x));
+      v.y = pack_bf16(bf16_lo(v.y) + bf16_lo(r.y), bf16_hi(v.y) + bf16_hi(r.y));
+      v.z = pack_bf16(bf16_lo(v.z) + bf16_lo(r.z), bf16_hi(v.z) + bf16_hi(r.z));
+      v.w = pack_bf16(bf16_lo(v.w) + bf16_lo(r.w), bf16_hi(v.w) + bf16_hi(r.w));
+      *reinterpret_cast<uint4*>(static_cast<__nv_bfloat16*>(g.D) + (long long)m * g.ldd + col) = v;
+    }
+    __syncwarp();
+    return;
+  }
   for (int it = 0; it < segs; ++it) {               // segs iterations x rows_per_it rows = 32 rows
     const int row = it * rows_per_it + r0;
     const int m = m_base + row;

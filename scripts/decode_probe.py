@@ -32,7 +32,18 @@ def run(tokens):
     return e0.elapsed_time(e1)
 
 
-if os.environ.get("PROBE_NCU"):
+if os.environ.get("PROBE_PROF"):   # CUDA-event time of every tagged kernel of a short run (events break PDL / the graph)
+    import ctypes as C
+    L = import_module("vlm-fo1_b200._lib").lib()
+    run(4)
+    L.fo1_profile_enable(1)
+    run(T)
+    buf = C.create_string_buffer(1 << 20)
+    L.fo1_profile_collect(buf, 1 << 20)
+    L.fo1_profile_enable(0)
+    prof = json.loads(buf.value.decode())
+    print(json.dumps({k: {"launches": v["launches"], "avg_us": round(1e3 * v["ms"] / v["launches"], 2)} for k, v in prof.items() if "skinny" in k or "decode" in k}))
+elif os.environ.get("PROBE_NCU"):
     run(T)
 else:
     run(4); run(4)

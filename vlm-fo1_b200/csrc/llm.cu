@@ -59,7 +59,7 @@ __global__ void __launch_bounds__(128) kv_store_kernel(const bf16* __restrict__ 
 // transposed out of two row loads with one PRMT each; the output dims come out permuted and are un-permuted on the
 // smem write.  The block merges its warps' (m, l, acc) and writes one un-normalised partial per (head, split);
 // decode_attn_combine_kernel merges the splits.
-constexpr int kDecSplits = 8;
+constexpr int kDecSplits = 8;   // most key splits per (sequence, kv head); the launch uses gridDim.z <= kDecSplits of them
 constexpr int kDecWarps = 4;
 __device__ __forceinline__ void mma_m16n8k16(float (&c)[4], uint32_t a0, uint32_t a2, uint32_t b0, uint32_t b1) {
   // rows 8..15 of A (a1, a3) are zero: only the G query heads in rows 0..7 carry data
@@ -87,7 +87,8 @@ __global__ void __launch_bounds__(kDecWarps * 32) decode_attn_kernel(const bf16*
   griddep_launch();
   griddep_wait();
   const int n = cache_len[b] + 1;  // the step's own K/V was appended at index cache_len[b]
-  const int chunk = ((n + kDecSplits - 1) / kDecSplits + 15) & ~15;
+  const int n_splits = gridDim.z;
+  const int chunk = ((n + n_splits - 1) / n_splits + 15) & ~15;
   const int t_begin = sp * chunk, t_end = min(n, t_begin + chunk);
   const int kv_dim = kv_heads * HD;
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -193,7 +194,7 @@ __global__ void __launch_bounds__(kDecWarps * 32) decode_attn_kernel(const bf16*
 
 // merge the kDecSplits partials of one (sequence, q head): out = sum_s acc_s * 2^(m_s - m) / sum_s l_s * 2^(m_s - m)
 __global__ void __launch_bounds__(128) decode_attn_combine_kernel(const float* __restrict__ part, bf16* __restrict__ out, long long ldo,
-                                                                  int q_heads) {
+                                                                  int q_heads, int n_splits) {
   constexpr int HD = 128;
   const int b = blockIdx.x, h = blockIdx.y, d = threadIdx.x;
   griddep_launch();
@@ -201,10 +202,10 @@ __global__ void __launch_bounds__(128) decode_attn_combine_kernel(const float* _
   const float* rec = part + (((long long)b * q_heads + h) * kDecSplits) * (HD + 4);
   float mm = -INFINITY;
 #pragma unroll
-  for (int s = 0; s < kDecSplits; ++s) mm = fmaxf(mm, rec[s * (HD + 4)]);
+  for (int s = 0; s < n_splits; ++s) mm = fmaxf(mm, rec[s * (HD + 4)]);
   float num = 0.f, den = 0.f;
 #pragma unroll
-  for (int s = 0; s < kDecSplits; ++s) {
+  for (int s = 0; s < n_splits; ++s) {
     const float ms = rec[s * (HD + 4)];
     const float sc = (ms == -INFINITY) ? 0.f : exp2f(ms - mm);
     num += rec[s * (HD + 4) + 4 + d] * sc;
@@ -413,14 +414,17 @@ static int llm_layer(Model* m, int li, const bf16* x_in, bf16* x_out, const Laye
     FO1_RUN(attention_varlen(a, s));
   } else if (!dry) {
     FO1_RUN(rope_kv_append(B_.qkv, ldq, cs, rows, c.llm_heads, c.llm_kv_heads, hd, st->cache_len, kc, vc, m->kv_cap, s));
-    dim3 grid(rows, c.llm_kv_heads, kDecSplits);
+    // one wave: 3 blocks of this kernel are resident per SM (154 registers); a 512-block grid on 444 slots ran two
+    const int slots = 3 * device_sm_count();
+    const int n_splits = std::max(1, std::min(kDecSplits, slots / std::max(1, rows * c.llm_kv_heads)));
+    dim3 grid(rows, c.llm_kv_heads, n_splits);
     ProfScope prof("decode_attn", 0.0, 0.0, s);
     const int G = c.llm_heads / c.llm_kv_heads;
     const float scale = 1.0f / sqrtf((float)hd);
     if (G > 8 || hd != 128) { set_error("decode attention: GQA group %d / head_dim %d unsupported (group <= 8, head_dim 128)", G, hd); return FO1_ERR_UNSUPPORTED; }
     launch_k(decode_attn_kernel, grid, dim3(kDecWarps * 32), 0, s, B_.qkv, (long long)ldq, kc, vc, st->cache_len, m->kv_cap, c.llm_kv_heads, G, B_.dec_part, scale);
     FO1_LAUNCH_CHECK();
-    launch_k(decode_attn_combine_kernel, dim3(rows, c.llm_heads), dim3(128), 0, s, B_.dec_part, B_.att, (long long)QD, c.llm_heads);
+    launch_k(decode_attn_combine_kernel, dim3(rows, c.llm_heads), dim3(128), 0, s, B_.dec_part, B_.att, (long long)QD, c.llm_heads, n_splits);
     FO1_LAUNCH_CHECK();
   }
   FO1_RUN(linear(B_.att, QD, L.o_w, QD, B_.x_mid, H, FO1_BF16, rows, H, QD, nullptr, 0, FO1_EPI_NONE, x_in, H, 0, s));

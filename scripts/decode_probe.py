@@ -34,13 +34,13 @@ def run(tokens):
 
 if os.environ.get("PROBE_PROF"):   # CUDA-event time of every tagged kernel of a short run (events break PDL / the graph)
     import ctypes as C
-    L = import_module("vlm-fo1_b200._lib").lib()
+    lib_ = import_module("vlm-fo1_b200._lib").lib()
     run(4)
-    L.fo1_profile_enable(1)
+    lib_.fo1_profile_enable(1)
     run(T)
     buf = C.create_string_buffer(1 << 20)
-    L.fo1_profile_collect(buf, 1 << 20)
-    L.fo1_profile_enable(0)
+    lib_.fo1_profile_collect(buf, 1 << 20)
+    lib_.fo1_profile_enable(0)
     prof = json.loads(buf.value.decode())
     print(json.dumps({k: {"launches": v["launches"], "avg_us": round(1e3 * v["ms"] / v["launches"], 2)} for k, v in prof.items() if "skinny" in k or "decode" in k}))
 elif os.environ.get("PROBE_NCU"):

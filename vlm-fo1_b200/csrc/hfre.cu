@@ -595,12 +595,25 @@ __global__ void __launch_bounds__(kSweepThreads, 4) hfre_sweep_mma_kernel(const 
     if (threadIdx.x < kMmaSlots) s_box[threadIdx.x] = threadIdx.x < ns ? recs[threadIdx.x * kRecWords] : -1;
     if (threadIdx.x < 2) s_mask[threadIdx.x] = 0u;
     __syncthreads();
-    for (int i = threadIdx.x; i < kMmaSlots * (kMmaRows + kRegion); i += kSweepThreads) {
-      const int sl = i / (kMmaRows + kRegion), j = i % (kMmaRows + kRegion);
-      const int axis = j >= kMmaRows, k = axis ? j - kMmaRows : j;
-      const float w = sl < ns ? __int_as_float(recs[sl * kRecWords + (axis ? 12 + k : 4 + k)]) : 0.0f;
-      if (axis) s_wb[sl][k] = w; else s_wa[sl][k] = w;
-      if (w != 0.0f) atomicOr(&s_mask[axis], axis ? (1u << (k >> 4)) : (1u << k));
+    {
+      // 8 threads per slot: words 4..11 of the record are a_y, 12..43 are b_x (five strided words per thread)
+      static_assert(kSweepThreads == kMmaSlots * 8 && kMmaRows == 8, "staging layout");
+      const int sl = threadIdx.x >> 3, q = threadIdx.x & 7;
+      const int* rec = recs + sl * kRecWords + 4 + q;
+      unsigned rbits = 0u, cbits = 0u;
+      float w[5];
+#pragma unroll
+      for (int r = 0; r < 5; ++r) w[r] = sl < ns ? __int_as_float(rec[8 * r]) : 0.0f;
+      s_wa[sl][q] = w[0];
+      if (w[0] != 0.0f) rbits = 1u << q;
+#pragma unroll
+      for (int r = 1; r < 5; ++r) {
+        s_wb[sl][q + 8 * (r - 1)] = w[r];
+        if (w[r] != 0.0f) cbits |= 1u << ((r - 1) >> 1);
+      }
+      rbits = __reduce_or_sync(0xffffffffu, rbits);
+      cbits = __reduce_or_sync(0xffffffffu, cbits);
+      if (lane == 0) { atomicOr(&s_mask[0], rbits); atomicOr(&s_mask[1], cbits); }
     }
     __syncthreads();
 
@@ -680,9 +693,15 @@ __global__ void __launch_bounds__(kSweepThreads, 4) hfre_sweep_mma_kernel(const 
       *reinterpret_cast<float2*>(&s_acc[(g + 8) * kMmaAccPitch + warp * 64 + e * 8 + 2 * t]) = make_float2(acc[e][2], acc[e][3]);
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < ns * kSweepCh; i += kSweepThreads) {
-      const int sl = i / kSweepCh, c = cgroup * kSweepCh + (i % kSweepCh);
-      if (c < L.C) atomicAdd(im.out + (long long)s_box[sl] * B.out_dim + L.out_off + c, s_acc[sl * kMmaAccPitch + (i % kSweepCh)]);
+    {
+      // thread -> channels (tid, tid + 128) of every box of the pass: one row pointer per box, two coalesced reductions
+      const int c0 = cgroup * kSweepCh + threadIdx.x;
+      float* obase = im.out + L.out_off + c0;
+      for (int sl = 0; sl < ns; ++sl) {
+        float* orow = obase + (long long)s_box[sl] * B.out_dim;
+        if (c0 < L.C) atomicAdd(orow, s_acc[sl * kMmaAccPitch + threadIdx.x]);
+        if (c0 + kSweepThreads < L.C) atomicAdd(orow + kSweepThreads, s_acc[sl * kMmaAccPitch + threadIdx.x + kSweepThreads]);
+      }
     }
     __syncthreads();
   }

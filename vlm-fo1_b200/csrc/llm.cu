@@ -53,36 +53,43 @@ __global__ void __launch_bounds__(128) kv_store_kernel(const bf16* __restrict__ 
 // Single-query GQA attention over the cache, split over the sequence (flash-decoding) and run on the tensor pipe:
 // one block per (sequence, kv head, split).  The G <= 8 query heads of the kv head are the rows of an m16n8k16 tile
 // (rows G..15 are zero), so K and V are read ONCE per kv head instead of once per query head.  Every warp owns
-// 16-key tiles of the split and loads its operands straight from global memory into mma fragments with 16-byte loads:
-// the contraction index of an mma is a free permutation, so lane (g, t) feeds dims [c*32 + t*8, +8) of key g as the
-// k-slots of two consecutive k-steps (Q uses the same permutation), and for P.V the two keys a B register pairs up are
-// transposed out of two row loads with one PRMT each; the output dims come out permuted and are un-permuted on the
-// smem write.  The block merges its warps' (m, l, acc) and writes one un-normalised partial per (head, split);
+// 16-key tiles of the split and streams them through a private cp.async ring (3 tiles = 24 KB, two in flight behind
+// the one being reduced; 16-byte chunks XOR-swizzled by key) -- the load -> use chain of a register-fed version left
+// a warp with one tile in flight and the kernel at 1.3 TB/s.  S = Q.K^T takes its B fragments with ldmatrix, P.V with
+// ldmatrix.trans; the block merges its warps' (m, l, acc) and writes one un-normalised partial per (head, split);
 // decode_attn_combine_kernel merges the splits.
 constexpr int kDecSplits = 8;   // most key splits per (sequence, kv head); the launch uses gridDim.z <= kDecSplits of them
 constexpr int kDecWarps = 4;
+constexpr int kDecStages = 3;
+constexpr int kDecTileBytes = 16 * 256 * 2;                      // 16 keys x (K row 256 B + V row 256 B)
+constexpr int kDecRingBytes = kDecWarps * kDecStages * kDecTileBytes;
+constexpr int kDecSmemBytes = kDecRingBytes;                     // the warp merge staging aliases the ring
 __device__ __forceinline__ void mma_m16n8k16(float (&c)[4], uint32_t a0, uint32_t a2, uint32_t b0, uint32_t b1) {
   // rows 8..15 of A (a1, a3) are zero: only the G query heads in rows 0..7 carry data
   asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%5}, {%7,%8}, {%0,%1,%2,%3};"
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                : "r"(a0), "r"(0u), "r"(a2), "r"(b0), "r"(b1));
 }
-__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {
-  uint32_t r;
-  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
-  return r;
-}
 __device__ __forceinline__ uint32_t pack2_bf16(float lo, float hi) {
   uint32_t r;
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
   return r;
 }
+__device__ __forceinline__ void dec_cp16(uint32_t dst, const void* src, bool valid) {
+  const int sz = valid ? 16 : 0;  // src-size 0 -> 16 bytes of zeros
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void dec_ldsm(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void dec_ldsm_t(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
 __global__ void __launch_bounds__(kDecWarps * 32) decode_attn_kernel(const bf16* __restrict__ q, long long ldq, const bf16* __restrict__ kc,
                                                                      const bf16* __restrict__ vc, const int* __restrict__ cache_len, int cap,
                                                                      int kv_heads, int G, float* __restrict__ part, float scale) {
   constexpr int HD = 128;
-  __shared__ float sm_o[kDecWarps][8][HD];
-  __shared__ float sm_m[kDecWarps][8], sm_l[kDecWarps][8];
+  extern __shared__ __align__(128) uint8_t dec_smem[];
   const int b = blockIdx.x, kvh = blockIdx.y, sp = blockIdx.z;
   griddep_launch();
   griddep_wait();
@@ -93,43 +100,65 @@ __global__ void __launch_bounds__(kDecWarps * 32) decode_attn_kernel(const bf16*
   const int kv_dim = kv_heads * HD;
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int g = lane >> 2, t = lane & 3;
-  uint4 qa[4];
+  // Q fragments (A operand, rows = heads): a0 = dims (16 ks + 2t, +1), a2 = dims (16 ks + 8 + 2t, +1) of head g
+  uint32_t qa[8][2];
 #pragma unroll
-  for (int c = 0; c < 4; ++c) qa[c] = make_uint4(0u, 0u, 0u, 0u);
+  for (int ks = 0; ks < 8; ++ks) { qa[ks][0] = 0u; qa[ks][1] = 0u; }
   if (g < G) {
-    const bf16* qp = q + (long long)b * ldq + (long long)(kvh * G + g) * HD + t * 8;
+    const bf16* qp = q + (long long)b * ldq + (long long)(kvh * G + g) * HD + 2 * t;
 #pragma unroll
-    for (int c = 0; c < 4; ++c) qa[c] = *reinterpret_cast<const uint4*>(qp + c * 32);
+    for (int ks = 0; ks < 8; ++ks) {
+      qa[ks][0] = *reinterpret_cast<const uint32_t*>(qp + ks * 16);
+      qa[ks][1] = *reinterpret_cast<const uint32_t*>(qp + ks * 16 + 8);
+    }
   }
   const float sc = scale * 1.4426950408889634f;
   float m = -INFINITY, l = 0.f, o[16][4];
 #pragma unroll
   for (int j = 0; j < 16; ++j) { o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f; }
-  const bf16* kb = kc + (long long)b * cap * kv_dim + kvh * HD + t * 8;
-  const bf16* vb = vc + (long long)b * cap * kv_dim + kvh * HD + g * 8;
+
+  const uint32_t ring = (uint32_t)__cvta_generic_to_shared(dec_smem) + w * kDecStages * kDecTileBytes;
+  // copy plan: instruction i moves chunk (key = 2i + lane/16, 16-byte chunk lane%16) of the K half and of the V half
+  const int cp_key = lane >> 4, cp_chunk = lane & 15;
+  const bf16* kbase = kc + (long long)b * cap * kv_dim + kvh * HD + cp_chunk * 8;
+  const bf16* vbase = vc + (long long)b * cap * kv_dim + kvh * HD + cp_chunk * 8;
+  int t_issue = t_begin + w * 16;
+  uint32_t st_issue = 0, st_done = 0;
+  auto issue_tile = [&]() {
+    if (t_issue < t_end) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int key = 2 * i + cp_key, tok = t_issue + key;
+        const bool ok = tok < t_end;                          // keys beyond the split: zero rows (their scores are masked)
+        const long long off = (long long)(ok ? tok : t_begin) * kv_dim;
+        const uint32_t dst = ring + st_issue + key * 256 + ((cp_chunk ^ (key & 7)) << 4);
+        dec_cp16(dst, kbase + off, ok);
+        dec_cp16(dst + 16 * 256, vbase + off, ok);
+      }
+      t_issue += kDecWarps * 16;
+      st_issue = (st_issue == (kDecStages - 1) * kDecTileBytes) ? 0u : st_issue + kDecTileBytes;
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  issue_tile();
+  issue_tile();
+  // ldmatrix lane roles: S: matrix m = lane/8 -> (keys (m/2)*8 + r, chunk 2 ks + (m&1)); PV (trans): (keys (m&1)*8 + r, chunk c + m/2)
+  const int lr = lane & 7, lm = lane >> 3;
   for (int t0 = t_begin + w * 16; t0 < t_end; t0 += kDecWarps * 16) {
-    uint4 kq[2][4], vq[4][2];
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const bf16* kp = kb + (long long)min(t0 + i * 8 + g, t_end - 1) * kv_dim;   // clamped rows are masked below
-#pragma unroll
-      for (int c = 0; c < 4; ++c) kq[i][c] = *reinterpret_cast<const uint4*>(kp + c * 32);
-    }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const bf16* vp = vb + (long long)min(t0 + (j >> 1) * 8 + 2 * t + (j & 1), t_end - 1) * kv_dim;  // finite data, weight 0
-      vq[j][0] = *reinterpret_cast<const uint4*>(vp);
-      vq[j][1] = *reinterpret_cast<const uint4*>(vp + 64);
-    }
+    issue_tile();
+    asm volatile("cp.async.wait_group 2;" ::: "memory");
+    __syncwarp();
+    const uint32_t kt = ring + st_done, vt = kt + 16 * 256;
     float s[2][4];
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f;
+    for (int i = 0; i < 2; ++i) { s[i][0] = s[i][1] = s[i][2] = s[i][3] = 0.f; }
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        mma_m16n8k16(s[i], qa[c].x, qa[c].y, kq[i][c].x, kq[i][c].y);
-        mma_m16n8k16(s[i], qa[c].z, qa[c].w, kq[i][c].z, kq[i][c].w);
-      }
+    for (int ks = 0; ks < 8; ++ks) {
+      uint32_t bk[4];
+      const int key = (lm >> 1) * 8 + lr;
+      dec_ldsm(bk, kt + key * 256 + (((2 * ks + (lm & 1)) ^ (key & 7)) << 4));
+      mma_m16n8k16(s[0], qa[ks][0], qa[ks][1], bk[0], bk[1]);
+      mma_m16n8k16(s[1], qa[ks][0], qa[ks][1], bk[2], bk[3]);
     }
     float tmax = -INFINITY;
 #pragma unroll
@@ -148,42 +177,40 @@ __global__ void __launch_bounds__(kDecWarps * 32) decode_attn_kernel(const bf16*
     m = mn;
     const uint32_t pa0 = pack2_bf16(p00, p01), pa2 = pack2_bf16(p10, p11);
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const uint32_t ra[4] = {vq[0][h].x, vq[0][h].y, vq[0][h].z, vq[0][h].w}, rb[4] = {vq[1][h].x, vq[1][h].y, vq[1][h].z, vq[1][h].w};
-      const uint32_t rc[4] = {vq[2][h].x, vq[2][h].y, vq[2][h].z, vq[2][h].w}, rd[4] = {vq[3][h].x, vq[3][h].y, vq[3][h].z, vq[3][h].w};
-#pragma unroll
-      for (int p4 = 0; p4 < 4; ++p4) {
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          const int j = h * 8 + p4 * 2 + u;
-          const uint32_t sel = u ? 0x7632u : 0x5410u;
-          o[j][0] *= alpha; o[j][1] *= alpha;
-          mma_m16n8k16(o[j], pa0, pa2, prmt(ra[p4], rb[p4], sel), prmt(rc[p4], rd[p4], sel));
-        }
-      }
+    for (int c = 0; c < 16; c += 2) {
+      uint32_t bv[4];
+      const int key = (lm & 1) * 8 + lr;
+      dec_ldsm_t(bv, vt + key * 256 + (((c + (lm >> 1)) ^ (key & 7)) << 4));
+      o[c][0] *= alpha; o[c][1] *= alpha; o[c + 1][0] *= alpha; o[c + 1][1] *= alpha;
+      mma_m16n8k16(o[c], pa0, pa2, bv[0], bv[1]);
+      mma_m16n8k16(o[c + 1], pa0, pa2, bv[2], bv[3]);
     }
+    __syncwarp();                               // the stage may be refilled by the next issue_tile()
+    st_done = (st_done == (kDecStages - 1) * kDecTileBytes) ? 0u : st_done + kDecTileBytes;
   }
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
   l += __shfl_xor_sync(0xffffffffu, l, 1);
   l += __shfl_xor_sync(0xffffffffu, l, 2);
-  // accumulator column 2t+e of n-tile j = h*8+u is output dim h*64 + (2t+e)*8 + u
-  if (t == 0) { sm_m[w][g] = m; sm_l[w][g] = l; }
+  __syncthreads();                              // every warp is done with its ring: reuse it for the merge
+  float* sm_o = reinterpret_cast<float*>(dec_smem);                    // [kDecWarps][8][HD]
+  float* sm_m = sm_o + kDecWarps * 8 * HD;                             // [kDecWarps][8]
+  float* sm_l = sm_m + kDecWarps * 8;
+  if (t == 0) { sm_m[w * 8 + g] = m; sm_l[w * 8 + g] = l; }
 #pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    sm_o[w][g][(j >> 3) * 64 + (2 * t) * 8 + (j & 7)] = o[j][0];
-    sm_o[w][g][(j >> 3) * 64 + (2 * t + 1) * 8 + (j & 7)] = o[j][1];
-  }
+  for (int j = 0; j < 16; ++j)
+    *reinterpret_cast<float2*>(&sm_o[(w * 8 + g) * HD + j * 8 + 2 * t]) = make_float2(o[j][0], o[j][1]);
   __syncthreads();
   const int d = threadIdx.x;   // kDecWarps * 32 == HD
   for (int r = 0; r < G; ++r) {
     float mm = -INFINITY;
 #pragma unroll
-    for (int ww = 0; ww < kDecWarps; ++ww) mm = fmaxf(mm, sm_m[ww][r]);
+    for (int ww = 0; ww < kDecWarps; ++ww) mm = fmaxf(mm, sm_m[ww * 8 + r]);
     float num = 0.f, den = 0.f;
 #pragma unroll
     for (int ww = 0; ww < kDecWarps; ++ww) {
-      const float f = (sm_m[ww][r] == -INFINITY) ? 0.f : exp2f(sm_m[ww][r] - mm);
-      num += sm_o[ww][r][d] * f;
-      den += sm_l[ww][r] * f;
+      const float f = (sm_m[ww * 8 + r] == -INFINITY) ? 0.f : exp2f(sm_m[ww * 8 + r] - mm);
+      num += sm_o[(ww * 8 + r) * HD + d] * f;
+      den += sm_l[ww * 8 + r] * f;
     }
     // partial record per (b, head, split): [m, l, pad, pad, acc[128]]
     float* rec = part + (((long long)b * kv_heads * G + kvh * G + r) * kDecSplits + sp) * (HD + 4);
@@ -414,15 +441,17 @@ static int llm_layer(Model* m, int li, const bf16* x_in, bf16* x_out, const Laye
     FO1_RUN(attention_varlen(a, s));
   } else if (!dry) {
     FO1_RUN(rope_kv_append(B_.qkv, ldq, cs, rows, c.llm_heads, c.llm_kv_heads, hd, st->cache_len, kc, vc, m->kv_cap, s));
-    // one wave: 3 blocks of this kernel are resident per SM (154 registers); a 512-block grid on 444 slots ran two
-    const int slots = 3 * device_sm_count();
+    // one wave: 2 blocks of this kernel (96 KB of shared memory each) are resident per SM
+    static bool attr_set = false;
+    if (!attr_set) { FO1_CUDA(cudaFuncSetAttribute(decode_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDecSmemBytes)); attr_set = true; }
+    const int slots = 2 * device_sm_count();
     const int n_splits = std::max(1, std::min(kDecSplits, slots / std::max(1, rows * c.llm_kv_heads)));
     dim3 grid(rows, c.llm_kv_heads, n_splits);
     ProfScope prof("decode_attn", 0.0, 0.0, s);
     const int G = c.llm_heads / c.llm_kv_heads;
     const float scale = 1.0f / sqrtf((float)hd);
     if (G > 8 || hd != 128) { set_error("decode attention: GQA group %d / head_dim %d unsupported (group <= 8, head_dim 128)", G, hd); return FO1_ERR_UNSUPPORTED; }
-    launch_k(decode_attn_kernel, grid, dim3(kDecWarps * 32), 0, s, B_.qkv, (long long)ldq, kc, vc, st->cache_len, m->kv_cap, c.llm_kv_heads, G, B_.dec_part, scale);
+    launch_k(decode_attn_kernel, grid, dim3(kDecWarps * 32), kDecSmemBytes, s, B_.qkv, (long long)ldq, kc, vc, st->cache_len, m->kv_cap, c.llm_kv_heads, G, B_.dec_part, scale);
     FO1_LAUNCH_CHECK();
     launch_k(decode_attn_combine_kernel, dim3(rows, c.llm_heads), dim3(128), 0, s, B_.dec_part, B_.att, (long long)QD, c.llm_heads, n_splits);
     FO1_LAUNCH_CHECK();

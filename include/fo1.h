@@ -145,6 +145,24 @@ typedef struct {
 } fo1_attn_desc;
 int fo1_attention_varlen(const fo1_attn_desc* d, void* stream);
 
+/* Single-query GQA attention of one decode step over the K/V cache (the per-step attention of the HF generate loop,
+ * modeling_qwen2_5_vl.py:731-780 with past_key_values; mm_utils.py:640-654 drives it).  The step's own K/V must already
+ * sit in the cache at index cache_len[b].  head_dim 128, q_heads / kv_heads <= 8.  Exposed so the parity tests can
+ * check the kernel directly; fo1_llm_generate runs the same code. */
+typedef struct {
+  const void* q; int64_t ldq;        /* bf16 [n_seqs][q_heads*128] (rotated), row stride ldq elements */
+  const void* k_cache;               /* bf16 [n_seqs][cap][kv_heads*128] */
+  const void* v_cache;
+  const int32_t* cache_len;          /* device [n_seqs]: keys 0 .. cache_len[b] (inclusive) are attended */
+  int32_t n_seqs, cap, q_heads, kv_heads, head_dim;
+  float scale;
+  void* out; int64_t ldo;            /* bf16 [n_seqs][q_heads*128] */
+  void* workspace;                   /* fp32 partials, fo1_decode_attention_workspace_bytes(n_seqs, q_heads) */
+  size_t workspace_bytes;
+} fo1_decode_attn_desc;
+size_t fo1_decode_attention_workspace_bytes(int32_t n_seqs, int32_t q_heads);
+int fo1_decode_attention(const fo1_decode_attn_desc* d, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Model-level engine.  One handle per GPU / rank; calls on one handle are not re-entrant.
  * Weights are BORROWED device pointers (the caller keeps them alive): the Python loader prepares

@@ -49,3 +49,34 @@ def test_attention_varlen(hd, qh, kvh, causal, lens):
     err = (out.cpu().float() - ref).abs().max().item()
     # P is rounded to bf16 before PV (as flash-attn does) and the output is bf16: 2^-8 relative of |V| ~ 4
     assert err < 3e-2, err
+
+
+@pytest.mark.parametrize("q_heads,kv_heads", [(16, 2), (8, 2), (4, 4), (8, 1)])
+@pytest.mark.parametrize("lens", [[1, 15, 16, 17], [600, 1195, 33, 2, 257], [48] * 40])
+def test_decode_attention_matches_reference(q_heads, kv_heads, lens):
+    """One decode step of GQA attention over the K/V cache (tensor-core tile of the group's query heads, cp.async ring,
+    split over the keys) vs torch fp32 on the same bf16 cache; ragged lengths incl. < 1 tile, tile edges, many splits."""
+    from importlib import import_module
+    import fo1_b200  # noqa: F401
+    ops = import_module("vlm-fo1_b200.ops")
+    B, cap, hd = len(lens), max(lens) + 3, 128
+    g = torch.Generator(device="cuda").manual_seed(q_heads * 100 + kv_heads + len(lens))
+    q = torch.randn(B, q_heads * hd, device="cuda", generator=g).to(torch.bfloat16)
+    kc = torch.randn(B, cap, kv_heads * hd, device="cuda", generator=g).to(torch.bfloat16)
+    vc = torch.randn(B, cap, kv_heads * hd, device="cuda", generator=g).to(torch.bfloat16)
+    kc[:, -2:] = float("nan")      # slots beyond every length must never be read into the result
+    vc[:, -2:] = float("inf")
+    n = torch.tensor(lens, dtype=torch.int32, device="cuda")
+    scale = hd ** -0.5
+    out = ops.decode_attention(q, kc, vc, n - 1, q_heads, kv_heads, scale)
+    torch.cuda.synchronize()
+    G = q_heads // kv_heads
+    for b in range(B):
+        L = lens[b]
+        qb = q[b].float().view(q_heads, hd)
+        kb = kc[b, :L].float().view(L, kv_heads, hd).repeat_interleave(G, dim=1)      # [L, q_heads, hd]
+        vb = vc[b, :L].float().view(L, kv_heads, hd).repeat_interleave(G, dim=1)
+        p = torch.softmax(torch.einsum("hd,lhd->hl", qb, kb) * scale, dim=-1)
+        ref = torch.einsum("hl,lhd->hd", p, vb).reshape(-1)
+        err = (out[b].float() - ref).abs().max().item()
+        assert err <= 2e-2 * max(1.0, ref.abs().max().item()), (b, L, err)     # P is rounded to bf16 before P.V

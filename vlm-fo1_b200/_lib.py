@@ -51,6 +51,12 @@ class AttnDesc(C.Structure):
                 ("scale", C.c_float), ("causal", C.c_int32)]
 
 
+class DecodeAttnDesc(C.Structure):
+    _fields_ = [("q", C.c_void_p), ("ldq", C.c_int64), ("k_cache", C.c_void_p), ("v_cache", C.c_void_p), ("cache_len", C.c_void_p),
+                ("n_seqs", C.c_int32), ("cap", C.c_int32), ("q_heads", C.c_int32), ("kv_heads", C.c_int32), ("head_dim", C.c_int32),
+                ("scale", C.c_float), ("out", C.c_void_p), ("ldo", C.c_int64), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]
+
+
 _lib = None
 
 
@@ -72,6 +78,10 @@ def lib() -> C.CDLL:
     L.fo1_hfre_forward.restype = C.c_int
     L.fo1_hfre_forward.argtypes = [C.POINTER(HfreImage), C.c_int32, C.POINTER(HfreParams), C.c_void_p,
                                    C.c_size_t, C.c_void_p]
+    L.fo1_decode_attention_workspace_bytes.restype = C.c_size_t
+    L.fo1_decode_attention_workspace_bytes.argtypes = [C.c_int32, C.c_int32]
+    L.fo1_decode_attention.restype = C.c_int
+    L.fo1_decode_attention.argtypes = [C.POINTER(DecodeAttnDesc), C.c_void_p]
     L.fo1_gemm_bf16.restype = C.c_int
     L.fo1_gemm_bf16.argtypes = [C.POINTER(GemmDesc), C.c_void_p]
     L.fo1_attention_varlen.restype = C.c_int

@@ -241,6 +241,28 @@ __global__ void __launch_bounds__(128) decode_attn_combine_kernel(const float* _
   out[(long long)b * ldo + (long long)h * HD + d] = __float2bfloat16_rn(num / den);
 }
 
+// host side of the decode attention: split count = one wave of blocks (2 per SM: 96 KB of shared memory each)
+static int decode_attention(const bf16* q, long long ldq, const bf16* kc, const bf16* vc, const int* cache_len, int rows, int cap,
+                            int q_heads, int kv_heads, int hd, float scale, bf16* out, long long ldo, float* part, cudaStream_t s) {
+  const int G = kv_heads > 0 ? q_heads / kv_heads : 0;
+  if (kv_heads <= 0 || q_heads % kv_heads != 0 || G > 8 || hd != 128) {
+    set_error("decode attention: %d/%d heads, head_dim %d unsupported (GQA group <= 8, head_dim 128)", q_heads, kv_heads, hd);
+    return FO1_ERR_UNSUPPORTED;
+  }
+  if (rows == 0) return FO1_OK;
+  static bool attr_set = false;
+  if (!attr_set) { FO1_CUDA(cudaFuncSetAttribute(decode_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDecSmemBytes)); attr_set = true; }
+  const int slots = 2 * device_sm_count();
+  const int n_splits = std::max(1, std::min(kDecSplits, slots / std::max(1, rows * kv_heads)));
+  dim3 grid(rows, kv_heads, n_splits);
+  ProfScope prof("decode_attn", 0.0, 0.0, s);
+  launch_k(decode_attn_kernel, grid, dim3(kDecWarps * 32), kDecSmemBytes, s, q, ldq, kc, vc, cache_len, cap, kv_heads, G, part, scale);
+  FO1_LAUNCH_CHECK();
+  launch_k(decode_attn_combine_kernel, dim3(rows, q_heads), dim3(128), 0, s, (const float*)part, out, ldo, q_heads, n_splits);
+  FO1_LAUNCH_CHECK();
+  return FO1_OK;
+}
+
 // greedy token: lowest index among the maxima of a fp32 logits row
 __global__ void __launch_bounds__(1024) argmax_kernel(const float* __restrict__ logits, int V, int* __restrict__ out) {
   griddep_launch();
@@ -441,20 +463,8 @@ static int llm_layer(Model* m, int li, const bf16* x_in, bf16* x_out, const Laye
     FO1_RUN(attention_varlen(a, s));
   } else if (!dry) {
     FO1_RUN(rope_kv_append(B_.qkv, ldq, cs, rows, c.llm_heads, c.llm_kv_heads, hd, st->cache_len, kc, vc, m->kv_cap, s));
-    // one wave: 2 blocks of this kernel (96 KB of shared memory each) are resident per SM
-    static bool attr_set = false;
-    if (!attr_set) { FO1_CUDA(cudaFuncSetAttribute(decode_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDecSmemBytes)); attr_set = true; }
-    const int slots = 2 * device_sm_count();
-    const int n_splits = std::max(1, std::min(kDecSplits, slots / std::max(1, rows * c.llm_kv_heads)));
-    dim3 grid(rows, c.llm_kv_heads, n_splits);
-    ProfScope prof("decode_attn", 0.0, 0.0, s);
-    const int G = c.llm_heads / c.llm_kv_heads;
-    const float scale = 1.0f / sqrtf((float)hd);
-    if (G > 8 || hd != 128) { set_error("decode attention: GQA group %d / head_dim %d unsupported (group <= 8, head_dim 128)", G, hd); return FO1_ERR_UNSUPPORTED; }
-    launch_k(decode_attn_kernel, grid, dim3(kDecWarps * 32), kDecSmemBytes, s, B_.qkv, (long long)ldq, kc, vc, st->cache_len, m->kv_cap, c.llm_kv_heads, G, B_.dec_part, scale);
-    FO1_LAUNCH_CHECK();
-    launch_k(decode_attn_combine_kernel, dim3(rows, c.llm_heads), dim3(128), 0, s, B_.dec_part, B_.att, (long long)QD, c.llm_heads, n_splits);
-    FO1_LAUNCH_CHECK();
+    FO1_RUN(decode_attention(B_.qkv, ldq, kc, vc, st->cache_len, rows, m->kv_cap, c.llm_heads, c.llm_kv_heads, hd,
+                             1.0f / sqrtf((float)hd), B_.att, QD, B_.dec_part, s));
   }
   FO1_RUN(linear(B_.att, QD, L.o_w, QD, B_.x_mid, H, FO1_BF16, rows, H, QD, nullptr, 0, FO1_EPI_NONE, x_in, H, 0, s));
   FO1_RUN(rmsnorm(B_.x_mid, H, L.ln2, B_.xn, H, rows, H, c.rms_eps, s));
@@ -744,4 +754,24 @@ extern "C" int fo1_llm_build_embeds(fo1_model* m, const int32_t* src_kind, const
 extern "C" int fo1_llm_generate(fo1_model* m, fo1_generate_desc* d, void* stream) {
   FO1_CHECK_ARG(m && d, "fo1_llm_generate: null argument");
   return llm_generate(m, d, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" size_t fo1_decode_attention_workspace_bytes(int32_t n_seqs, int32_t q_heads) {
+  return (size_t)(n_seqs > 0 ? n_seqs : 0) * (q_heads > 0 ? q_heads : 0) * fo1::kDecSplits * (128 + 4) * sizeof(float);
+}
+
+extern "C" int fo1_decode_attention(const fo1_decode_attn_desc* d, void* stream) {
+  using namespace fo1;
+  FO1_CHECK_ARG(d != nullptr, "fo1_decode_attention: null descriptor");
+  FO1_CHECK_ARG(d->n_seqs >= 0 && d->cap > 0, "fo1_decode_attention: bad n_seqs / cap");
+  if (d->n_seqs == 0) return FO1_OK;
+  FO1_CHECK_ARG(d->q && d->k_cache && d->v_cache && d->cache_len && d->out, "fo1_decode_attention: null pointer");
+  FO1_CHECK_ARG(d->n_seqs <= 65535, "fo1_decode_attention: n_seqs %d exceeds the grid limit", d->n_seqs);
+  FO1_CHECK_ARG((d->ldq % 2) == 0 && (d->ldo % 8) == 0 && (reinterpret_cast<uintptr_t>(d->k_cache) & 15) == 0 && (reinterpret_cast<uintptr_t>(d->v_cache) & 15) == 0,
+                "fo1_decode_attention: pitches / cache pointers misaligned");
+  const size_t need = fo1_decode_attention_workspace_bytes(d->n_seqs, d->q_heads);
+  if (d->workspace == nullptr || d->workspace_bytes < need) { set_error("fo1_decode_attention: workspace %zu B < required %zu B", d->workspace_bytes, need); return FO1_ERR_WORKSPACE; }
+  return decode_attention(static_cast<const bf16*>(d->q), d->ldq, static_cast<const bf16*>(d->k_cache), static_cast<const bf16*>(d->v_cache), d->cache_len,
+                          d->n_seqs, d->cap, d->q_heads, d->kv_heads, d->head_dim, d->scale, static_cast<bf16*>(d->out), d->ldo,
+                          static_cast<float*>(d->workspace), static_cast<cudaStream_t>(stream));
 }

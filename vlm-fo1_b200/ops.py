@@ -88,3 +88,24 @@ def attention_varlen(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, cu_seqle
     d.scale, d.causal = scale, 1 if causal else 0
     check(lib().fo1_attention_varlen(C.byref(d), C.c_void_p(_stream())), "fo1_attention_varlen")
     return out
+
+
+def decode_attention(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tensor, cache_len: torch.Tensor, q_heads: int, kv_heads: int,
+                     scale: float, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """One decode step of GQA attention over the cache: q bf16 [B, q_heads*128]; k_cache / v_cache bf16 [B, cap, kv_heads*128];
+    cache_len int32 [B] on the device (keys 0..cache_len[b] inclusive are attended)."""
+    _require_cuda(q, k_cache, v_cache, cache_len)
+    B, cap = k_cache.shape[0], k_cache.shape[1]
+    assert q.dtype == torch.bfloat16 and k_cache.dtype == torch.bfloat16 and v_cache.dtype == torch.bfloat16 and cache_len.dtype == torch.int32
+    assert k_cache.is_contiguous() and v_cache.is_contiguous() and q.stride(1) == 1
+    if out is None:
+        out = torch.empty((B, q_heads * 128), dtype=torch.bfloat16, device=q.device)
+    L = lib()
+    need = L.fo1_decode_attention_workspace_bytes(B, q_heads)
+    ws = torch.empty(max(need, 16), dtype=torch.uint8, device=q.device)
+    d = _lib.DecodeAttnDesc()
+    d.q, d.ldq, d.k_cache, d.v_cache, d.cache_len = q.data_ptr(), q.stride(0), k_cache.data_ptr(), v_cache.data_ptr(), cache_len.data_ptr()
+    d.n_seqs, d.cap, d.q_heads, d.kv_heads, d.head_dim, d.scale = B, cap, q_heads, kv_heads, 128, scale
+    d.out, d.ldo, d.workspace, d.workspace_bytes = out.data_ptr(), out.stride(0), ws.data_ptr(), ws.numel()
+    check(L.fo1_decode_attention(C.byref(d), C.c_void_p(_stream())), "fo1_decode_attention")
+    return out

@@ -21,7 +21,7 @@ SHAPES = {"qkv": (2560, 2048, False, True), "o": (2048, 2048, False, False), "ga
 CANDS = {
     "qkv": [None, (32, 1), (32, 2), (64, 2), (64, 3), (64, 4), (64, 7), (128, 4), (128, 7), (128, 8), (128, 14), (256, 8), (256, 14), (256, 16)],
     "o": [None, (32, 2), (32, 4), (64, 4), (64, 8), (128, 8), (128, 9), (128, 16), (256, 16), (256, 18)],
-    "gateup": [None, (64, 1), (128, 1), (256, 1), (64, 3), (128, 3), (128, 6), (128, 7), (256, 5), (256, 7), (256, 12), (64, 2)],
+    "gateup": [None, (64, 1), (128, 1), (192, 1), (256, 1), (64, 3), (128, 3), (128, 6), (128, 7), (256, 5), (256, 7), (256, 12), (64, 2)],
     "down": [None, (32, 2), (32, 4), (64, 4), (64, 9), (128, 8), (128, 9), (128, 18), (128, 27), (256, 16), (256, 18), (256, 36)],
 }
 

@@ -85,7 +85,7 @@ def test_gemm_skinny_splitk(M, N, K):
     assert torch.equal(out, out2)      # fixed reduction order -> bitwise reproducible
 
 
-@pytest.mark.parametrize("tile_n,split_k", [(32, 1), (32, 4), (64, 3), (128, 8), (256, 5), (128, 1)])
+@pytest.mark.parametrize("tile_n,split_k", [(32, 1), (32, 4), (64, 3), (128, 8), (256, 5), (128, 1), (192, 1), (192, 3)])
 @pytest.mark.parametrize("M", [32, 130])
 def test_gemm_pinned_tile_and_split(tile_n, split_k, M):
     """every tile width x split-K variant the descriptor can pin: cooperative reduction by the last CTA of a tile,
@@ -107,7 +107,7 @@ def test_gemm_pinned_tile_and_split(tile_n, split_k, M):
     assert torch.equal(outs[0], outs[2])
 
 
-@pytest.mark.parametrize("tile_n,split_k", [(64, 1), (64, 3), (128, 4), (256, 2), (256, 7)])
+@pytest.mark.parametrize("tile_n,split_k", [(64, 1), (64, 3), (128, 4), (256, 2), (256, 7), (192, 1), (192, 2)])
 def test_gemm_gated_split(tile_n, split_k):
     """the gated epilogue after a split-K reduction (decode gate/up projection)"""
     ops = _ops()

@@ -54,8 +54,8 @@ constexpr int kMaxStages = 24;
 template <int BN>
 struct GemmCfg {
   static constexpr int kStageBytes = (BM * BK + BN * BK) * 2;
-  static constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : (BN == 64 ? 8 : 9));   // sets the smem budget; the ring depth is planned per launch
-  static constexpr int kTmemCols = 2 * BN;
+  static constexpr int kStages = (BN == 256) ? 4 : (BN == 192 ? 4 : (BN == 128 ? 6 : (BN == 64 ? 8 : 9)));   // sets the smem budget; the ring depth is planned per launch
+  static constexpr int kTmemCols = (BN == 192) ? 512 : 2 * BN;   // TMEM allocations are powers of two
   static constexpr int kStagingBytes = 8 * 4096;   // epilogue: 32 rows x 128 B per epilogue warp
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 512 /*barriers*/ + kStagingBytes;
   static_assert(kSmemBytes <= 232448, "exceeds the 227 KB of shared memory a CTA may opt into");
@@ -479,7 +479,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
     // tiles too narrow to split leave the second warp of a quarter idle (it still takes part in the barriers)
     constexpr bool kSplit32 = BN >= 64, kSplit64 = BN >= 128;
     const int p_beg = kSplit32 ? half * (BN / 2) : 0, p_end = kSplit32 ? (half + 1) * (BN / 2) : (half == 0 ? BN : 0);
-    const int g_beg = kSplit64 ? half * (BN / 2) : 0, g_end = kSplit64 ? (half + 1) * (BN / 2) : (half == 0 ? BN : 0);
+    // (BN = 192: the gated split must fall on a 64-column pair boundary -> 128 + 64)
+    const int g_cut = (BN == 192) ? 128 : BN / 2;
+    const int g_beg = kSplit64 ? half * g_cut : 0, g_end = kSplit64 ? (half == 0 ? g_cut : BN) : (half == 0 ? BN : 0);
     uint32_t tcount = 0;
     griddep_wait();   // residual reads / output writes are ordered after the previous kernel
     for (int work = blockIdx.x; work < num_tiles; work += gridDim.x, ++tcount) {
@@ -757,14 +759,18 @@ int gemm_bf16(const fo1_gemm_desc* d, cudaStream_t stream) {
       case 32: return launch_gemm<32>(d, stream, ks);
       case 64: return launch_gemm<64>(d, stream, ks);
       case 128: return launch_gemm<128>(d, stream, ks);
+      case 192: return launch_gemm<192>(d, stream, ks);
       case 256: return launch_gemm<256>(d, stream, ks);
-      default: set_error("fo1_gemm_bf16: tile_n=%d unsupported (32, 64, 128, 256)", d->tile_n); return FO1_ERR_INVALID_ARG;
+      default: set_error("fo1_gemm_bf16: tile_n=%d unsupported (32, 64, 128, 192, 256)", d->tile_n); return FO1_ERR_INVALID_ARG;
     }
   }
   // tile-width choice: widest tile that still yields >= 1 wave of CTAs, else narrower for occupancy
   const int sms = device_sm_count();
   const long long tm = ceil_div(d->M, BM);
   if (d->N >= 256 && tm * ceil_div(d->N, 256) >= sms) return launch_gemm<256>(d, stream);
+  // weight-streaming problems whose 128-wide tiles need a second, mostly empty wave (decode gate/up: 172 tiles on 148 SMs)
+  // run as ONE wave of 192-wide tiles instead (measured 27.3 -> 22.3 us, profiles/r01_sweep_skinny.json)
+  if (tm == 1 && d->N >= 192 && ceil_div(d->N, 128) > sms && ceil_div(d->N, 192) <= sms) return launch_gemm<192>(d, stream);
   if (d->N >= 128 && tm * ceil_div(d->N, 128) >= sms) return launch_gemm<128>(d, stream);
   if (d->gated || tm * ceil_div(d->N, 64) >= sms) return launch_gemm<64>(d, stream);
   // skinny problems (decode: M = batch, weight streaming): 64-wide tiles (the activation tile every CTA re-reads is

@@ -56,3 +56,33 @@ def hfre_level(feat_hwc, boxes, scale, P, up_hw):
         b = axis_weights(x1, x2, scale, P, W, up_hw[1])
         out[n] = np.einsum("r,rkc,k->c", a.astype(np.float64), feat_hwc.astype(np.float64), b.astype(np.float64))
     return out
+
+
+def _bf16_round(x):
+    """fp32 -> nearest-even bf16 -> fp32 (numpy)."""
+    u = np.asarray(x, dtype=np.float32).view(np.uint32).astype(np.uint64)
+    r = ((u + 0x7FFF + ((u >> 16) & 1)) >> 16) << 16
+    return r.astype(np.uint32).view(np.float32)
+
+
+def hfre_level_tensor_sweep(feat_hwc, boxes, scale, P, up_hw, region_rows=8, region_cols=32):
+    """Model of hfre_sweep_mma_kernel (algo 3): per (8 x 32)-cell region and box, the row sums over the region's columns
+    use the column weights as hi + lo bf16 halves against the bf16 map (products exact, fp32 accumulation), the row
+    weight a_y is applied in fp32, regions are added into the output."""
+    H, W, C = feat_hwc.shape
+    L = _bf16_round(feat_hwc)                      # the kernels read bf16 maps
+    out = np.zeros((len(boxes), C), dtype=np.float32)
+    for n, (x1, y1, x2, y2) in enumerate(boxes):
+        a = axis_weights(y1, y2, scale, P, H, up_hw[0]).astype(np.float32)
+        b = axis_weights(x1, x2, scale, P, W, up_hw[1]).astype(np.float32)
+        b_hi = _bf16_round(b)
+        b_lo = _bf16_round(b - b_hi)
+        for r0 in range(0, H, region_rows):
+            for c0 in range(0, W, region_cols):
+                aa, rows = a[r0:r0 + region_rows], L[r0:r0 + region_rows, c0:c0 + region_cols]
+                if not aa.any() or not b[c0:c0 + region_cols].any():
+                    continue
+                row_sum = (np.einsum("rkc,k->rc", rows, b_hi[c0:c0 + region_cols]).astype(np.float32)
+                           + np.einsum("rkc,k->rc", rows, b_lo[c0:c0 + region_cols]).astype(np.float32))
+                out[n] += np.einsum("r,rc->c", aa, row_sum).astype(np.float32)
+    return out

@@ -533,6 +533,9 @@ __device__ __forceinline__ void cp_async16_zfill(uint32_t dst_smem, const void* 
   const int sz = valid ? 16 : 0;  // src-size 0 -> 16 bytes of zeros
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(sz) : "memory");
 }
+__device__ __forceinline__ void cp_async16_plain(uint32_t dst_smem, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_smem), "l"(src) : "memory");
+}
 __device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], uint32_t addr) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
 }
@@ -640,11 +643,19 @@ __global__ void __launch_bounds__(kSweepThreads, 4) hfre_sweep_mma_kernel(const 
         const int y = __ffs(pending) - 1;
         pending &= pending - 1;
         const __nv_bfloat16* prow = cp_src + (long long)(row0 + y) * rowpitch;
+        if (cp_ok == 0xffu) {                                // region and channel slice fully on the map: no predication
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          if (!((cols_any >> (i >> 2)) & 1u)) continue;    // column half without weights: neither loaded nor multiplied
-          const bool ok = (cp_ok >> i) & 1u;               // off-map cells / channels: zero-filled, source pointer stays in range
-          cp_async16_zfill(((i & 1) ? cp_dst_odd + (i - 1) * 512 : cp_dst_even + i * 512) + st_issue, ok ? prow + i * cp_step : prow, ok);
+          for (int i = 0; i < 8; ++i) {
+            if (!((cols_any >> (i >> 2)) & 1u)) continue;  // column half without weights: neither loaded nor multiplied
+            cp_async16_plain(((i & 1) ? cp_dst_odd + (i - 1) * 512 : cp_dst_even + i * 512) + st_issue, prow + i * cp_step);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            if (!((cols_any >> (i >> 2)) & 1u)) continue;
+            const bool ok = (cp_ok >> i) & 1u;             // off-map cells / channels: zero-filled, source pointer stays in range
+            cp_async16_zfill(((i & 1) ? cp_dst_odd + (i - 1) * 512 : cp_dst_even + i * 512) + st_issue, ok ? prow + i * cp_step : prow, ok);
+          }
         }
         st_issue = (st_issue == (kMmaStages - 1) * kMmaRowBytes) ? 0u : st_issue + kMmaRowBytes;
       }

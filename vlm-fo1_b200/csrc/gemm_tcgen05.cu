@@ -42,7 +42,6 @@ struct GemmArgs {
   // `counters[tile]` reduces them in split order (deterministic) and runs the epilogue
   int ksplit, kb_per_split;
   int coalesce;   // 1: epilogue stages rows through shared memory and writes full 128-byte lines (needs 16-byte aligned D / residual rows)
-  int debug_skip_a;   // tuning experiment only (env FO1_GEMM_SKIP_A): do not fetch A (results are garbage)
   int stages;     // ring depth actually used (<= kMaxStages): skinny problems trade the unused A rows for more stages in flight
   int a_stage_bytes, b_stage_bytes;
   int stage_tx;   // bytes one ring stage receives (A box rows x 128 B + BN x 128 B): skinny problems load only the live A rows
@@ -426,9 +425,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
             ptx::tma_load_2d(ptx::smem_u32(smem_b + i * g.b_stage_bytes), &tmW, fb, (kb0 + i) * BK, n0);
           }
           griddep_wait();
-          if (!g.debug_skip_a)
-            for (int i = 0; i < pre; ++i)
-              ptx::tma_load_2d(ptx::smem_u32(smem_a + i * g.a_stage_bytes), &tmA, ptx::smem_u32(full_bar + i), (kb0 + i) * BK, m0);
+          for (int i = 0; i < pre; ++i)
+            ptx::tma_load_2d(ptx::smem_u32(smem_a + i * g.a_stage_bytes), &tmA, ptx::smem_u32(full_bar + i), (kb0 + i) * BK, m0);
           it = pre; kb = kb0 + pre;
         }
         for (; kb < kb1; ++kb, ++it) {
@@ -436,7 +434,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           ptx::mbar_wait(ptx::smem_u32(empty_bar + s), ph ^ 1);
           const uint32_t fb = ptx::smem_u32(full_bar + s);
           ptx::mbar_expect_tx(fb, (uint32_t)g.stage_tx);
-          if (!g.debug_skip_a) ptx::tma_load_2d(ptx::smem_u32(smem_a + s * g.a_stage_bytes), &tmA, fb, kb * BK, m0);
+          ptx::tma_load_2d(ptx::smem_u32(smem_a + s * g.a_stage_bytes), &tmA, fb, kb * BK, m0);
           ptx::tma_load_2d(ptx::smem_u32(smem_b + s * g.b_stage_bytes), &tmW, fb, kb * BK, n0);
         }
       }
@@ -694,9 +692,7 @@ static int launch_gemm(const fo1_gemm_desc* d, cudaStream_t stream, int ksplit =
   g.gated = d->gated;
   g.tiles_m = ceil_div(d->M, BM);
   g.tiles_n = ceil_div(d->N, BN);
-  static const bool tune_skip_a = getenv("FO1_GEMM_SKIP_A") != nullptr;
-  g.debug_skip_a = tune_skip_a ? 1 : 0;
-  g.stage_tx = ((tune_skip_a ? 0 : a_rows) + BN) * BK * 2;
+  g.stage_tx = (a_rows + BN) * BK * 2;
   // the UMMA reads all 128 A rows of a stage: keep the full 16 KB slot unless only the live rows are loaded AND the
   // rows beyond them may alias the next stage's data (harmless: those accumulator rows are never stored)
   g.a_stage_bytes = (a_rows < BM) ? ((a_rows * BK * 2 + 1023) & ~1023) : BM * BK * 2;

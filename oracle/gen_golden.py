@@ -482,6 +482,51 @@ def gen_mm_utils() -> None:
 STAGES.update({"mm_utils": gen_mm_utils})
 
 
+def gen_processors() -> None:
+    """Pins vlm_fo1/processors.py (the host-side pre-processing):
+    * aux tower: the REFERENCE's own CLIPImageProcessor (davit/image_processing_clip.py:222-367 with the img_cfg of
+      davit/configs.py:139-152), loaded by file path, in both resize modes ('dynamic' = the released checkpoint, 'squash');
+    * primary tower: the reference calls transformers' Qwen2VLImageProcessor (qwen2_5_vl_encoder.py:210-225, transformers
+      4.50.1).  That release is not installed here; the INSTALLED transformers (version recorded in the fixture) provides
+      the same class, whose resize may differ from the pinned release by <= 2 uint8 steps on a small fraction of pixels, so
+      images that need no resize pin the patch order / normalisation exactly and resized ones pin the grid + values to 2 LSB.
+    Outputs are stored as a strided sample + a float64 sum; the input images are re-drawn by the test (seed 11)."""
+    import importlib.util
+    import transformers
+    from PIL import Image
+    spec = importlib.util.spec_from_file_location("ref_clip_ip", os.path.join(ref_shim.REFERENCE_ROOT, "vlm_fo1/model/multimodal_encoder/davit/image_processing_clip.py"))
+    RC = importlib.util.module_from_spec(spec); spec.loader.exec_module(RC)
+    from transformers.models.qwen2_vl.image_processing_qwen2_vl import Qwen2VLImageProcessor
+    base = {"do_resize": True, "size": {"height": 768, "width": 768}, "resample": 3, "do_center_crop": False, "do_rescale": True,
+            "do_normalize": True, "image_mean": [0.485, 0.456, 0.406], "image_std": [0.229, 0.224, 0.225], "do_convert_rgb": True}
+    rng = np.random.default_rng(11)
+    out = {"transformers_version": np.array(transformers.__version__)}
+    sizes = [(56, 84), (399, 500), (64, 33), (20, 20), (301, 1203)]
+    out["sizes"] = np.array(sizes)
+    prim = Qwen2VLImageProcessor(min_pixels=56 * 56, max_pixels=2048 * 2048)
+    for i, hw in enumerate(sizes):
+        arr = rng.integers(0, 256, hw + (3,), dtype=np.uint8)   # the test regenerates the images from the same seed / order
+        img = Image.fromarray(arr)
+        for mode in ("dynamic", "squash"):
+            cfg = dict(base); cfg["resize_mode"] = mode
+            if mode == "dynamic":
+                cfg["do_resize"] = False
+            r = RC.CLIPImageProcessor(**cfg).preprocess(img, return_tensors="pt")["pixel_values"][0].numpy()
+            out[f"aux_{mode}{i}_shape"] = np.array(r.shape)
+            out[f"aux_{mode}{i}_sample"] = r[:, ::7, ::5].copy()
+            out[f"aux_{mode}{i}_sum"] = np.array(r.astype(np.float64).sum())
+        q = prim.preprocess(img, return_tensors="pt")
+        px = q["pixel_values"].numpy()
+        out[f"prim{i}_grid"] = q["image_grid_thw"].numpy()
+        out[f"prim{i}_shape"] = np.array(px.shape)
+        out[f"prim{i}_sample"] = px[::3, ::11].copy()
+        out[f"prim{i}_sum"] = np.array(px.astype(np.float64).sum())
+    save("processors", **out)
+
+
+STAGES.update({"processors": gen_processors})
+
+
 if __name__ == "__main__":
     torch.set_grad_enabled(False)
     wanted = sys.argv[1:] or list(STAGES)

@@ -708,7 +708,8 @@ static int launch_gemm(const fo1_gemm_desc* d, cudaStream_t stream, int ksplit =
     const int esz = d->d_dtype == FO1_BF16 ? 2 : 4;
     const bool d_ok = (reinterpret_cast<uintptr_t>(d->D) & 15) == 0 && (d->ldd * esz) % 16 == 0;
     const bool r_ok = d->residual == nullptr || ((reinterpret_cast<uintptr_t>(d->residual) & 15) == 0 && (d->ldr * 2) % 16 == 0);
-    g.coalesce = (d_ok && r_ok && getenv("FO1_GEMM_DIRECT_STORE") == nullptr) ? 1 : 0;
+    static const bool direct_store = getenv("FO1_GEMM_DIRECT_STORE") != nullptr;   // A/B knob: per-row stores instead of the smem-staged lines
+    g.coalesce = (d_ok && r_ok && !direct_store) ? 1 : 0;
   }
   const int num_kb = ceil_div(d->K, BK);
   g.kb_per_split = ceil_div(num_kb, ksplit);

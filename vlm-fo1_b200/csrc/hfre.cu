@@ -507,20 +507,18 @@ __global__ void __launch_bounds__(kSweepThreads) hfre_sweep_kernel(const BatchDe
 // the bf16 map, fp32 accumulate) and only the per-row scaling by a_y stays on the FMA pipe (1 FMA per 32 MACs).
 // The fp32 weights are fed as hi + lo bf16 halves (two MMAs): the map is bf16 already, so products are exact and
 // the weights keep 16 mantissa bits -- inside the 1e-3 parity budget with three orders of margin.
-// Same work split as the SIMT sweep: CTA = (level, 32 x 32 cell region, 256 channels), warp = 64 channels, a pass
-// accumulates 32 boxes (2 m-tiles); A fragments depend on the boxes only and are built once per pass; B fragments
-// come straight from global memory (16-byte loads of 8 channels of one cell; the two cells an mma B register pairs
-// are transposed out of two loads with one PRMT each).
+// Work split: CTA = (level, 8 x 32 cell region, 256 channels), warp = 64 channels, a pass accumulates 16 boxes (one
+// m-tile; regions with more boxes take further passes whose rows come from L2 -- 8-row regions keep the footprint of
+// all resident CTAs below the L2 size).  A fragments depend on the boxes only and are built once per pass from the
+// region's weight records (hfre_region_records_kernel).  Every region row is copied ONCE per pass into a per-warp
+// cp.async ring (3 rows, two in flight behind the one being reduced; 16-byte chunks XOR-swizzled by cell) and its
+// B fragments are taken with ldmatrix.trans.  The partial sums of the pass leave through shared memory (aliasing the
+// ring) as coalesced fp32 reductions into out[box][channel].
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-__device__ __forceinline__ uint32_t prmt_b32(uint32_t a, uint32_t b, uint32_t sel) {
-  uint32_t r;
-  asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
-  return r;
 }
 // w0, w1 -> packed bf16 pairs of their high parts and of the remainders
 __device__ __forceinline__ void split_pair(float w0, float w1, uint32_t& hi, uint32_t& lo) {

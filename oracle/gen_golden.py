@@ -527,6 +527,23 @@ def gen_processors() -> None:
 STAGES.update({"processors": gen_processors})
 
 
+def gen_prompt_data() -> None:
+    """Pins the pure-data mirrors vlm_fo1/constants.py and vlm_fo1/task_templates.py: every public str / int of the
+    REFERENCE's two modules, dumped to tests/golden/prompt_data.json."""
+    import importlib.util, json
+    out = {}
+    for mod in ("constants", "task_templates"):
+        spec = importlib.util.spec_from_file_location(f"ref_{mod}", os.path.join(ref_shim.REFERENCE_ROOT, "vlm_fo1", mod + ".py"))
+        m = importlib.util.module_from_spec(spec); spec.loader.exec_module(m)
+        out[mod] = {k: v for k, v in vars(m).items() if not k.startswith("_") and isinstance(v, (str, int))}
+    path = os.path.join(GOLD, "prompt_data.json")
+    json.dump(out, open(path, "w"), indent=1, sort_keys=True)
+    print(f"wrote {path}")
+
+
+STAGES.update({"prompt_data": gen_prompt_data})
+
+
 if __name__ == "__main__":
     torch.set_grad_enabled(False)
     wanted = sys.argv[1:] or list(STAGES)

@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define FO1_ABI_VERSION 1
+#define FO1_ABI_VERSION 2
 
 typedef enum {
   FO1_OK = 0,
@@ -131,8 +131,10 @@ int fo1_gemm_bf16(const fo1_gemm_desc* d, void* stream);
 /* ------------------------------------------------------------------------------------------------
  * Variable-length softmax attention over packed token rows (replaces flash_attn_varlen_func at
  * modeling_qwen2_5_vl.py:205 and _flash_attention_forward at :895, and DaViT's window attention
- * modeling_davit.py:261-268).  q/k/v/o: bf16 rows with the given pitches (elements); head h of a row
- * starts at h*head_dim.  cu_seqlens: device int32 [n_seqs+1].  head_dim in {32, 80, 128}.
+ * modeling_davit.py:261-268) on tcgen05 / TMEM with TMA-fed K/V rings.  q/k/v/o: bf16 rows with the given
+ * pitches (elements, multiples of 8; 16-byte aligned bases); head h of a row starts at h*head_dim.
+ * cu_seqlens: device int32 [n_seqs+1]; total_rows = cu_seqlens[n_seqs] (the host passes it: it sizes the grid).
+ * head_dim in {32, 64, 80, 128}.
  * ---------------------------------------------------------------------------------------------- */
 typedef struct {
   const void* q; const void* k; const void* v; void* o;
@@ -142,6 +144,7 @@ typedef struct {
   int32_t q_heads, kv_heads, head_dim;
   float scale;
   int32_t causal;
+  int32_t total_rows;
 } fo1_attn_desc;
 int fo1_attention_varlen(const fo1_attn_desc* d, void* stream);
 
@@ -192,6 +195,9 @@ typedef struct {
 } fo1_model_config;
 
 int fo1_model_create(const fo1_model_config* cfg, fo1_model** out);
+/* Entries of the handle's cache of device-side integer tables (window indices, cu_seqlens ...).  The cache is trimmed
+ * only at the entry of a forward, never while one is using its tables; exposed for the test of that rule. */
+int fo1_int_cache_entries(fo1_model* m);
 void fo1_model_destroy(fo1_model* m);
 /* Register one prepared weight (device pointer, borrowed).  Names: see DESIGN.md / vlm-fo1_b200/weights.py. */
 int fo1_model_set_weight(fo1_model* m, const char* name, const void* dev_ptr, int32_t dtype, int32_t ndim,
@@ -228,6 +234,10 @@ int fo1_fpn_forward(fo1_model* m, const void* tap, int32_t gh, int32_t gw, int32
 
 /* Region projector mm_projector_aux (omchat_qwen2_5_vl.py:107): bf16 [n][region_dim] -> bf16 [n][llm_hidden]. */
 int fo1_region_project(fo1_model* m, const void* feats, int32_t n, void* out, void* stream);
+/* Image projector mm_projector (encode_images, omchat_qwen2_5_vl.py:58-66; multimodal_projector/builder.py:39-76) for the
+ * `linear` / `mlpNx_gelu` types: bf16 [n][vit_out_hidden] -> bf16 [n][llm_hidden].  The released checkpoint uses
+ * `identity` (proj_img_layers = 0): the call is then an error and the caller passes the tower output through. */
+int fo1_image_project(fo1_model* m, const void* feats, int32_t n, void* out, void* stream);
 
 
 /* ------------------------------------------------------------------------------------------------

@@ -14,15 +14,20 @@ from typing import Dict, List
 import torch
 import torch.nn.functional as F
 
+try:
+    from .precision import R
+except ImportError:  # run from inside the directory (gen_golden.py)
+    from precision import R  # type: ignore
+
 
 def _ln(x, w, b, eps=1e-5):
-    return F.layer_norm(x, (x.shape[-1],), w, b, eps)
+    return R(F.layer_norm(x, (x.shape[-1],), w, b, eps))
 
 
 def _dw(x, H, W, w, b):  # tokens [N, C] -> + depth-wise 3x3
     C = x.shape[1]
     y = F.conv2d(x.t().reshape(1, C, H, W), w, b, padding=1, groups=C)
-    return x + y.reshape(C, H * W).t()
+    return R(x + y.reshape(C, H * W).t())
 
 
 def _window_attn(y, H, W, heads, ws, p, w):
@@ -31,22 +36,22 @@ def _window_attn(y, H, W, heads, ws, p, w):
     m = F.pad(y.reshape(H, W, C), (0, 0, 0, pad_r, 0, pad_b))          # zero pad AFTER the norm (:248-251)
     Hp, Wp = H + pad_b, W + pad_r
     win = m.reshape(Hp // ws, ws, Wp // ws, ws, C).permute(0, 2, 1, 3, 4).reshape(-1, ws * ws, C)
-    qkv = (win @ w[p + "qkv.weight"].t() + w[p + "qkv.bias"]).reshape(win.shape[0], ws * ws, 3, heads, C // heads).permute(2, 0, 3, 1, 4)
+    qkv = R(win @ w[p + "qkv.weight"].t() + w[p + "qkv.bias"]).reshape(win.shape[0], ws * ws, 3, heads, C // heads).permute(2, 0, 3, 1, 4)
     q, k, v = qkv[0] * (C // heads) ** -0.5, qkv[1], qkv[2]
-    o = ((q @ k.transpose(-2, -1)).softmax(-1) @ v).transpose(1, 2).reshape(win.shape[0], ws * ws, C)
-    o = o @ w[p + "proj.weight"].t() + w[p + "proj.bias"]
+    o = R((q @ k.transpose(-2, -1)).softmax(-1) @ v).transpose(1, 2).reshape(win.shape[0], ws * ws, C)
+    o = R(o @ w[p + "proj.weight"].t() + w[p + "proj.bias"])
     o = o.reshape(Hp // ws, Wp // ws, ws, ws, C).permute(0, 2, 1, 3, 4).reshape(Hp, Wp, C)[:H, :W]
     return o.reshape(H * W, C)
 
 
 def _channel_attn(y, groups, p, w):
     N, C = y.shape
-    qkv = (y @ w[p + "qkv.weight"].t() + w[p + "qkv.bias"]).reshape(N, 3, groups, C // groups).permute(1, 2, 0, 3)
+    qkv = R(y @ w[p + "qkv.weight"].t() + w[p + "qkv.bias"]).reshape(N, 3, groups, C // groups).permute(1, 2, 0, 3)
     q, k, v = qkv[0] * float(N) ** -0.5, qkv[1], qkv[2]                  # [g, N, c]
     a = (q.transpose(-1, -2) @ k).softmax(-1)                              # [g, c, c]
     o = (a @ v.transpose(-1, -2)).transpose(-1, -2)                        # [g, N, c]
-    o = o.permute(1, 0, 2).reshape(N, C)
-    return o @ w[p + "proj.weight"].t() + w[p + "proj.bias"]
+    o = R(o.permute(1, 0, 2).reshape(N, C))
+    return R(o @ w[p + "proj.weight"].t() + w[p + "proj.bias"])
 
 
 def davit_forward(sd: Dict[str, torch.Tensor], cfg: dict, image: torch.Tensor, timing: dict = None) -> List[torch.Tensor]:
@@ -67,7 +72,7 @@ def davit_forward(sd: Dict[str, torch.Tensor], cfg: dict, image: torch.Tensor, t
         if cfg["patch_prenorm"][s]:
             x = _ln(x, w[p + "norm.weight"], w[p + "norm.bias"])
             x4 = x.t().reshape(1, -1, H, W)
-        y = F.conv2d(x4, w[p + "proj.weight"], w[p + "proj.bias"], stride=cfg["patch_stride"][s], padding=cfg["patch_padding"][s])
+        y = R(F.conv2d(R(x4), w[p + "proj.weight"], w[p + "proj.bias"], stride=cfg["patch_stride"][s], padding=cfg["patch_padding"][s]))
         _, C, H, W = y.shape
         x = y.reshape(C, H * W).t()
         if not cfg["patch_prenorm"][s]:
@@ -82,15 +87,15 @@ def davit_forward(sd: Dict[str, torch.Tensor], cfg: dict, image: torch.Tensor, t
                 if kind == "spatial_block":
                     a = "window_attn."
                     yy = _ln(x, w[q + a + "norm.weight"], w[q + a + "norm.bias"])
-                    x = x + _window_attn(yy, H, W, cfg["num_heads"][s], ws, q + a + "fn.", w)
+                    x = R(x + _window_attn(yy, H, W, cfg["num_heads"][s], ws, q + a + "fn.", w))
                 else:
                     a = "channel_attn."
                     yy = _ln(x, w[q + a + "norm.weight"], w[q + a + "norm.bias"])
-                    x = x + _channel_attn(yy, cfg["num_groups"][s], q + a + "fn.", w)
+                    x = R(x + _channel_attn(yy, cfg["num_groups"][s], q + a + "fn.", w))
                 x = _dw(x, H, W, w[q + "conv2.fn.dw.weight"], w[q + "conv2.fn.dw.bias"])
                 yy = _ln(x, w[q + "ffn.norm.weight"], w[q + "ffn.norm.bias"])
-                hmid = F.gelu(yy @ w[q + "ffn.fn.net.fc1.weight"].t() + w[q + "ffn.fn.net.fc1.bias"])
-                x = x + hmid @ w[q + "ffn.fn.net.fc2.weight"].t() + w[q + "ffn.fn.net.fc2.bias"]
+                hmid = R(F.gelu(yy @ w[q + "ffn.fn.net.fc1.weight"].t() + w[q + "ffn.fn.net.fc1.bias"]))
+                x = R(x + hmid @ w[q + "ffn.fn.net.fc2.weight"].t() + w[q + "ffn.fn.net.fc2.bias"])
             if timing is not None:
                 timing["block_s"][s].append(_time.perf_counter() - _tb)
         outs.append(x.reshape(H, W, C).clone())
@@ -101,7 +106,7 @@ def davit_forward(sd: Dict[str, torch.Tensor], cfg: dict, image: torch.Tensor, t
 def _chan_ln(x, w, b, eps=1e-6):  # [1, C, H, W], simple_fpn.py:73-78
     u = x.mean(1, keepdim=True)
     s = (x - u).pow(2).mean(1, keepdim=True)
-    return w[None, :, None, None] * ((x - u) / torch.sqrt(s + eps)) + b[None, :, None, None]
+    return R(w[None, :, None, None] * ((x - u) / torch.sqrt(s + eps)) + b[None, :, None, None])
 
 
 def fpn_forward(sd: Dict[str, torch.Tensor], tap_hwc: torch.Tensor) -> List[torch.Tensor]:
@@ -113,20 +118,20 @@ def fpn_forward(sd: Dict[str, torch.Tensor], tap_hwc: torch.Tensor) -> List[torc
         p = f"simfp_{stage}."
         y = x
         if stage == 1:
-            y = F.conv_transpose2d(y, w[p + "0.weight"], w[p + "0.bias"], stride=2)
-            y = F.gelu(_chan_ln(y, w[p + "1.weight"], w[p + "1.bias"]))
-            y = F.conv_transpose2d(y, w[p + "3.weight"], w[p + "3.bias"], stride=2)
+            y = R(F.conv_transpose2d(y, w[p + "0.weight"], w[p + "0.bias"], stride=2))
+            y = R(F.gelu(_chan_ln(y, w[p + "1.weight"], w[p + "1.bias"])))
+            y = R(F.conv_transpose2d(y, w[p + "3.weight"], w[p + "3.bias"], stride=2))
             i = 4
         elif stage == 2:
-            y = F.conv_transpose2d(y, w[p + "0.weight"], w[p + "0.bias"], stride=2)
+            y = R(F.conv_transpose2d(y, w[p + "0.weight"], w[p + "0.bias"], stride=2))
             i = 1
         elif stage == 3:
             i = 0
         else:
             y = F.max_pool2d(y, 2, 2)
             i = 1
-        y = _chan_ln(F.conv2d(y, w[p + f"{i}.weight"]), w[p + f"{i}.norm.weight"], w[p + f"{i}.norm.bias"])
-        y = _chan_ln(F.conv2d(y, w[p + f"{i + 1}.weight"], padding=1), w[p + f"{i + 1}.norm.weight"], w[p + f"{i + 1}.norm.bias"])
+        y = _chan_ln(R(F.conv2d(y, w[p + f"{i}.weight"])), w[p + f"{i}.norm.weight"], w[p + f"{i}.norm.bias"])
+        y = _chan_ln(R(F.conv2d(y, w[p + f"{i + 1}.weight"], padding=1)), w[p + f"{i + 1}.norm.weight"], w[p + f"{i + 1}.norm.bias"])
         outs.append(y[0].permute(1, 2, 0).contiguous())
     return outs
 
@@ -140,6 +145,6 @@ def projector_forward(sd: Dict[str, torch.Tensor], x: torch.Tensor) -> torch.Ten
     idx = sorted({int(k.split(".")[0]) for k in w})
     for n, i in enumerate(idx):
         if n:
-            y = F.gelu(y)
-        y = y @ w[f"{i}.weight"].t() + w[f"{i}.bias"]
+            y = R(F.gelu(y))
+        y = R(y @ w[f"{i}.weight"].t() + w[f"{i}.bias"])
     return y

@@ -19,6 +19,11 @@ from typing import Dict, List, Sequence, Tuple
 import torch
 import torch.nn.functional as F
 
+try:
+    from .precision import R
+except ImportError:  # run from inside the directory (gen_golden.py)
+    from precision import R  # type: ignore
+
 IMAGE_PLACEHOLDER = -200   # vlm_fo1/constants.py IMAGE_TOKEN_INDEX
 REGION_PLACEHOLDER = -300  # DEFAULT_REGION_INDEX
 
@@ -74,7 +79,7 @@ def rope_index(ids: Sequence[int], image_grids: Sequence[Tuple[int, int]], image
 
 
 def rms_norm(x, w, eps):
-    return w * (x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + eps))
+    return R(w * R(x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + eps)))   # :137-140 casts before the gain
 
 
 def _rot_half(x):
@@ -115,11 +120,11 @@ class Decoder:
             _tl = _time.perf_counter()
             p = f"layers.{i}."
             y = rms_norm(x, w[p + "input_layernorm.weight"], c["rms_norm_eps"])
-            q = (y @ w[p + "self_attn.q_proj.weight"].t() + w[p + "self_attn.q_proj.bias"]).reshape(n, self.nh, self.hd)
-            k = (y @ w[p + "self_attn.k_proj.weight"].t() + w[p + "self_attn.k_proj.bias"]).reshape(n, self.nkv, self.hd)
-            v = (y @ w[p + "self_attn.v_proj.weight"].t() + w[p + "self_attn.v_proj.bias"]).reshape(n, self.nkv, self.hd)
-            q = q * cos[:, None, :] + _rot_half(q) * sin[:, None, :]
-            k = k * cos[:, None, :] + _rot_half(k) * sin[:, None, :]
+            q = R(y @ w[p + "self_attn.q_proj.weight"].t() + w[p + "self_attn.q_proj.bias"]).reshape(n, self.nh, self.hd)
+            k = R(y @ w[p + "self_attn.k_proj.weight"].t() + w[p + "self_attn.k_proj.bias"]).reshape(n, self.nkv, self.hd)
+            v = R(y @ w[p + "self_attn.v_proj.weight"].t() + w[p + "self_attn.v_proj.bias"]).reshape(n, self.nkv, self.hd)
+            q = R(q * cos[:, None, :] + _rot_half(q) * sin[:, None, :])
+            k = R(k * cos[:, None, :] + _rot_half(k) * sin[:, None, :])
             pk, pv = self.kv[i]
             k_all = k if pk is None else torch.cat([pk, k], 0)
             v_all = v if pv is None else torch.cat([pv, v], 0)
@@ -129,10 +134,10 @@ class Decoder:
             s = torch.einsum("qhd,khd->hqk", q, k_all.repeat_interleave(rep, 1)) / math.sqrt(self.hd)
             mask = torch.arange(k_all.shape[0])[None, :] > (past + torch.arange(n))[:, None]
             s = s.masked_fill(mask[None], float("-inf"))
-            a = torch.einsum("hqk,khd->qhd", s.softmax(-1), v_all.repeat_interleave(rep, 1)).reshape(n, self.H)
-            x = x + a @ w[p + "self_attn.o_proj.weight"].t()
+            a = R(torch.einsum("hqk,khd->qhd", s.softmax(-1), v_all.repeat_interleave(rep, 1))).reshape(n, self.H)
+            x = R(x + a @ w[p + "self_attn.o_proj.weight"].t())
             y = rms_norm(x, w[p + "post_attention_layernorm.weight"], c["rms_norm_eps"])
-            x = x + (F.silu(y @ w[p + "mlp.gate_proj.weight"].t()) * (y @ w[p + "mlp.up_proj.weight"].t())) @ w[p + "mlp.down_proj.weight"].t()
+            x = R(x + R(F.silu(y @ w[p + "mlp.gate_proj.weight"].t()) * (y @ w[p + "mlp.up_proj.weight"].t())) @ w[p + "mlp.down_proj.weight"].t())
             self.layer_seconds.append(_time.perf_counter() - _tl)
         return x
 

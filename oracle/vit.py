@@ -16,6 +16,11 @@ from typing import Dict, List, Sequence, Tuple
 import torch
 import torch.nn.functional as F
 
+try:
+    from .precision import R
+except ImportError:  # run from inside the directory (gen_golden.py)
+    from precision import R  # type: ignore
+
 
 def window_index(gh: int, gw: int, window_size: int = 112, merge: int = 2, patch: int = 14) -> Tuple[List[int], List[int]]:
     """get_window_index (:465-504) for one image with t = 1, after unique_consecutive (encoder :109).
@@ -49,7 +54,7 @@ def patch_positions(gh: int, gw: int, merge: int = 2) -> torch.Tensor:
 
 
 def rms_norm(x: torch.Tensor, w: torch.Tensor, eps: float = 1e-6) -> torch.Tensor:
-    return w * (x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + eps))
+    return R(w * R(x * torch.rsqrt(x.pow(2).mean(-1, keepdim=True) + eps)))   # :137-140 casts before the gain
 
 
 def _rot_half(x):
@@ -67,7 +72,7 @@ def vit_forward(sd: Dict[str, torch.Tensor], cfg: dict, pixel_values: torch.Tens
     import time as _time
     _t0 = _time.perf_counter()
     w = {k: v.float() for k, v in sd.items()}
-    x = pixel_values.float() @ w["patch_embed.proj.weight"].reshape(H, -1).t()
+    x = R(R(pixel_values.float()) @ w["patch_embed.proj.weight"].reshape(H, -1).t())
     widx, cu_win = window_index(gh, gw, cfg["window_size"], merge, cfg["patch_size"])
     perm = torch.tensor(widx)
     x = x.reshape(T // unit, unit, H)[perm].reshape(T, H)
@@ -87,10 +92,10 @@ def vit_forward(sd: Dict[str, torch.Tensor], cfg: dict, pixel_values: torch.Tens
         full = L in cfg["fullatt_block_indexes"]
         cu = [0, T] if full else cu_win
         y = rms_norm(x, w[p + "norm1.weight"])
-        qkv = (y @ w[p + "attn.qkv.weight"].t() + w[p + "attn.qkv.bias"]).reshape(T, 3, heads, hd)
+        qkv = R(y @ w[p + "attn.qkv.weight"].t() + w[p + "attn.qkv.bias"]).reshape(T, 3, heads, hd)
         q, k, v = qkv[:, 0], qkv[:, 1], qkv[:, 2]
-        q = q * cos + _rot_half(q) * sin
-        k = k * cos + _rot_half(k) * sin
+        q = R(q * cos + _rot_half(q) * sin)
+        k = R(k * cos + _rot_half(k) * sin)
         out = torch.empty(T, heads, hd)
         seg = cu[1] - cu[0]
         if all(b - a == seg for a, b in zip(cu[:-1], cu[1:])):   # equal-length segments: one batched product
@@ -102,11 +107,11 @@ def vit_forward(sd: Dict[str, torch.Tensor], cfg: dict, pixel_values: torch.Tens
             for a, b in zip(cu[:-1], cu[1:]):
                 s = torch.einsum("qhd,khd->hqk", q[a:b], k[a:b]) / math.sqrt(hd)
                 out[a:b] = torch.einsum("hqk,khd->qhd", s.softmax(-1), v[a:b])
-        x = x + out.reshape(T, H) @ w[p + "attn.proj.weight"].t() + w[p + "attn.proj.bias"]
+        x = R(x + R(out).reshape(T, H) @ w[p + "attn.proj.weight"].t() + w[p + "attn.proj.bias"])
         y = rms_norm(x, w[p + "norm2.weight"])
         g = y @ w[p + "mlp.gate_proj.weight"].t() + w[p + "mlp.gate_proj.bias"]
         u = y @ w[p + "mlp.up_proj.weight"].t() + w[p + "mlp.up_proj.bias"]
-        x = x + (F.silu(g) * u) @ w[p + "mlp.down_proj.weight"].t() + w[p + "mlp.down_proj.bias"]
+        x = R(x + R(F.silu(g) * u) @ w[p + "mlp.down_proj.weight"].t() + w[p + "mlp.down_proj.bias"])
         if full:
             # un-window: merged cell j of the sequence is cell widx[j] of the image; its 4 tokens are the 2x2 patches
             cells = torch.empty(T // unit, unit, H)
@@ -117,7 +122,7 @@ def vit_forward(sd: Dict[str, torch.Tensor], cfg: dict, pixel_values: torch.Tens
             timing["blocks"].append((bool(full), _time.perf_counter() - _tb))
     _tm = _time.perf_counter()
     y = rms_norm(x, w["merger.ln_q.weight"]).reshape(T // unit, unit * H)
-    y = F.gelu(y @ w["merger.mlp.0.weight"].t() + w["merger.mlp.0.bias"]) @ w["merger.mlp.2.weight"].t() + w["merger.mlp.2.bias"]
+    y = R(R(F.gelu(y @ w["merger.mlp.0.weight"].t() + w["merger.mlp.0.bias"])) @ w["merger.mlp.2.weight"].t() + w["merger.mlp.2.bias"])
     merged = torch.empty_like(y)
     merged[perm] = y
     if timing is not None:

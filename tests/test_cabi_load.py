@@ -7,7 +7,7 @@ def test_library_loads_and_exports_header_symbols():
     G.build()
     import fo1_b200
     L = fo1_b200.lib()
-    assert L.fo1_abi_version() == 1
+    assert L.fo1_abi_version() == 2
     syms = fo1_b200._lib.exported_symbols()
     assert "fo1_hfre_forward" in syms and "fo1_gemm_bf16" in syms
     for s in syms:

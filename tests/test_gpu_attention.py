@@ -28,6 +28,13 @@ def _ref(q, k, v, cu, qh, kvh, hd, scale, causal):
     (32, 8, 8, False, [144] * 7),                       # DaViT 12x12 windows
     (128, 16, 2, True, [333, 1195, 64, 1]),             # LLM causal GQA prefill
     (128, 16, 2, False, [200]),
+    (80, 2, 2, False, [2116, 2116]),                    # C4 geometry: 46x46 grid, whole images straddle the 128-row tiles
+    (80, 2, 2, False, [64] * 33 + [48] * 2 + [36]),     # one 46x46 image's ragged window list (A2 table of SURVEY.md)
+    (80, 2, 2, False, [1, 127, 128, 129, 2, 255]),      # segment edges on / around the tile and key-tile boundaries
+    (32, 4, 4, False, [144] * 3 + [100]),               # last tile partly beyond T
+    (128, 8, 2, True, [1259] * 3),                      # C4 prompt length (244 + 529 + ...): causal tiles across sequences
+    (128, 4, 2, True, [64, 64, 64, 64, 5]),             # several short causal sequences inside one tile
+    (64, 4, 2, False, [300, 20]),
 ])
 def test_attention_varlen(hd, qh, kvh, causal, lens):
     from importlib import import_module
@@ -49,6 +56,50 @@ def test_attention_varlen(hd, qh, kvh, causal, lens):
     err = (out.cpu().float() - ref).abs().max().item()
     # P is rounded to bf16 before PV (as flash-attn does) and the output is bf16: 2^-8 relative of |V| ~ 4
     assert err < 3e-2, err
+    assert torch.isfinite(out).all()
+
+
+def test_attention_large_logits_rescale():
+    """Rows whose running maximum keeps growing (keys sorted by increasing score) force the lazy O rescale in TMEM on every
+    key tile; a peaked softmax (logit range ~ 60) must still match fp32."""
+    from importlib import import_module
+    import fo1_b200  # noqa: F401
+    ops = import_module("vlm-fo1_b200.ops")
+    T, hd, h = 1000, 128, 2
+    g = torch.Generator().manual_seed(7)
+    q = torch.randn(T, h * hd, generator=g)
+    k = torch.randn(T, h * hd, generator=g)
+    ramp = torch.linspace(0.0, 6.0, T).unsqueeze(1)
+    k = (k + ramp * torch.sign(q.mean(0, keepdim=True))).bfloat16()          # later keys score higher for most rows
+    q = (q * 3.0).bfloat16()
+    v = torch.randn(T, h * hd, generator=g).bfloat16()
+    cu = torch.tensor([0, T], dtype=torch.int32, device="cuda")
+    for causal in (False, True):
+        out = ops.attention_varlen(q.cuda(), k.cuda(), v.cuda(), cu, T, h, h, hd, hd ** -0.5, causal)
+        torch.cuda.synchronize()
+        ref = _ref(q, k, v, [0, T], h, h, hd, hd ** -0.5, causal)
+        err = (out.cpu().float() - ref).abs().max().item()
+        assert err < 3e-2, (causal, err)
+
+
+def test_attention_strided_inputs_and_reuse():
+    """q/k/v as column slices of one packed buffer with an odd number of heads in front, output with a pitch; the same
+    call twice (the rowseg scratch and the tensor maps are rebuilt per call) gives identical bits."""
+    from importlib import import_module
+    import fo1_b200  # noqa: F401
+    ops = import_module("vlm-fo1_b200.ops")
+    T, hd, qh, kvh = 777, 80, 3, 3
+    buf = torch.randn(T, 8 + 3 * qh * hd, device="cuda").to(torch.bfloat16)
+    q, k, v = buf[:, 8: 8 + qh * hd], buf[:, 8 + qh * hd: 8 + 2 * qh * hd], buf[:, 8 + 2 * qh * hd:]
+    cu = torch.tensor([0, 300, 301, 777], dtype=torch.int32, device="cuda")
+    obuf = torch.zeros(T, qh * hd + 16, device="cuda", dtype=torch.bfloat16)
+    o1 = ops.attention_varlen(q, k, v, cu, 476, qh, kvh, hd, hd ** -0.5, False, out=obuf[:, 8: 8 + qh * hd]).clone()
+    o2 = ops.attention_varlen(q, k, v, cu, 476, qh, kvh, hd, hd ** -0.5, False, out=obuf[:, 8: 8 + qh * hd]).clone()
+    torch.cuda.synchronize()
+    assert torch.equal(o1, o2)
+    assert obuf[:, :8].abs().max().item() == 0 and obuf[:, 8 + qh * hd:].abs().max().item() == 0     # nothing written outside
+    ref = _ref(q.cpu(), k.cpu(), v.cpu(), [0, 300, 301, 777], qh, kvh, hd, hd ** -0.5, False)
+    assert (o1.cpu().float() - ref).abs().max().item() < 3e-2
 
 
 @pytest.mark.parametrize("q_heads,kv_heads", [(16, 2), (8, 2), (4, 4), (8, 1)])

@@ -48,7 +48,7 @@ class AttnDesc(C.Structure):
                 ("ldq", C.c_int64), ("ldk", C.c_int64), ("ldv", C.c_int64), ("ldo", C.c_int64),
                 ("cu_seqlens", C.c_void_p), ("n_seqs", C.c_int32), ("max_seqlen", C.c_int32),
                 ("q_heads", C.c_int32), ("kv_heads", C.c_int32), ("head_dim", C.c_int32),
-                ("scale", C.c_float), ("causal", C.c_int32)]
+                ("scale", C.c_float), ("causal", C.c_int32), ("total_rows", C.c_int32)]
 
 
 class DecodeAttnDesc(C.Structure):

@@ -121,6 +121,8 @@ def random_state_dicts(cfg: EngineConfig, device, seed: int = 0) -> Dict[str, Di
         out["davit"] = random_davit(cfg.davit, g, device)
     if cfg.proj_aux_layers:
         out["proj_aux"] = random_projector(cfg.region_dim, cfg.llm["hidden_size"], cfg.proj_aux_layers, g, device)
+    if cfg.proj_img_layers and cfg.use_vit:
+        out["proj_img"] = random_projector(cfg.vit["out_hidden_size"], cfg.llm["hidden_size"], cfg.proj_img_layers, g, device)
     if cfg.use_llm:
         out["llm"] = random_llm(cfg.llm, g, device)
     return out

@@ -96,11 +96,17 @@ static int davit_forward_impl(Model* m, const float* const* images, int H0, int 
     }
     const int nwh = ceil_div(Hh, ws), nww = ceil_div(Ww, ws);
     const int n_win = B * nwh * nww, wtok = n_win * ws * ws;
-    const int* d_cu = nullptr;
+    const int *d_cu = nullptr, *d_tiles = nullptr;
+    int n_tiles = 0;
     if (!dry) {
-      std::vector<int> cu(n_win + 1);
+      std::vector<int> cu(n_win + 1), img_cu(B + 1), tiles;
       for (int i = 0; i <= n_win; ++i) cu[i] = i * ws * ws;
-      FO1_TRY(cached_ints(m, "dvcu:" + std::to_string(n_win) + ":" + std::to_string(ws), cu, &d_cu, s));
+      for (int b = 0; b <= B; ++b) img_cu[b] = b * nwh * nww * ws * ws;
+      attention_tile_table(img_cu, tiles);    // query tiles restart at every image (its bits do not depend on the batch slot)
+      n_tiles = (int)tiles.size() / 2;
+      const std::string key = "dv:" + std::to_string(B) + ":" + std::to_string(nwh * nww) + ":" + std::to_string(ws);
+      FO1_TRY(cached_ints(m, key + ":cu", cu, &d_cu, s));
+      FO1_TRY(cached_ints(m, key + ":til", tiles, &d_tiles, s));
     }
     for (int j = 0; j < c.davit_depths[st]; ++j) {
       for (int half = 0; half < 2; ++half) {
@@ -116,7 +122,8 @@ static int davit_forward_impl(Model* m, const float* const* images, int H0, int 
           AttnArgs a;
           a.q = qkv; a.k = qkv + C; a.v = qkv + 2 * C; a.o = ao;
           a.ldq = a.ldk = a.ldv = 3 * C; a.ldo = C;
-          a.cu_seqlens = d_cu; a.n_seqs = n_win; a.max_seqlen = ws * ws;
+          a.cu_seqlens = d_cu; a.n_seqs = n_win; a.max_seqlen = ws * ws; a.total_rows = wtok; a.tiles = d_tiles; a.n_tiles = n_tiles;
+          a.flops = 4.0 * wtok * (ws * ws) * C;
           a.q_heads = a.kv_heads = c.davit_heads[st]; a.head_dim = C / c.davit_heads[st];
           a.scale = 1.0f / sqrtf((float)a.head_dim); a.causal = 0;
           FO1_RUN(attention_varlen(a, s));
@@ -151,6 +158,7 @@ int davit_forward(Model* m, const float* const* images, int H, int W, int B, voi
   for (int i = 0; i < 4; ++i)
     FO1_CHECK_ARG(m->cfg.davit_dims[i] == 32 * m->cfg.davit_heads[i] && m->cfg.davit_dims[i] == 32 * m->cfg.davit_groups[i],
                   "DaViT stage %d: this engine needs 32 channels per head/group", i);
+  FO1_TRY(int_cache_trim(m));
   m->arena.reset(true);
   FO1_TRY(davit_forward_impl(m, images, H, W, B, stage_out, s, true));
   FO1_TRY(arena_ensure(m, m->arena.peak));
@@ -244,6 +252,7 @@ static int fpn_forward_impl(Model* m, const bf16* tap, int gh, int gw, int B, vo
 int fpn_forward(Model* m, const void* tap, int gh, int gw, int B, void* const* level_out, cudaStream_t s) {
   FO1_CHECK_ARG(m->fpn.ok, "fo1_fpn_forward: model not finalized (SimpleFPN weights unresolved)");
   FO1_CHECK_ARG(gh % 2 == 0 && gw % 2 == 0, "fo1_fpn_forward: grid %dx%d must be even", gh, gw);
+  FO1_TRY(int_cache_trim(m));
   m->arena.reset(true);
   FO1_TRY(fpn_forward_impl(m, static_cast<const bf16*>(tap), gh, gw, B, level_out, s, true));
   FO1_TRY(arena_ensure(m, m->arena.peak));
@@ -310,6 +319,12 @@ extern "C" int fo1_fpn_forward(fo1_model* m, const void* tap, int32_t gh, int32_
   if (n_images <= 0) return FO1_OK;
   return fpn_forward(m, tap, gh, gw, n_images, level_out, static_cast<cudaStream_t>(stream));
 }
+extern "C" int fo1_image_project(fo1_model* m, const void* feats, int32_t n, void* out, void* stream) {
+  FO1_CHECK_ARG(m && (n == 0 || (feats && out)), "fo1_image_project: null argument");
+  FO1_CHECK_ARG(m->cfg.proj_img_layers > 0, "fo1_image_project: mm_projector is the identity for this model (proj_img_layers = 0)");
+  return project(m, m->proj_img, static_cast<const bf16*>(feats), n, static_cast<bf16*>(out), static_cast<cudaStream_t>(stream));
+}
+
 extern "C" int fo1_region_project(fo1_model* m, const void* feats, int32_t n, void* out, void* stream) {
   FO1_CHECK_ARG(m && (n == 0 || (feats && out)), "fo1_region_project: null argument");
   return project(m, m->proj_aux, static_cast<const bf16*>(feats), n, static_cast<bf16*>(out), static_cast<cudaStream_t>(stream));

@@ -16,14 +16,19 @@ int arena_ensure(Model* m, size_t bytes) {
   return FO1_OK;
 }
 
+// Eviction happens ONLY here, at the entry of a forward (before its first lookup): callers hold the raw device pointers
+// of several tables across one forward, so freeing inside cached_ints() would hand a kernel a dangling table.
+int int_cache_trim(Model* m, size_t keep_below) {
+  if (m->int_cache.size() < keep_below) return FO1_OK;
+  FO1_CUDA(cudaDeviceSynchronize());   // tables of earlier forwards may still be read by kernels in flight
+  for (auto& kv : m->int_cache) cudaFree(kv.second.dev);
+  m->int_cache.clear();
+  return FO1_OK;
+}
+
 int cached_ints(Model* m, const std::string& key, const std::vector<int>& host, const int** dev, cudaStream_t s) {
   auto it = m->int_cache.find(key);
   if (it == m->int_cache.end()) {
-    if (m->int_cache.size() > 256) {  // bound the cache; tables are tiny but shapes may vary forever
-      FO1_CUDA(cudaDeviceSynchronize());
-      for (auto& kv : m->int_cache) cudaFree(kv.second.dev);
-      m->int_cache.clear();
-    }
     DeviceInts d;
     d.n = host.size();
     FO1_CUDA(cudaMalloc(reinterpret_cast<void**>(&d.dev), (host.size() + 1) * sizeof(int)));
@@ -39,6 +44,8 @@ int cached_ints(Model* m, const std::string& key, const std::vector<int>& host, 
 
 using namespace fo1;
 
+
+extern "C" int fo1_int_cache_entries(fo1_model* m) { return m ? (int)m->int_cache.size() : 0; }
 
 extern "C" int fo1_model_create(const fo1_model_config* cfg, fo1_model** out) {
   FO1_CHECK_ARG(cfg && out, "fo1_model_create: null argument");

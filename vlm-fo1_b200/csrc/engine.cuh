@@ -111,6 +111,7 @@ struct WeightGetter {
 };
 
 int arena_ensure(Model* m, size_t bytes);
+int int_cache_trim(Model* m, size_t keep_below = 192);   // call at the entry of a forward only
 int cached_ints(Model* m, const std::string& key, const std::vector<int>& host, const int** dev, cudaStream_t s);
 
 int vit_finalize(Model* m);

@@ -634,6 +634,30 @@ int make_tmap_2d_bf16(CUtensorMap* out, const void* ptr, uint64_t inner, uint64_
   return FO1_OK;
 }
 
+// 3-D bf16 tensor map (attention operands: (head_dim, head, row)), 128B swizzle; out-of-range elements read as zero.
+int make_tmap_3d_bf16(CUtensorMap* out, const void* ptr, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t stride1_bytes,
+                      uint64_t stride2_bytes, uint32_t b0, uint32_t b1, uint32_t b2) {
+  PFN_tmapEncodeTiled fn = get_encode_fn();
+  if (fn == nullptr) {
+    set_error("cuTensorMapEncodeTiled is not available from the driver");
+    return FO1_ERR_CUDA;
+  }
+  cuuint64_t dims[3] = {d0, d1, d2};
+  cuuint64_t strides[2] = {stride1_bytes, stride2_bytes};
+  cuuint32_t box[3] = {b0, b1, b2};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(3d) failed (%d): ptr=%p dims=%llu,%llu,%llu strides=%llu,%llu box=%u,%u,%u", (int)r, ptr,
+              (unsigned long long)d0, (unsigned long long)d1, (unsigned long long)d2, (unsigned long long)stride1_bytes,
+              (unsigned long long)stride2_bytes, b0, b1, b2);
+    return FO1_ERR_CUDA;
+  }
+  return FO1_OK;
+}
+
 int device_sm_count() {
   static int sms = 0;
   if (sms == 0) {

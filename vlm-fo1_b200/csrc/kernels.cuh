@@ -2,6 +2,8 @@
 #pragma once
 #include <cuda.h>
 
+#include <vector>
+
 #include "common.cuh"
 
 namespace fo1 {
@@ -37,19 +39,28 @@ int rope_apply(bf16* x, long long ld, const float* cos_sin, int T, int n_heads, 
 int rope_kv_append(bf16* qkv, long long ld, const float* cos_sin, int T, int q_heads, int kv_heads, int head_dim, const int* cache_len,
                    bf16* kc, bf16* vc, int cap, cudaStream_t s);
 
-// ---- attention.cu ----
-// varlen flash attention over packed rows; q/k/v may live in one packed buffer (pitches in elements)
+// ---- attention_tc.cu ----
+// varlen flash attention over packed rows (tcgen05 / TMEM / TMA); q/k/v may live in one packed buffer (pitches in elements)
 struct AttnArgs {
   const bf16* q; const bf16* k; const bf16* v; bf16* o;
   long long ldq, ldk, ldv, ldo;     // row pitches (elements)
   const int* cu_seqlens;            // [n_seqs + 1] token offsets (device); q and kv share them
+  const int* rowseg = nullptr;      // optional [total_rows][2] (lo, hi) table from attention_rowseg(); built per call when null
+  const int* tiles = nullptr;       // optional [n_tiles][2] (first row, rows <= 128) query-tile table from attention_tile_table(); null:
+  int n_tiles = 0;                  //   128-row tiles from row 0 (a sample's bits then depend on its offset in the batch)
   int n_seqs;
-  int max_seqlen;                   // longest segment (host knowledge, sizes the grid)
+  int total_rows;                   // cu_seqlens[n_seqs] (host knowledge: sizes the grid and the tensor maps)
+  int max_seqlen;                   // longest segment (informational)
   int q_heads, kv_heads, head_dim;
   float scale;
   int causal;
+  double flops = 0.0;               // algorithmic FLOPs of the call for the optional profiler (4 * sum len^2 * hd * heads, / 2 causal)
 };
 int attention_varlen(const AttnArgs& a, cudaStream_t s);
+// (lo, hi) key range of every packed row: callers that reuse one cu_seqlens for many layers build it once
+int attention_rowseg(const int* cu_seqlens, int n_seqs, int T, int* rowseg, cudaStream_t s);
+// host helper: 128-row query tiles that restart at every group boundary (image / prompt) -> flat (row0, rows) pairs
+void attention_tile_table(const std::vector<int>& group_cu, std::vector<int>& tiles);
 
 // ---- misc.cu ----
 int cast_gather_rows_f32_bf16(const float* src, long long lds, const int* row_idx, bf16* dst, long long ldd, int rows, int cols, cudaStream_t s);

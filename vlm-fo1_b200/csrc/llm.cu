@@ -434,7 +434,7 @@ static int ensure_state(Model* m, int B, int n_stop, DecodeState* st) {
 
 // one decoder layer over `rows` packed rows.  x_in -> x_out (x_mid scratch).  prefill: varlen causal attention
 // + cache fill; decode: cache append + single-query attention.
-struct LayerBuf { bf16 *xn, *qkv, *att, *x_mid, *h; float* dec_part; };
+struct LayerBuf { bf16 *xn, *qkv, *att, *x_mid, *h; float* dec_part; int* rowseg = nullptr; double attn_flops = 0.0; const int* tiles = nullptr; int n_tiles = 0; };
 
 static int llm_layer(Model* m, int li, const bf16* x_in, bf16* x_out, const LayerBuf& B_, int rows, const float* cs, bool prefill,
                      const int* d_cu, int n_seqs, int max_len, const int* d_row_seq, const int* d_row_t, const DecodeState* st,
@@ -457,7 +457,7 @@ static int llm_layer(Model* m, int li, const bf16* x_in, bf16* x_out, const Laye
     AttnArgs a;
     a.q = B_.qkv; a.k = B_.qkv + QD; a.v = B_.qkv + QD + KD; a.o = B_.att;
     a.ldq = a.ldk = a.ldv = ldq; a.ldo = QD;
-    a.cu_seqlens = d_cu; a.n_seqs = n_seqs; a.max_seqlen = max_len;
+    a.cu_seqlens = d_cu; a.n_seqs = n_seqs; a.max_seqlen = max_len; a.total_rows = rows; a.rowseg = B_.rowseg; a.flops = B_.attn_flops; a.tiles = B_.tiles; a.n_tiles = B_.n_tiles;
     a.q_heads = c.llm_heads; a.kv_heads = c.llm_kv_heads; a.head_dim = hd;
     a.scale = 1.0f / sqrtf((float)hd); a.causal = 1;
     FO1_RUN(attention_varlen(a, s));
@@ -495,6 +495,8 @@ static int llm_generate_impl(Model* m, fo1_generate_desc* d, cudaStream_t s, boo
   float* cs_pre = A.alloc<float>((size_t)R * hd);
   float* cs_dec = A.alloc<float>((size_t)B * hd);
   buf.dec_part = A.alloc<float>((size_t)B * c.llm_heads * kDecSplits * (128 + 4));
+  buf.rowseg = A.alloc<int>((size_t)R * 2);
+  for (int b = 0; b < B; ++b) buf.attn_flops += 2.0 * (double)d->seq_lens[b] * d->seq_lens[b] * QD;   // causal: half of 4 L^2 d
   bf16* last = A.alloc<bf16>((size_t)B * H);
   bf16* lastn = A.alloc<bf16>((size_t)B * H);
   float* logits = A.alloc<float>((size_t)B * V);
@@ -517,12 +519,17 @@ static int llm_generate_impl(Model* m, fo1_generate_desc* d, cudaStream_t s, boo
     FO1_TRY(cached_ints(m, key + ":rs", row_seq, &d_row_seq, s));
     FO1_TRY(cached_ints(m, key + ":rt", row_t, &d_row_t, s));
     FO1_TRY(cached_ints(m, key + ":last", lastrow, &d_last, s));
+    std::vector<int> tiles;
+    attention_tile_table(cu, tiles);        // query tiles restart at every prompt
+    FO1_TRY(cached_ints(m, key + ":til", tiles, &buf.tiles, s));
+    buf.n_tiles = (int)tiles.size() / 2;
     FO1_CUDA(cudaMemcpyAsync(d_lens, d->seq_lens, B * sizeof(int), cudaMemcpyHostToDevice, s));
     FO1_CUDA(cudaMemcpyAsync(d_deltas, d->rope_deltas, B * sizeof(int), cudaMemcpyHostToDevice, s));
     if (d->n_stop_ids > 0) FO1_CUDA(cudaMemcpyAsync(st.stop_ids, d->stop_ids, d->n_stop_ids * sizeof(int), cudaMemcpyHostToDevice, s));
   }
 
   // ---- prefill ----
+  FO1_RUN(attention_rowseg(d_cu, B, (int)T, buf.rowseg, s));
   const bf16* x = static_cast<const bf16*>(d->inputs_embeds);
   FO1_RUN(mrope_table(d->position_ids, cs_pre, (int)T, hd, c.mrope_section[0], c.mrope_section[1], c.mrope_section[2], c.rope_theta, s));
   for (int li = 0; li < c.llm_layers; ++li) {
@@ -630,6 +637,7 @@ int llm_generate(Model* m, fo1_generate_desc* d, cudaStream_t s) {
   DecodeState st;
   FO1_TRY(ensure_state(m, d->n_seqs, d->n_stop_ids, &st));
   FO1_TRY(ensure_kv(m, d->n_seqs, max_len + std::max(d->max_new_tokens, 1)));
+  FO1_TRY(int_cache_trim(m));
   m->arena.reset(true);
   FO1_TRY(llm_generate_impl(m, d, s, true, st));
   FO1_TRY(arena_ensure(m, m->arena.peak));

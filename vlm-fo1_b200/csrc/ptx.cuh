@@ -102,6 +102,36 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32])
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// 32 lanes x 32 consecutive fp32 columns, registers -> TMEM (the mirror of tmem_ld_32x32)
+__device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+        "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+        "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+        "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// generic-proxy shared-memory writes (st.shared) -> visible to the async proxy (tcgen05.mma / TMA reads)
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// MN-major, 128-byte-swizzled operand (e.g. V[key][dim] used as the B operand of P.V: N = dim is the contiguous
+// direction): rows of 128 B = 64 MN-elements of one K index, 8-row (8 K indices) groups SBO = 1024 B apart; a single
+// 64-element atom along MN, so the leading byte offset is not used (cute::UMMA::make_umma_desc<Major::MN>).
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)(8192 >> 4) << 16;                    // LBO: next 64-element atom along MN (unused: N <= 64)
+  d |= (uint64_t)(1024 >> 4) << 32;                    // SBO: next group of 8 K indices
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;                              // SWIZZLE_128B
+  return d;
+}
+constexpr uint32_t kUmmaBMajorMN = 1u << 16;           // instruction-descriptor bit: B operand is MN-major
+
 // K-major, 128-byte-swizzled shared-memory operand descriptor (UMMA SmemDescriptor, sm_100 version 1):
 // rows of 128 B, 8-row swizzle atoms 1024 B apart (SBO), LBO unused for a single K atom.
 __device__ __forceinline__ uint64_t umma_desc_k_sw128(uint32_t smem_addr) {

@@ -99,8 +99,10 @@ static int vit_forward_impl(Model* m, const float* const* pixel_values, const in
     key += ":" + std::to_string(grid_hw[2 * b]) + "x" + std::to_string(grid_hw[2 * b + 1]);
   }
   const int Tm = (int)(T / unit);
-  const int *d_src_row = nullptr, *d_pos = nullptr, *d_cu_win = nullptr, *d_cu_full = nullptr, *d_pix = nullptr, *d_unperm = nullptr;
+  const int *d_src_row = nullptr, *d_pos = nullptr, *d_cu_win = nullptr, *d_cu_full = nullptr, *d_pix = nullptr, *d_unperm = nullptr, *d_tiles = nullptr;
+  int n_tiles = 0;
   int n_win = 0, max_win = 0, max_full = 0;
+  double flops_win = 0.0, flops_full = 0.0;   // 4 * sum len^2 * hidden
   {
     std::vector<int> src_row, pos, cu_win(1, 0), cu_full(1, 0), pix, unperm;
     int tok_off = 0, cell_off = 0;
@@ -116,13 +118,20 @@ static int vit_forward_impl(Model* m, const float* const* pixel_values, const in
         pos.push_back(ph[2 * t]); pos.push_back(ph[2 * t + 1]);
         pix.push_back(tok_off + ph[2 * t] * gw + ph[2 * t + 1]);
       }
-      for (size_t i = 1; i < cw.size(); ++i) { cu_win.push_back(tok_off + cw[i]); max_win = std::max(max_win, cw[i] - cw[i - 1]); }
+      for (size_t i = 1; i < cw.size(); ++i) {
+        cu_win.push_back(tok_off + cw[i]); max_win = std::max(max_win, cw[i] - cw[i - 1]);
+        flops_win += 4.0 * (double)(cw[i] - cw[i - 1]) * (cw[i] - cw[i - 1]) * H;
+      }
+      flops_full += 4.0 * (double)gh * gw * gh * gw * H;
       tok_off += gh * gw;
       cell_off += gh * gw / unit;
       cu_full.push_back(tok_off);
       max_full = std::max(max_full, gh * gw);
     }
     n_win = (int)cu_win.size() - 1;
+    std::vector<int> tiles;
+    attention_tile_table(cu_full, tiles);   // query tiles restart at every image: an image's bits do not depend on its batch slot
+    n_tiles = (int)tiles.size() / 2;
     if (!dry) {
       FO1_TRY(cached_ints(m, key + ":src", src_row, &d_src_row, s));
       FO1_TRY(cached_ints(m, key + ":pos", pos, &d_pos, s));
@@ -130,6 +139,7 @@ static int vit_forward_impl(Model* m, const float* const* pixel_values, const in
       FO1_TRY(cached_ints(m, key + ":cuf", cu_full, &d_cu_full, s));
       FO1_TRY(cached_ints(m, key + ":pix", pix, &d_pix, s));
       FO1_TRY(cached_ints(m, key + ":unp", unperm, &d_unperm, s));
+      FO1_TRY(cached_ints(m, key + ":til", tiles, &d_tiles, s));
     }
   }
 
@@ -144,6 +154,8 @@ static int vit_forward_impl(Model* m, const float* const* pixel_values, const in
   float* cs = A.alloc<float>((size_t)T * hd);
   bf16* mg = A.alloc<bf16>((size_t)Tm * H * unit);
   bf16* mo = A.alloc<bf16>((size_t)Tm * c.vit_out_hidden);
+  int* rs_win = A.alloc<int>((size_t)T * 2);
+  int* rs_full = A.alloc<int>((size_t)T * 2);
 
   // ---- patch embed: cast + window-order gather, then GEMM (Conv3d with stride == kernel is a GEMM, :88-111) ----
   {
@@ -156,6 +168,9 @@ static int vit_forward_impl(Model* m, const float* const* pixel_values, const in
   }
   FO1_RUN(linear(px, pk, w.patch_w, pk, x, H, FO1_BF16, (int)T, H, pk, nullptr, 0, FO1_EPI_NONE, nullptr, 0, 0, s));
   FO1_RUN(vit_rope_table(d_pos, cs, (int)T, hd, 10000.0f, s));
+  // key range of every packed row for the two segmentations (windows / whole images): built once, read by every layer
+  FO1_RUN(attention_rowseg(d_cu_win, n_win, (int)T, rs_win, s));
+  FO1_RUN(attention_rowseg(d_cu_full, B, (int)T, rs_full, s));
 
   int tap_i = 0;
   for (int L = 0; L < c.vit_depth; ++L) {
@@ -171,6 +186,10 @@ static int vit_forward_impl(Model* m, const float* const* pixel_values, const in
     a.cu_seqlens = full ? d_cu_full : d_cu_win;
     a.n_seqs = full ? B : n_win;
     a.max_seqlen = full ? max_full : max_win;
+    a.total_rows = (int)T;
+    a.rowseg = full ? rs_full : rs_win;
+    a.tiles = d_tiles; a.n_tiles = n_tiles;
+    a.flops = full ? flops_full : flops_win;
     a.q_heads = a.kv_heads = heads; a.head_dim = hd;
     a.scale = 1.0f / sqrtf((float)hd);
     a.causal = 0;
@@ -206,6 +225,7 @@ int vit_forward(Model* m, const float* const* pixel_values, const int32_t* grid_
     FO1_CHECK_ARG(gh > 0 && gw > 0 && gh % c.vit_merge == 0 && gw % c.vit_merge == 0, "image %d: grid %dx%d not a multiple of merge %d", b, gh, gw, c.vit_merge);
     FO1_CHECK_ARG(pixel_values[b] != nullptr, "image %d: null pixel_values", b);
   }
+  FO1_TRY(int_cache_trim(m));
   m->arena.reset(true);
   FO1_TRY(vit_forward_impl(m, pixel_values, grid_hw, B, nullptr, nullptr, s, true));
   FO1_TRY(arena_ensure(m, m->arena.peak));

@@ -104,7 +104,7 @@ class Engine:
         L.fo1_model_set_weight.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_int64)]
         L.fo1_model_finalize.restype = C.c_int
         L.fo1_model_finalize.argtypes = [C.c_void_p]
-        for fn in ("fo1_vit_forward", "fo1_davit_forward", "fo1_fpn_forward", "fo1_region_project"):
+        for fn in ("fo1_vit_forward", "fo1_davit_forward", "fo1_fpn_forward", "fo1_region_project", "fo1_image_project"):
             getattr(L, fn).restype = C.c_int
         check(L.fo1_model_create(C.byref(self._c), C.byref(self._h)), "fo1_model_create")
         self.weights: Dict[str, torch.Tensor] = {}
@@ -173,6 +173,16 @@ class Engine:
         op = (C.c_void_p * 4)(*[o.data_ptr() for o in outs])
         check(lib().fo1_fpn_forward(self._h, C.c_void_p(tap.data_ptr()), gh, gw, B, op, _stream()), "fo1_fpn_forward")
         return outs
+
+    def image_project(self, feats: torch.Tensor) -> torch.Tensor:
+        """mm_projector on the merged image tokens (encode_images, omchat_qwen2_5_vl.py:58-66); identity when proj_img_layers == 0."""
+        if self.cfg.proj_img_layers == 0:
+            return feats
+        feats = feats.contiguous()
+        out = torch.empty((feats.shape[0], self.cfg.llm["hidden_size"]), dtype=torch.bfloat16, device=self.device)
+        check(lib().fo1_image_project(self._h, C.c_void_p(feats.data_ptr()), feats.shape[0], C.c_void_p(out.data_ptr()), _stream()),
+              "fo1_image_project")
+        return out
 
     def region_project(self, feats: torch.Tensor) -> torch.Tensor:
         feats = feats.contiguous()

@@ -86,6 +86,7 @@ def attention_varlen(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, cu_seqle
     d.n_seqs, d.max_seqlen = cu_seqlens.numel() - 1, max_seqlen
     d.q_heads, d.kv_heads, d.head_dim = q_heads, kv_heads, head_dim
     d.scale, d.causal = scale, 1 if causal else 0
+    d.total_rows = T
     check(lib().fo1_attention_varlen(C.byref(d), C.c_void_p(_stream())), "fo1_attention_varlen")
     return out
 

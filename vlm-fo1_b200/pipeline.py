@@ -29,11 +29,11 @@ class SampleInputs:
 
 class Fo1Pipeline:
     def __init__(self, engine: Engine, vt_mode: str = "fpn", image_token_id: int = 151655, vision_start_token_id: int = 151652,
-                 video_token_id: int = 151656):
+                 video_token_id: int = 151656, roi_size: int = 7, apply_pos_embed: bool = True):
         self.eng = engine
         self.vt_mode = vt_mode
         self.ids = dict(image_token_id=image_token_id, vision_start_token_id=vision_start_token_id, video_token_id=video_token_id)
-        self.hcfg = HF.HfreConfig(region_dim=engine.cfg.region_dim, vt_mode=vt_mode)
+        self.hcfg = HF.HfreConfig(region_dim=engine.cfg.region_dim, vt_mode=vt_mode, roi_size=roi_size, apply_pos_embed=apply_pos_embed)
         self.ws = HF.HfreWorkspace()
         self.profile_stages = False          # when set, CUDA events bracket every stage (read with stage_ms())
         self._marks = []
@@ -61,6 +61,7 @@ class Fo1Pipeline:
         self._marks = []
         self._mark("start")
         feats, taps = eng.vit_forward([s.pixel_values for s in samples], grids)
+        feats = eng.image_project(feats)                                             # mm_projector (:58-66); identity for the released checkpoint
         self._mark("vit")
         B = len(samples)
         H0, W0 = samples[0].image_aux.shape[-2:]

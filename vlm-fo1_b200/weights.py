@@ -138,7 +138,12 @@ def prepare_projector(sd: Dict[str, torch.Tensor], prefix: str, device) -> Dict[
 def prepare_llm(sd: Dict[str, torch.Tensor], cfg: dict, device) -> Dict[str, torch.Tensor]:
     """sd keys: 'embed_tokens.weight', 'layers.N.*', 'norm.weight', 'lm_head.weight' (optional when tied)."""
     out = {"llm.embed": _dev(sd["embed_tokens.weight"], device), "llm.norm.w": _dev(sd["norm.weight"], device)}
-    out["llm.lm_head"] = _dev(sd["lm_head.weight"], device) if "lm_head.weight" in sd else out["llm.embed"]
+    if "lm_head.weight" in sd:
+        out["llm.lm_head"] = _dev(sd["lm_head.weight"], device)
+    elif cfg.get("tie_word_embeddings", False):
+        out["llm.lm_head"] = out["llm.embed"]                     # tied head (configuration_qwen2_5_vl.py: tie_word_embeddings)
+    else:
+        raise KeyError("lm_head.weight is missing and tie_word_embeddings is false: refusing to decode with the embedding table")
     for i in range(cfg["num_hidden_layers"]):
         s, d = f"layers.{i}.", f"llm.l{i}."
         out[d + "ln1.w"] = _dev(sd[s + "input_layernorm.weight"], device)

@@ -55,6 +55,23 @@ def load_pretrained_model(model_path, load_8bit=False, load_4bit=False, device="
     if not g("mm_use_vision_tower_region_feature", False):
         raise ValueError("mm_use_vision_tower_region_feature=False is a dead configuration in the reference "
                          "(hybrid_finegrained_region_encoder.py:456 raises); not supported")
+    # ---- the HFRE variant flags the reference reads in omchat_arch.py:17-31: honoured or refused, never ignored ----
+    roi_size = int(g("mm_roi_output_size", 7))
+    apply_pos = bool(g("mm_apply_position_embedding", True))
+    pos_strategy = str(g("mm_pos_embedding_strategy", "bbox_based"))
+    combination = str(g("mm_region_feature_combination", "concat"))
+    unsupported = []
+    if roi_size < 1 or roi_size > 16:
+        unsupported.append(f"mm_roi_output_size={roi_size}")
+    if apply_pos and pos_strategy != "bbox_based":
+        unsupported.append(f"mm_pos_embedding_strategy={pos_strategy!r} (only 'bbox_based', hybrid_finegrained_region_encoder.py:436-467)")
+    if combination != "concat":
+        unsupported.append(f"mm_region_feature_combination={combination!r} (the mean / *_sep_pos paths hard-code ConvNeXt widths, :384-432)")
+    for flag in ("mm_use_vt_region_feature_only", "mm_apply_region_layer_norm", "mm_use_separate_mlp_for_regions"):
+        if g(flag, False):
+            unsupported.append(f"{flag}=True")
+    if unsupported:
+        raise ValueError("checkpoint flags not supported by the fo1-b200 engine: " + "; ".join(unsupported))
     cfg = E.EngineConfig()
     cfg.vit = dict(depth=vc["depth"], hidden_size=vc["hidden_size"], num_heads=vc["num_heads"], intermediate_size=vc["intermediate_size"],
                    out_hidden_size=vc["out_hidden_size"], patch_size=vc.get("patch_size", 14), spatial_merge_size=vc.get("spatial_merge_size", 2),
@@ -102,7 +119,7 @@ def load_pretrained_model(model_path, load_8bit=False, load_4bit=False, device="
     gen_path = os.path.join(model_path, "generation_config.json")
     eos = json.load(open(gen_path)).get("eos_token_id", []) if os.path.exists(gen_path) else g("eos_token_id", [])
     stop_ids = [int(e) for e in (eos if isinstance(eos, list) else [eos]) if e is not None]
-    model = Fo1ForCausalLM(engine, config, "fpn" if use_fpn else "concat", stop_ids)
+    model = Fo1ForCausalLM(engine, config, "fpn" if use_fpn else "concat", stop_ids, roi_size=roi_size, apply_pos_embed=apply_pos)
     primary = PrimaryImageProcessor(cfg.vit["patch_size"], cfg.vit["spatial_merge_size"], cfg.vit["temporal_patch_size"], 56 * 56, 2048 * 2048)
     aux = AuxImageProcessor(int(g("aux_image_size", 768)), str(g("aux_image_aspect_ratio", "squash")))
     return tokenizer, model, (primary, aux)

@@ -12,12 +12,13 @@ import torch
 
 
 class Fo1ForCausalLM:
-    def __init__(self, engine, config: SimpleNamespace, vt_mode: str, stop_ids: List[int]):
+    def __init__(self, engine, config: SimpleNamespace, vt_mode: str, stop_ids: List[int], roi_size: int = 7, apply_pos_embed: bool = True):
         P = import_module("vlm-fo1_b200.pipeline")
         self.engine = engine
         self.config = config
         self.pipeline = P.Fo1Pipeline(engine, vt_mode=vt_mode, image_token_id=config.image_token_id,
-                                      vision_start_token_id=config.vision_start_token_id, video_token_id=config.video_token_id)
+                                      vision_start_token_id=config.vision_start_token_id, video_token_id=config.video_token_id,
+                                      roi_size=roi_size, apply_pos_embed=apply_pos_embed)
         self._P = P
         self.default_stop_ids = list(stop_ids)
         self.device = engine.device
@@ -54,16 +55,20 @@ class Fo1ForCausalLM:
             for kw in getattr(crit, "keyword_ids", []):
                 if kw.numel() == 1:                      # single-token keywords are tested on the device
                     stop.append(int(kw.item()))
+                else:
+                    # the reference matches the decoded text (mm_utils.py:158-181); a multi-token keyword cannot be tested by
+                    # the device-side stop list, and silently ignoring it would change where generation ends
+                    raise NotImplementedError(f"multi-token stop keyword {kw.tolist()} is not supported by the device-side stop test "
+                                              "(every caller in the reference stops on the single token <|im_end|>)")
         pad = pad_token_id if pad_token_id is not None else (stop[0] if stop else 0)
         out = self.pipeline.generate([sample], int(max_new_tokens), sorted(set(stop)), pad_id=int(pad), early_exit_interval=8)
         n = int(out["lens"][0].item())
         new = out["tokens"][0, :n].to(torch.long)
         full = torch.cat([inputs[0].to(new.device), new]).unsqueeze(0)
         if streamer is not None:
-            try:
-                streamer.put(inputs.cpu())
-                streamer.put(new.cpu())
-                streamer.end()
-            except Exception:
-                pass
+            # the whole completion is handed over at once (the decode loop is device-resident: no per-token host sync);
+            # a streamer error is the caller's to see, as in HF's generate
+            streamer.put(inputs.cpu())
+            streamer.put(new.cpu())
+            streamer.end()
         return full

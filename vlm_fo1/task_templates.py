@@ -1,28 +1,21 @@
-"""The nine task prompts -- the model's trained text interface, so the VALUES are fixed (reference:
-vlm_fo1/task_templates.py:1-17, including its spelling ``Viusal_Region_Reasoning_template`` and the doubled word in that
-prompt).  They are assembled from their shared phrases and pinned against the reference's module by
-tests/test_boundary_prompt_data.py."""
-from .constants import DEFAULT_THINK_END, DEFAULT_THINK_START
+"""The nine task prompts -- the model's trained text interface, so the values are fixed (reference:
+vlm_fo1/task_templates.py:1-17, including its spelling ``Viusal_Region_Reasoning_template``).  Pinned against the
+reference's module by tests/test_boundary_prompt_data.py."""
 
-_IN_IMAGE = "in this image"
-_WITH_INDEXES = "with object indexes"
-_ANSWER_INDEXED = f"Answer the question {_WITH_INDEXES}."
+Brief_Region_Caption_template = "Provide a brief description for {}."
 
-_detect = f"Please detect {{}} {_IN_IMAGE}. {_ANSWER_INDEXED}"
-OD_template = _detect
-REC_template = _detect
-OD_Counting_template = (f"How many {{}} are there {_IN_IMAGE}? Count each instance of the target object. "
-                        f"Locate them {_WITH_INDEXES} and then answer the question with the number of objects.")
-Region_OCR_template = "Please provide the ocr results of {} in the image."
-Brief_Region_Caption_template, Detailed_Region_Caption_template = (f"Provide a {kind} description for {{}}." for kind in ("brief", "detailed"))
+Detailed_Region_Caption_template = "Provide a detailed description for {}."
+
 Grounding_template = "Briefly describe this image and detect all mentioned objects. Answer with grounded object indexes."
-Visual_Prompt_OD_template = (f"Using the provided object {{}} as a reference, identify all other objects of the same category "
-                             f"{_IN_IMAGE}. Respond {_WITH_INDEXES}.")
-_RP, _ANS = "reasoning process", "answer"
-_tags = f"{DEFAULT_THINK_START} {DEFAULT_THINK_END} and <{_ANS}> </{_ANS}>"
-_example = f"{DEFAULT_THINK_START} {_RP} here {DEFAULT_THINK_END}<{_ANS}> {_ANS} here </{_ANS}>"
-Viusal_Region_Reasoning_template = " ".join([
-    f"First thinks about the {_RP} in the mind and then provides the user with the {_ANS}.",
-    f"The {_RP} and {_ANS} are enclosed within {_tags} tags, respectively, i.e., {_example}.",
-    f"Please give a detailed {_RP} process and provide image regions that can help you {_ANS} the question better.",
-    "{}"])
+
+OD_Counting_template = "How many {} are there in this image? Count each instance of the target object. Locate them with object indexes and then answer the question with the number of objects."
+
+OD_template = "Please detect {} in this image. Answer the question with object indexes."
+
+REC_template = "Please detect {} in this image. Answer the question with object indexes."
+
+Region_OCR_template = "Please provide the ocr results of {} in the image."
+
+Visual_Prompt_OD_template = "Using the provided object {} as a reference, identify all other objects of the same category in this image. Respond with object indexes."
+
+Viusal_Region_Reasoning_template = "First thinks about the reasoning process in the mind and then provides the user with the answer. The reasoning process and answer are enclosed within <think> </think> and <answer> </answer> tags, respectively, i.e., <think> reasoning process here </think><answer> answer here </answer>. Please give a detailed reasoning process process and provide image regions that can help you answer the question better. {}"

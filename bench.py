@@ -7,14 +7,22 @@ HFRE region tokens -> projector -> splice -> Qwen2.5-3B prefill -> 64-token gree
 fixed), one NCCL all-gather of the decoded ids per step.  A "step" is one pass of that pipeline over one batch.
 
   value : images/sec, inputs already resident in HBM, CUDA-event timed, max over ranks.
-  e2e   : the same through the public pipeline API from pinned HOST buffers (H2D of pixel rows / aux images /
-          boxes and D2H of the token ids inside the timed region).
+  e2e   : the same through the public pipeline API from pinned HOST buffers: H2D of the raw uint8 images and the boxes,
+          device-side pre-processing (bicubic smart-resize, normalise, patchify for both towers) and D2H of the token ids,
+          all inside the timed region.
   roofline     : the dominant kernel (tcgen05 GEMM) -- algorithmic FLOPs / CUDA-event launch time (one extra
                  instrumented step after the timed region) vs the measured cuBLAS bf16 sustained peak.
   roofline_hfre: HFRE gather -- SURVEY 8d algorithmic bytes / launch time vs the measured HBM copy bandwidth.
-  cpu_baseline : the CPU oracle port of the same path (oracle/pipeline.py) timed on the host cores on ONE image.
-``--impl reference`` times only that CPU arm (the reference's PyTorch path restated; the original modules cannot
-travel to the GPU box)."""
+  roofline_decode: one decode step -- bytes it must stream (bf16 weights + the live K/V) / its device time vs HBM.
+  cpu_baseline : the reference's OWN modules (oracle/reference_path.py over the copy in baseline/_ref/, ``kind: "reference"``)
+                 timed on the host cores on ONE full-depth image with a shortened decode (stated in ``sample``); the oracle
+                 port (``kind: "port"``) only if that copy is absent.
+``--impl reference`` times that CPU arm alone: one full-depth image per step, all decode tokens, every host thread.
+
+Workloads (``--workload``): c3 (default, the headline configuration), c4 (COCO shape: 640 px -> 46x46 grid, 100 boxes,
+16 images / GPU), c5 (counting: 1344 px, 300 boxes, 128 tokens, 8 images / GPU), c2 (HFRE-only: towers + region tokens of
+8 x 896 px x 100 boxes; value = GB/s of the HFRE operator).  ``--global-batch G`` fixes the TOTAL batch and splits it over
+the ranks (strong scaling) instead of the per-GPU batch (weak scaling)."""
 import argparse
 import json
 import os
@@ -32,6 +40,12 @@ sys.path.insert(0, REPO)
 
 METRIC = "images/sec (prefill+64-tok decode) 3B FO1"
 UNIT = "images/s"
+WORKLOADS = {   # BASELINE.json configs[1..4] (SURVEY.md section 8d "Config -> concrete workload"); batch = images per GPU
+    "c3": dict(batch=32, size=896, boxes=64, tokens=64, name="configs[2] full prefill + 64-token decode"),
+    "c4": dict(batch=16, size=640, boxes=100, tokens=64, name="configs[3] COCO-shape detection template (640 -> 644 px, grid 46x46)"),
+    "c5": dict(batch=8, size=1344, boxes=300, tokens=128, name="configs[4] counting template (1344 px, 300 boxes, 128-token decode)"),
+    "c2": dict(batch=8, size=896, boxes=100, tokens=0, name="configs[1] HFRE-only: dual-ViT forward + region-token extraction"),
+}
 
 
 def load_peaks():
@@ -91,66 +105,79 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-CPU_SAMPLE_NOTE = ("1 image at full resolution through oracle/pipeline.py (fp32, all host threads) on a REDUCED-DEPTH copy of the model with "
-                   "the real layer widths: ViT 1 windowed + 1 full-attention block, DaViT 1 block per stage, LLM 2 layers, {tok} decode steps; "
-                   "per-block / per-layer wall times are measured and extrapolated to the real depths (ViT 28+4 blocks, DaViT 1/1/9/1, LLM 36 "
-                   "layers, {T}-token decode); patch-embed, merger, conv-embeds, FPN, HFRE, projector and lm_head are measured at full size")
-
-
-def reduced_cfg(E, cfg):
-    """Same widths, minimal depth: what the CPU arm actually executes."""
-    r = E.EngineConfig()
-    r.vit = dict(cfg.vit, depth=2, fullatt_block_indexes=[1])
-    r.davit = dict(cfg.davit, depths=[1, 1, 1, 1])
-    r.llm = dict(cfg.llm, num_hidden_layers=2)
-    r.fpn_out, r.region_dim, r.proj_aux_layers = cfg.fpn_out, cfg.region_dim, cfg.proj_aux_layers
-    return r
-
-
-def cpu_arm(args, CK, E, cfg, steps):
-    """Time the CPU oracle port.  Bounded sample (CPU_SAMPLE_NOTE): returns (images/s, stage seconds, per-step seconds)."""
+def reference_arm(args, cfg, steps, decode_tokens):
+    """The CPU arm: ONE full-depth image per step through the reference's own modules (oracle/reference_path.py; the oracle
+    port if baseline/_ref is absent), fp32, every host thread.  ``decode_tokens`` < args.tokens shortens the greedy loop; the
+    remaining steps are then added at the measured per-token cost (stated in the returned note).
+    Returns (images/s, kind, cores, note, stage seconds of the last step)."""
     from importlib import import_module
-    from oracle import pipeline as OP
     SY = import_module("vlm-fo1_b200.synthetic")
-    # thread count: all host cores unless a quick matmul calibration shows fewer threads are faster (oversubscribed or
-    # shared hosts make 128-thread GEMVs pathologically slow); the count used is reported as `cores`
-    best_t, best_s = os.cpu_count() or 1, None
-    a = torch.randn(1195, 2048); w = torch.randn(11008, 2048); v = torch.randn(1, 2048)
-    for nt in sorted({os.cpu_count() or 1, 64, 32, 16}, reverse=True):
-        if nt > (os.cpu_count() or 1):
-            continue
-        torch.set_num_threads(nt)
-        t0 = time.perf_counter()
-        for _ in range(2):
-            (a @ w.t()); [(v @ w.t()) for _ in range(8)]
-        dt = time.perf_counter() - t0
-        if best_s is None or dt < best_s:
-            best_t, best_s = nt, dt
-    torch.set_num_threads(best_t)
-    rc = reduced_cfg(E, cfg)
-    sds = CK.random_state_dicts(rc, "cpu", 0)
-    sds = {k: {n: t.float() for n, t in v.items()} for k, v in sds.items()}
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
     s = SY.synthetic_batch(0, 1, args.size, args.boxes)[0]
+    T = max(args.tokens, 1)
+    dt = max(1, min(decode_tokens, T))
+    from oracle import reference_path as RP
     times, detail = [], None
-    for _ in range(steps):
-        with torch.no_grad():
-            out = OP.run_sample(sds, rc.vit, rc.davit, rc.llm, input_ids=s.input_ids, pixel_values=s.pixel_values, grid_hw=s.grid_hw,
-                                image_aux=s.image_aux, boxes=s.boxes, region_dim=cfg.region_dim, max_new_tokens=args.cpu_tokens)
-        t = out["timings"]
-        vd, dd = t["vit_detail"], t["davit_detail"]
-        t_win = statistics.mean(x for f, x in vd["blocks"] if not f)
-        t_full = statistics.mean(x for f, x in vd["blocks"] if f)
-        n_full = len(cfg.vit["fullatt_block_indexes"])
-        vit = vd["embed_s"] + vd["merger_s"] + (cfg.vit["depth"] - n_full) * t_win + n_full * t_full
-        davit = sum(dd["embed_s"]) + sum(cfg.davit["depths"][i] * statistics.mean(dd["block_s"][i]) for i in range(4))
-        L = cfg.llm["num_hidden_layers"]
-        prefill = L * statistics.mean(t["llm_prefill_layer_s"]) + t["llm_head_s"]
-        per_tok = L * statistics.mean(t["llm_decode_layer_s"]) + t["llm_head_s"]
-        total = vit + davit + t["fpn_s"] + t["hfre_s"] + t["proj_s"] + prefill + (args.tokens - 1) * per_tok
-        times.append(total)
-        detail = {"vit_s": vit, "davit_s": davit, "fpn_s": t["fpn_s"], "hfre_s": t["hfre_s"], "proj_s": t["proj_s"], "llm_prefill_s": prefill,
-                  "llm_decode_s_per_token": per_tok, "vit_block_windowed_s": t_win, "vit_block_full_s": t_full}
-    return 1.0 / statistics.mean(times), detail, times
+    if RP.available():
+        kind = "reference"
+        rp = RP.ReferencePath(cfg.vit, "davit-large", cfg.llm, region_dim=cfg.region_dim, davit_depths=cfg.davit["depths"])
+        for _ in range(steps):
+            out = rp.run(input_ids=s.input_ids, pixel_values=s.pixel_values, grid_hw=s.grid_hw, image_aux=s.image_aux, boxes=s.boxes,
+                         max_new_tokens=dt)
+            t = dict(out["timings"])
+            per_tok = t["llm_decode_s"] / max(dt - 1, 1)
+            total = t["total_s"] + (T - dt) * per_tok
+            t["llm_decode_s_per_token"] = per_tok
+            times.append(total); detail = t
+        what = ("the reference's own modules (baseline/_ref copy of vlm_fo1: Qwen2_5_VisionTransformerPretrainedModel + custom_forward + "
+                f"GATHER, DaViT, HFREModule incl. SimpleFP, mm_projector_aux, {cfg.llm['num_hidden_layers']} x Qwen2_5_VLDecoderLayer; "
+                f"attention '{rp.attn}'), model loop / splice / greedy loop restated")
+    else:
+        kind = "port"
+        CK = import_module("vlm-fo1_b200.checkpoint")
+        from oracle import pipeline as OP
+        sds = CK.random_state_dicts(cfg, "cpu", 0)
+        sds = {k: {n: v.float() for n, v in d.items()} for k, d in sds.items()}
+        for _ in range(steps):
+            with torch.no_grad():
+                out = OP.run_sample(sds, cfg.vit, cfg.davit, cfg.llm, input_ids=s.input_ids, pixel_values=s.pixel_values, grid_hw=s.grid_hw,
+                                    image_aux=s.image_aux, boxes=s.boxes, region_dim=cfg.region_dim, max_new_tokens=dt)
+            t = {k: v for k, v in out["timings"].items() if isinstance(v, float)}
+            per_tok = t.get("llm_decode_s_per_token", 0.0)
+            total = t["vit_s"] + t["davit_s"] + t["fpn_s"] + t["hfre_s"] + t["proj_s"] + t["llm_prefill_s"] + (T - 1) * per_tok
+            times.append(total); detail = t
+        what = "oracle/pipeline.py (the CPU restatement of the reference; baseline/_ref is absent on this machine)"
+    note = (f"1 image per step, {args.size}x{args.size}, {args.boxes} boxes, FULL depth (ViT {cfg.vit['depth']} blocks, DaViT "
+            f"{cfg.davit['depths']}, LLM {cfg.llm['num_hidden_layers']} layers), fp32, {cores} host threads, through {what}; "
+            + (f"all {T} decode tokens executed" if dt >= T else
+               f"{dt} of {T} decode tokens executed, the remaining {T - dt} added at the measured per-token time (extrapolated term: "
+               f"{(T - dt) * detail.get('llm_decode_s_per_token', 0.0):.1f} s of {statistics.mean(times):.1f} s)"))
+    return 1.0 / statistics.mean(times), kind, cores, note, detail
+
+
+def hfre_algorithmic_bytes(HF, cfg, host, size):
+    """SURVEY.md section 8d unique bytes of the HFRE stage for these samples (host-side rasterisation of the boxes)."""
+    tot = 0
+    for s in host:
+        H0 = s.image_aux.shape[-1] // 4
+        gh, gw = s.grid_hw
+        Sa = s.image_aux.shape[-1]
+        shapes = [(Sa // (4 << i), Sa // (4 << i), c) for i, c in enumerate(cfg.davit["dim_embed"])] + \
+                 [(int(gh * f), int(gw * f), cfg.fpn_out) for f in (4, 2, 1, 0.5)]
+        sc = gh * 14 / Sa
+        bl = [s.boxes.numpy()] * 4 + [s.boxes.numpy() * sc] * 4
+        scales = [0.25] * 4 + [1 / x for x in HF.FPN_STRIDES]
+        ups = [H0 // sh[0] for sh in shapes[:4]] + [1] * 4
+        tot += HF.algorithmic_bytes(shapes, bl, scales, ups, s.boxes.shape[0], cfg.region_dim)["unique_bytes"]
+    return tot
+
+
+def load_traffic():
+    """DRAM bytes per launch of the roofline kernels from the committed ncu capture of this round (profiles/): the bench
+    cannot run under ncu, so `traffic` is read from the capture of the same command."""
+    p = os.path.join(REPO, "profiles", "r02_traffic.json")
+    return json.load(open(p)) if os.path.exists(p) else {}
 
 
 def main():
@@ -160,48 +187,65 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="fo1", choices=["fo1", "reference"])
-    ap.add_argument("--batch", type=int, default=32, help="images per GPU")
-    ap.add_argument("--size", type=int, default=896)
-    ap.add_argument("--boxes", type=int, default=64)
-    ap.add_argument("--tokens", type=int, default=64)
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--batch", type=int, default=None, help="images per GPU (default: the workload's)")
+    ap.add_argument("--global-batch", type=int, default=None, help="TOTAL images, split over the ranks (strong scaling)")
+    ap.add_argument("--size", type=int, default=None)
+    ap.add_argument("--boxes", type=int, default=None)
+    ap.add_argument("--tokens", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-tokens", type=int, default=3, help="decode steps the CPU arm actually runs (rest extrapolated)")
+    ap.add_argument("--cpu-tokens", type=int, default=8, help="decode steps the in-run cpu_baseline executes (rest at the measured per-token time)")
     ap.add_argument("--profile-run", action="store_true", help="warm-up exactly as given, one timed pass, nothing else (for ncu)")
     ap.add_argument("--small", action="store_true", help="tiny architecture (plumbing check only; NOT a valid bench number)")
     args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    for k in ("batch", "size", "boxes", "tokens"):
+        if getattr(args, k) is None:
+            setattr(args, k, wl[k])
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     from importlib import import_module
     import fo1_b200  # noqa: F401
-    E = import_module("vlm-fo1_b200.engine"); CK = import_module("vlm-fo1_b200.checkpoint")
+    E = import_module("vlm-fo1_b200.engine"); CK = import_module("vlm-fo1_b200.checkpoint"); DP = import_module("vlm-fo1_b200.dp")
     P = import_module("vlm-fo1_b200.pipeline"); SY = import_module("vlm-fo1_b200.synthetic"); HF = import_module("vlm-fo1_b200.hfre")
     cfg = E.EngineConfig()
     if args.small:
         cfg.vit = dict(cfg.vit, depth=4, fullatt_block_indexes=[1, 3])
         cfg.davit = dict(cfg.davit, depths=[1, 1, 1, 1])
         cfg.llm = dict(cfg.llm, num_hidden_layers=2)
-    config = {"workload": f"full prefill + {args.tokens}-token decode: batch {args.batch}/GPU, {args.size}x{args.size}, {args.boxes} boxes/img, "
-                          f"random-init 3B FO1 (variant B: SimpleFPN, D=5888, mlp2x_gelu projector)",
-              "global_batch": args.batch * world, "per_gpu_batch": args.batch, "image_size": args.size, "boxes_per_image": args.boxes,
-              "decode_tokens": args.tokens, "parallelism": f"dp{world}", "l2_policy": "working set (8.3 GB weights + GBs of activations per step) >> 126 MB L2; no flush needed",
+    strong = args.global_batch is not None
+    G = args.global_batch if strong else args.batch * world
+    lo, hi = DP.shard_range(G, rank, world)                      # this rank's contiguous slice of the sample list
+    B, T = hi - lo, args.tokens
+    per_rank_max = max(DP.shard_range(G, r, world)[1] - DP.shard_range(G, r, world)[0] for r in range(world))
+    hfre_only = args.workload == "c2"
+    config = {"workload": f"{wl['name']}: {'global batch ' + str(G) if strong else 'batch ' + str(args.batch) + '/GPU'}, {args.size}x{args.size}, "
+                          f"{args.boxes} boxes/img, {T}-token greedy decode, random-init 3B FO1 (variant B: SimpleFPN, D=5888, mlp2x_gelu projector)",
+              "workload_id": args.workload, "global_batch": G, "per_gpu_batch": per_rank_max, "image_size": args.size,
+              "boxes_per_image": args.boxes, "decode_tokens": T, "parallelism": f"dp{world}",
+              "l2_policy": "working set (8.3 GB weights + GBs of activations per step) >> 126 MB L2; no flush needed",
               "small_arch": bool(args.small)}
+    metric, unit = (METRIC, UNIT) if not hfre_only else ("HFRE GB/s (SURVEY 8d unique bytes / fo1_hfre_forward time), dual-ViT forward + region tokens", "GB/s")
 
     # ------------------------------------------------------------------ reference (CPU) arm
     if args.impl == "reference":
         if rank != 0:
             return
-        args.steps = max(1, min(args.steps, 3)); args.warmup = 0   # bounded: each step is tens of seconds of CPU work
-        ips, detail, times = cpu_arm(args, CK, E, cfg, args.steps)
-        cores = torch.get_num_threads()
-        line = {"impl": "reference", "metric": METRIC, "value": ips, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": 0,
-                "ms_per_step": 1000.0 / ips, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": config,
-                "cpu_baseline": {"value": ips, "unit": UNIT, "cores": cores, "kind": "port",
-                                 "sample": CPU_SAMPLE_NOTE.format(tok=args.cpu_tokens, T=args.tokens),
-                                 "stage_seconds": detail},
-                "e2e": {"value": ips, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        steps = max(1, min(args.steps, 2))           # bounded: one full-depth image is about a minute of CPU work
+        ips, kind, cores, note, detail = reference_arm(args, cfg, steps, max(T, 1))
+        value = ips
+        if hfre_only:                                # the HFRE stage alone, same unit as the GPU arm
+            host1 = SY.synthetic_batch(0, 1, args.size, args.boxes)
+            sec = detail.get("fpn_hfre_s", detail.get("hfre_s", 0.0) + detail.get("fpn_s", 0.0))
+            value = hfre_algorithmic_bytes(HF, cfg, host1, args.size) / max(sec, 1e-9) / 1e9
+            note += "; value = unique HFRE bytes of that image / the reference's SimpleFP + HFREModule time"
+        line = {"impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus, "steps": steps, "warmup": 0,
+                "ms_per_step": 1000.0 / ips, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": kind, "sample": note, "stage_seconds": detail},
+                "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line), file=out, flush=True)
         return
 
@@ -219,27 +263,35 @@ def main():
     del sds
     torch.cuda.empty_cache()
     pipe = P.Fo1Pipeline(eng)
-    B, T = args.batch, args.tokens
-    host = SY.synthetic_batch(rank * B, B, args.size, args.boxes)
-    for s in host:
-        s.pixel_values = s.pixel_values.pin_memory(); s.image_aux = s.image_aux.pin_memory(); s.boxes = s.boxes.pin_memory()
+    host = SY.synthetic_batch(lo, B, args.size, args.boxes)
+    # end-to-end arm: the raw uint8 images in pinned host memory; resize / normalise / patchify run on the device (fo1_preprocess_*)
+    host_u8 = [SY.synthetic_sample_u8(lo + k, args.size, args.boxes) for k in range(B)]
+    for s in host_u8:
+        s.image_u8 = s.image_u8.pin_memory(); s.boxes = s.boxes.pin_memory()
     resident = [P.SampleInputs(s.input_ids, s.pixel_values.to(dev), s.grid_hw, s.image_aux.to(dev), s.boxes.to(dev)) for s in host]
-    gathered = torch.empty((world * B, T), dtype=torch.int32, device=dev) if world > 1 else None
-    host_tokens = torch.empty((B, T), dtype=torch.int32).pin_memory()
+    Tc = max(T, 1)
+    host_tokens = torch.empty((B, Tc), dtype=torch.int32).pin_memory()
+    host_regions = torch.empty((B * args.boxes, cfg.llm["hidden_size"]), dtype=torch.bfloat16).pin_memory() if hfre_only else None
 
     def step(samples):
-        out = pipe.generate(samples, T, stop_ids=[], early_exit_interval=0)
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, out["tokens"])   # the path's only collective: decoded ids over NVLink
-        return out
+        if hfre_only:                                 # C2: towers + region tokens, no language model
+            feats, img_off, region_tokens, region_f32 = pipe.encode(samples)
+            return {"region_tokens": torch.cat(region_tokens, 0)}
+        res = pipe.generate(samples, T, stop_ids=[], early_exit_interval=0)
+        # the path's only collective: every rank's decoded ids (ragged shards padded to the largest) over NVLink
+        res["all_tokens"], res["all_lens"] = DP.gather_ids(res["tokens"], res["lens"], world, per_rank_max)
+        return res
 
     def step_e2e():
-        moved = [P.SampleInputs(s.input_ids, s.pixel_values.to(dev, non_blocking=True), s.grid_hw, s.image_aux.to(dev, non_blocking=True),
-                                s.boxes.to(dev, non_blocking=True)) for s in host]
-        out = step(moved)
-        host_tokens.copy_(out["tokens"], non_blocking=True)
+        moved = [P.SampleInputs(s.input_ids, None, None, None, s.boxes.to(dev, non_blocking=True), image_u8=s.image_u8.to(dev, non_blocking=True))
+                 for s in host_u8]
+        res = step(moved)
+        if hfre_only:
+            host_regions.copy_(res["region_tokens"], non_blocking=True)
+        else:
+            host_tokens.copy_(res["tokens"], non_blocking=True)
         torch.cuda.current_stream().synchronize()
-        return out
+        return res
 
     def timed(fn, steps):
         if dist is not None:
@@ -273,24 +325,27 @@ def main():
         ms = timed(lambda: step(resident), args.steps)
     launches = int(L.fo1_launch_count())
     clocks = cs.summary()
-    value = world * B * args.steps / (ms / 1000.0)
+    ips = G * args.steps / (ms / 1000.0)
     step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
-    e2e = world * B * args.steps / (ms_e2e / 1000.0)
-    h2d = sum(s.pixel_values.numel() * 4 + s.image_aux.numel() * 4 + s.boxes.numel() * 4 for s in host)
-    d2h = B * T * 4
+    ips_e2e = G * args.steps / (ms_e2e / 1000.0)
+    h2d = sum(s.image_u8.numel() + s.boxes.numel() * 4 for s in host_u8)
+    d2h = host_regions.numel() * 2 if hfre_only else B * Tc * 4
 
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+    line = {"metric": metric, "value": ips, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic", "config": config, "clocks": clocks,
-            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": launches}
+            "e2e": {"value": ips_e2e, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches, "images_per_s": ips, "images_per_s_e2e": ips_e2e}
 
     if rank == 0:
-        # ---- one extra instrumented step: per-kernel CUDA-event times for the roofline objects ----
+        # ---- extra instrumented steps (rank 0 only, no collective: the other ranks are already at the final barrier) ----
         peaks = load_peaks()
-        # (rank-0-only passes must not contain the collective: the other ranks are already at the final barrier)
-        local_step = lambda: pipe.generate(resident, T, stop_ids=[], early_exit_interval=0)
+        traffic = load_traffic()
+        if hfre_only:
+            local_step = lambda: pipe.encode(resident)
+        else:
+            local_step = lambda: pipe.generate(resident, T, stop_ids=[], early_exit_interval=0)
         pipe.profile_stages = True
         local_step()
         line["stage_ms"] = pipe.stage_ms()          # un-instrumented kernels, CUDA events between the stages
@@ -301,7 +356,6 @@ def main():
         L.fo1_profile_collect(buf, 1 << 20)
         L.fo1_profile_enable(0)
         raw = json.loads(buf.value.decode())
-        # fold the per-shape GEMM records into two totals, keep the 12 heaviest shapes for the report
         prof, shapes = {}, []
         for k, v in raw.items():
             base = k.split(":")[0]
@@ -311,40 +365,80 @@ def main():
             a = prof.setdefault(base, {"launches": 0, "ms": 0.0, "flops": 0.0, "bytes": 0.0, "max_ms": 0.0})
             a["launches"] += v["launches"]; a["ms"] += v["ms"]; a["flops"] += v["flops"]; a["bytes"] += v["bytes"]
             a["max_ms"] = max(a["max_ms"], v["max_ms"])
+        for v in prof.values():
+            if v["flops"] > 0 and v["ms"] > 0:
+                v["tflops"] = v["flops"] / v["ms"] / 1e9
         line["kernel_profile"] = prof
         line["gemm_shapes_top"] = sorted(shapes, key=lambda r: -r["ms"])[:14]
+        step_ms = ms / args.steps
         g = prof.get("gemm")
+        roof_gemm = None
         if g and g["ms"] > 0:
             ach = g["flops"] / g["ms"] / 1e9
-            line["roofline"] = {"kernel": "gemm_bf16_tcgen05_kernel (M > 128 launches of one step)", "bound": "tensor", "achieved": ach,
-                                "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": ach / peaks["tflops"], "traffic": None,
-                                "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['source']})",
-                                "launches": g["launches"], "ms_per_launch": g["ms"] / g["launches"], "share_of_step": g["ms"] / (ms / args.steps)}
+            roof_gemm = {"kernel": "gemm_bf16_tcgen05_kernel (M > 128 launches of one step)", "bound": "tensor", "achieved": ach,
+                         "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": ach / peaks["tflops"], "traffic": traffic.get("gemm_bytes_per_launch"),
+                         "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['source']})",
+                         "launches": g["launches"], "ms_per_launch": g["ms"] / g["launches"], "share_of_step": g["ms"] / step_ms,
+                         "algorithmic_bytes_per_launch": g["bytes"] / g["launches"]}
+        for tag in ("attn", "attn_causal"):
+            a = prof.get(tag)
+            if a and a["ms"] > 0 and a["flops"] > 0:
+                ach = a["flops"] / a["ms"] / 1e9
+                line["roofline_" + tag] = {"kernel": "attn_tc_kernel (tcgen05 flash attention" + (", causal GQA prefill)" if tag == "attn_causal" else ", ViT / DaViT)"),
+                                           "bound": "tensor", "achieved": ach, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": ach / peaks["tflops"],
+                                           "traffic": traffic.get(tag + "_bytes_per_launch"), "launches": a["launches"], "share_of_step": a["ms"] / step_ms}
         h = prof.get("hfre_sweep_mma") or prof.get("hfre_sweep") or prof.get("hfre_gather")
+        roof_hfre = None
         if h and h["ms"] > 0:
-            tot = 0
-            for s in host:
-                H0 = args.size // 4
-                gh, gw = s.grid_hw
-                shapes = [(args.size // (4 << i), args.size // (4 << i), c) for i, c in enumerate(cfg.davit["dim_embed"])] + \
-                         [(int(gh * f), int(gw * f), cfg.fpn_out) for f in (4, 2, 1, 0.5)]
-                sc = gh * 14 / args.size
-                bl = [s.boxes.numpy()] * 4 + [s.boxes.numpy() * sc] * 4
-                scales = [0.25] * 4 + [1 / x for x in HF.FPN_STRIDES]
-                ups = [H0 // sh[0] for sh in shapes[:4]] + [1] * 4
-                tot += HF.algorithmic_bytes(shapes, bl, scales, ups, s.boxes.shape[0], cfg.region_dim)["unique_bytes"]
+            tot = hfre_algorithmic_bytes(HF, cfg, host, args.size)
             ach = tot / h["ms"] / 1e6
-            line["roofline_hfre"] = {"kernel": "hfre_sweep_mma_kernel" if "hfre_sweep_mma" in prof else ("hfre_sweep_kernel" if "hfre_sweep" in prof else "hfre_gather_kernel"), "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                                     "frac": ach / peaks["hbm_gbs"], "traffic": None, "algorithmic_bytes": tot, "ms": h["ms"],
-                                     "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peaks['source']})"}
-        # ---- CPU baseline (rank 0, N = 1 only) ----
+            hname = "hfre_sweep_mma_kernel" if "hfre_sweep_mma" in prof else ("hfre_sweep_kernel" if "hfre_sweep" in prof else "hfre_gather_kernel")
+            stage = line["stage_ms"].get("hfre")
+            roof_hfre = {"kernel": hname, "bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
+                         "traffic": traffic.get("hfre_bytes_per_launch"), "algorithmic_bytes": tot, "launches": h["launches"],
+                         "algorithmic_bytes_per_launch": tot / h["launches"], "ms": h["ms"],
+                         "operator_ms": stage, "operator_GBs": (tot / stage / 1e6) if stage else None,
+                         "operator_frac": (tot / stage / 1e6 / peaks["hbm_gbs"]) if stage else None,
+                         "peak_source": f"MEASURED_PEAKS.json hbm_gbs ({peaks['source']})"}
+            line["roofline_hfre"] = roof_hfre
+        if hfre_only and roof_hfre:
+            # C2's metric IS the HFRE rate: value = whole operator (all its kernels), roofline = its sweep kernel
+            line["value"] = roof_hfre["operator_GBs"]
+            line["e2e"]["value"] = roof_hfre["operator_GBs"]; line["e2e"]["note"] = "images_per_s_e2e carries the host-buffer images/s of the C2 step"
+            line["roofline"] = roof_hfre
+        elif roof_gemm:
+            line["roofline"] = roof_gemm
+        if not hfre_only and T > 2:
+            # one decode step: what it must stream (bf16 weights of every layer + head, K/V of the live prefixes) over its time
+            lc = cfg.llm
+            hd = lc["hidden_size"] // lc["num_attention_heads"]
+            per_layer = lc["hidden_size"] * (lc["num_attention_heads"] + 2 * lc["num_key_value_heads"]) * hd + lc["hidden_size"] ** 2 + \
+                3 * lc["hidden_size"] * lc["intermediate_size"]
+            wbytes = 2 * (lc["num_hidden_layers"] * per_layer + lc["vocab_size"] * lc["hidden_size"])
+            prompt = sum(len(s.input_ids) - 1 + s.grid_hw[0] * s.grid_hw[1] // 4 for s in host)
+            kv = 2 * 2 * lc["num_hidden_layers"] * lc["num_key_value_heads"] * hd * (prompt + B * T / 2)
+            e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True); e2 = torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record(); pipe.generate(resident, 2, stop_ids=[], early_exit_interval=0); e1.record()
+            pipe.generate(resident, T, stop_ids=[], early_exit_interval=0); e2.record()
+            torch.cuda.synchronize()
+            dms = (e1.elapsed_time(e2) - e0.elapsed_time(e1)) / (T - 2)
+            ach = (wbytes + kv) / dms / 1e6
+            line["roofline_decode"] = {"kernel": "one greedy decode step (CUDA graph of the per-layer kernels)", "bound": "hbm", "achieved": ach,
+                                       "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": None,
+                                       "algorithmic_bytes": wbytes + kv, "weight_bytes": wbytes, "kv_bytes": kv, "ms_per_step": dms,
+                                       "share_of_step": dms * (T - 1) / step_ms}
+        # ---- CPU baseline (rank 0, N = 1 only): the reference's own modules on the host cores ----
         if keep_cpu:
             try:
-                ips, detail, times = cpu_arm(args, CK, E, cfg, 1)
-                line["cpu_baseline"] = {"value": ips, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-                                        "sample": CPU_SAMPLE_NOTE.format(tok=args.cpu_tokens, T=args.tokens), "stage_seconds": detail}
+                cips, kind, cores, note, detail = reference_arm(args, cfg, 1, args.cpu_tokens)
+                cval = cips
+                if hfre_only:
+                    sec = detail.get("fpn_hfre_s", detail.get("hfre_s", 0.0) + detail.get("fpn_s", 0.0))
+                    cval = hfre_algorithmic_bytes(HF, cfg, host[:1], args.size) / max(sec, 1e-9) / 1e9
+                line["cpu_baseline"] = {"value": cval, "unit": unit, "cores": cores, "kind": kind, "sample": note, "stage_seconds": detail}
             except Exception as exc:  # the baseline is a report, never a reason to lose the GPU number
-                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": f"failed: {exc!r}"}
+                line["cpu_baseline"] = {"value": None, "unit": unit, "cores": os.cpu_count(), "kind": "reference", "sample": f"failed: {exc!r}"}
         print(json.dumps(line), file=out, flush=True)
     if dist is not None:
         dist.barrier()

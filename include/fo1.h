@@ -148,6 +148,15 @@ typedef struct {
 } fo1_attn_desc;
 int fo1_attention_varlen(const fo1_attn_desc* d, void* stream);
 
+/* DaViT channel-group attention (ChannelAttention.forward, modeling_davit.py:151-172) for n_images maps of n_tokens tokens:
+ * qkv bf16 [n_images][n_tokens][3*channels] (q | k | v as the fused Linear emits them), groups * 32 == channels;
+ * out bf16 [n_images][n_tokens][channels] = (softmax_c2((q N^-0.5)^T k) v^T)^T per group of 32 channels.  Both contractions
+ * run on tcgen05 (the Gram over the token axis with MN-major operands straight from the TMA tiles); partial Grams of the
+ * token chunks live in `workspace` and are summed in a fixed order (bit-reproducible, no atomics). */
+size_t fo1_channel_attention_workspace_bytes(int32_t n_images, int32_t n_tokens, int32_t channels);
+int fo1_channel_attention(const void* qkv, int32_t n_images, int32_t n_tokens, int32_t channels, int32_t groups, void* out,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
 /* Single-query GQA attention of one decode step over the K/V cache (the per-step attention of the HF generate loop,
  * modeling_qwen2_5_vl.py:731-780 with past_key_values; mm_utils.py:640-654 drives it).  The step's own K/V must already
  * sit in the cache at index cache_len[b].  head_dim 128, q_heads / kv_heads <= 8.  Exposed so the parity tests can
@@ -241,6 +250,25 @@ int fo1_image_project(fo1_model* m, const void* feats, int32_t n, void* out, voi
 
 
 /* ------------------------------------------------------------------------------------------------
+ * Device-side image pre-processing: uint8 RGB [H][W][3] in device memory -> the tensors the two
+ * host processors produce, bit-identical (integer resize; float32 normalisation in the processors' operation order).
+ * ---------------------------------------------------------------------------------------------- */
+/* PIL's bicubic resize of an 8-bit image (what Qwen2VLImageProcessor / CLIPImageProcessor call: mm_utils.py:615, :596 ->
+ * PIL Image.resize(BICUBIC)): horizontal pass then vertical pass with the uint8 intermediate.  bounds: host-computed, DEVICE
+ * int32 [out][2] = (first input index, count); coef: DEVICE int32 [out][ksize], 22 fractional bits (PIL's normalised
+ * coefficients; vlm-fo1_b200/preprocess.py computes them).  tmp: [H][out_w][3] bytes when both axes change.  A pass whose
+ * size does not change is skipped (its tables may be NULL). */
+int fo1_resize_bicubic_u8(const void* img, int32_t H, int32_t W, int32_t out_h, int32_t out_w, const int32_t* h_bounds,
+                          const int32_t* h_coef, int32_t h_ksize, const int32_t* v_bounds, const int32_t* v_coef, int32_t v_ksize,
+                          void* tmp, void* out, void* stream);
+/* Qwen2VLImageProcessor's rescale + normalise + patchify (2x2-merge order, frame repeated over the temporal patch) of an image
+ * whose sides are already multiples of patch*merge: -> fp32 [H/patch * W/patch][3*temporal*patch*patch].  mean / std: HOST [3]. */
+int fo1_preprocess_primary_u8(const void* img, int32_t H, int32_t W, int32_t patch, int32_t merge, int32_t temporal, const float* mean,
+                              const float* std, float* pixel_values, void* stream);
+/* CLIPImageProcessor's rescale + normalise + channels-first (davit/image_processing_clip.py:344-358): -> fp32 [3][H][W]. */
+int fo1_preprocess_aux_u8(const void* img, int32_t H, int32_t W, const float* mean, const float* std, float* out, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * LLM half: embedding splice, M-RoPE bookkeeping, prefill and greedy decode.
  * ---------------------------------------------------------------------------------------------- */
 typedef struct {
@@ -264,6 +292,30 @@ int fo1_splice_plan(const int64_t* input_ids, int32_t n_ids, const int32_t* imag
                     int32_t n_regions, const fo1_splice_cfg* cfg, int64_t* new_ids, int32_t* src_kind,
                     int32_t* src_index, int32_t* position_ids, int32_t* rope_delta, int32_t* out_len,
                     int32_t capacity);
+
+/* The same integer work for a whole BATCH of prompts in one launch, on the device: all pointers
+ * are DEVICE int32 arrays.  ids / id_off: the prompts' ids concatenated + offsets [n_samples+1]; grids / img_off: (gh, gw) of
+ * every image + offsets [n_samples+1]; n_regions [n_samples]; out_off [n_samples+1]: row offsets of the spliced sequences
+ * (L_b = n_ids_b - n_img_b + sum gh*gw/merge^2, host arithmetic); img_row_off / reg_row_off [n_samples]: first row of the
+ * sample in the batch's image- / region-feature matrices (added to src_index).  Outputs over total_rows = out_off[n_samples]:
+ * new_ids, src_kind, src_index [total_rows], position_ids [3][total_rows], rope_delta / status [n_samples] (status 0 or a
+ * fo1_status per sample).  Bit-identical to fo1_splice_plan sample by sample. */
+int fo1_splice_plan_batch(const int32_t* ids, const int32_t* id_off, const int32_t* grids, const int32_t* img_off,
+                          const int32_t* n_regions, const int32_t* out_off, const int32_t* img_row_off,
+                          const int32_t* reg_row_off, int32_t n_samples, int64_t total_rows, const fo1_splice_cfg* cfg,
+                          int32_t* new_ids, int32_t* src_kind, int32_t* src_index, int32_t* position_ids, int32_t* rope_delta,
+                          int32_t* status, void* stream);
+
+/* extract_predictions_to_indexes (vlm_fo1/mm_utils.py:346-369) over the decoded TOKEN IDS of a batch, on the device, for
+ * tokenizers that hold "<ground>", "</ground>", "<objects>", "</objects>" and every "<regionN>" as single tokens: tokens DEVICE
+ * int32 [n_samples][ld], lens [n_samples]; region_ids DEVICE [n_region_ids] (id of <region0>, <region1>, ...); newline_bitmap
+ * DEVICE, bit t set iff the text of token t contains a newline ("." of the reference's regex does not cross one), or NULL.
+ * records DEVICE [n_samples][max_records][3] = (first label token, label end token (exclusive), N or -1 for a label without
+ * regions), n_records DEVICE [n_samples]. */
+int fo1_parse_predictions(const int32_t* tokens, int64_t ld, const int32_t* lens, int32_t n_samples, int32_t ground_start_id,
+                          int32_t ground_end_id, int32_t objects_start_id, int32_t objects_end_id, const int32_t* region_ids,
+                          int32_t n_region_ids, const uint32_t* newline_bitmap, int32_t vocab, int32_t* records, int32_t max_records,
+                          int32_t* n_records, void* stream);
 
 /* inputs_embeds[r] = embed_tokens[src_index[r]] | img_feats[src_index[r]] | region_feats[src_index[r]]
  * (omchat_qwen2_5_vl.py:333-368).  src_kind / src_index: device int32 [n_rows]; feature matrices bf16

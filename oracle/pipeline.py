@@ -26,7 +26,12 @@ def _bf(x: torch.Tensor) -> torch.Tensor:
 def run_sample(sds: Dict[str, Dict[str, torch.Tensor]], vit_cfg: dict, davit_cfg: dict, llm_cfg: dict, *, input_ids: Sequence[int],
                pixel_values: torch.Tensor, grid_hw, image_aux: torch.Tensor, boxes: torch.Tensor, region_dim: int,
                max_new_tokens: int, stop_ids: Sequence[int] = (), vt_mode: str = "fpn", image_token_id: int = 151655,
-               vision_start_token_id: int = 151652, stages_only: bool = False) -> dict:
+               vision_start_token_id: int = 151652, stages_only: bool = False, forced: Sequence[int] = None,
+               keep_stages: bool = False, round_towers: bool = True) -> dict:
+    """``forced``: teacher forcing -- feed these tokens instead of the argmax (the per-step logits are still returned).
+    ``keep_stages``: also return the taps, DaViT stage maps and FPN levels.  ``round_towers=False`` keeps even the tensors the
+    reference stores in bf16 between its towers in fp32 (the all-fp32 yardstick of the parity tests)."""
+    _bf = (lambda x: x.to(torch.bfloat16).to(torch.float32)) if round_towers else (lambda x: x)
     t = {}
     gh, gw = grid_hw
     t0 = time.perf_counter()
@@ -55,6 +60,8 @@ def run_sample(sds: Dict[str, Dict[str, torch.Tensor]], vit_cfg: dict, davit_cfg
     region_tokens = _bf(OD.projector_forward(sds["proj_aux"], _bf(region)))
     t["proj_s"] = time.perf_counter() - t0
     out = dict(region_features=region, region_tokens=region_tokens, image_features=merged, timings=t)
+    if keep_stages:
+        out.update(taps=taps, davit=aux, fpn=vt if vt_mode == "fpn" else None)
     if stages_only:
         return out
     t0 = time.perf_counter()
@@ -80,8 +87,9 @@ def run_sample(sds: Dict[str, Dict[str, torch.Tensor]], vit_cfg: dict, davit_cfg
     td = time.perf_counter()
     for s_ in range(max_new_tokens):
         lgs.append(lg)
-        tok = int(lg.argmax()); toks.append(tok)
-        if tok in stop_ids or s_ == max_new_tokens - 1:
+        tok = int(lg.argmax()) if forced is None else int(forced[s_])
+        toks.append(tok)
+        if (forced is None and tok in stop_ids) or s_ == max_new_tokens - 1:
             break
         h = dec.forward(emb[tok][None, :], torch.full((3, 1), L + s_ + delta, dtype=torch.long))
         t.setdefault("llm_decode_layer_s", []).append(sum(dec.layer_seconds) / max(len(dec.layer_seconds), 1))

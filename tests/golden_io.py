@@ -24,3 +24,11 @@ def load(name):
 def nerr(got: torch.Tensor, ref: torch.Tensor) -> float:
     """max |got - ref| / max |ref| -- the normalised error every parity test bounds by 1e-3 (fp32 stages)."""
     return float((got.float() - ref.float()).abs().max() / ref.float().abs().max().clamp_min(1e-30))
+
+
+def rerr(got: torch.Tensor, ref: torch.Tensor) -> float:
+    """||got - ref||_2 / ||ref||_2 -- the relative (RMS) error.  Under bf16 storage the MAX-norm error of a tensor with millions of
+    elements is an extreme-value statistic of single-ulp rounding flips at its largest elements; the RMS error is what stays
+    at the 1e-3 level when two implementations agree."""
+    g, r = got.double(), ref.double()
+    return float((g - r).norm() / r.norm().clamp_min(1e-30))

@@ -54,3 +54,36 @@ def test_inference_py_call_sequence(tmp_path):
     model.default_stop_ids = [new[2]]
     again = model.generate(**generation_kwargs)
     assert again[0, P:].tolist() == new[: new.index(new[2]) + 1]
+
+
+def test_reference_inference_py_runs_unmodified(tmp_path, monkeypatch):
+    """The reference's own ``inference.py`` FILE (staged byte-for-byte into baseline/_ref/ by __graft_entry__.build()), executed
+    with runpy from a working directory laid out like the reference's (./resources/<checkpoint>, ./demo/demo_image.jpg) with
+    this repo first on sys.path, so that its imports resolve to the repo's ``vlm_fo1`` / ``detect_tools`` mirror.  No statement
+    of the script is re-typed here; max_tokens stays at the script's 4096 (a random-init model never emits <|im_end|>)."""
+    import runpy
+    import sys
+    REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    script = os.path.join(REPO, "baseline", "_ref", "inference.py")
+    if not os.path.exists(script):
+        pytest.skip("baseline/_ref/inference.py not staged (build() copies it where /root/reference exists)")
+    from importlib import import_module
+    import fo1_b200  # noqa: F401
+    E = import_module("vlm-fo1_b200.engine"); FB = import_module("vlm-fo1_b200.fabricate")
+    cfg = E.EngineConfig()
+    cfg.vit = dict(cfg.vit, depth=2, fullatt_block_indexes=[0, 1])
+    cfg.davit = dict(cfg.davit, depths=[1, 1, 1, 1])
+    cfg.llm = dict(cfg.llm, num_hidden_layers=1)
+    FB.fabricate_checkpoint(str(tmp_path / "resources" / "VLM-FO1_Qwen2.5-VL-3B-v01"), cfg, seed=0, device="cuda")
+    os.makedirs(tmp_path / "demo")
+    Image.fromarray(np.random.default_rng(0).integers(0, 256, (399, 500, 3), dtype=np.uint8)).save(str(tmp_path / "demo" / "demo_image.jpg"))
+    monkeypatch.chdir(tmp_path)
+    monkeypatch.setattr(sys, "path", [REPO] + [p for p in sys.path if p != REPO])
+    for k in [k for k in sys.modules if k == "vlm_fo1" or k.startswith("vlm_fo1.")]:
+        if REPO not in (getattr(sys.modules[k], "__file__", "") or ""):
+            del sys.modules[k]                     # a reference copy imported by another test must not shadow the mirror
+    g = runpy.run_path(script, run_name="__main__")
+    P = g["generation_kwargs"]["inputs"].shape[1]
+    assert g["output_ids"].shape[0] == 1 and P < g["output_ids"].shape[1] <= P + 4096
+    assert isinstance(g["outputs"], str) and isinstance(g["bboxes"], dict)
+    assert os.path.exists(tmp_path / "demo" / "vlm_fo1_result.jpg")

@@ -41,23 +41,24 @@ def test_prefill_logits_and_greedy_tokens_match_oracle():
     out = eng.generate(embs, poss, [L, L2, L], [delta, delta2, delta], max_new, stop_ids=[], pad_id=0,
                        want_prefill_logits=True, want_all_logits=True, early_exit_interval=0)
     torch.cuda.synchronize()
-    ref_toks, ref_step, ref_prompt = OL.generate(sd, cfg, emb, pos, delta, max_new, stop_ids=[])
-    assert nerr(out["all_logits"][:L].cpu(), ref_prompt) < 2e-2
-    assert nerr(out["prefill_logits"][0].cpu(), ref_prompt[-1]) < 2e-2
-    assert torch.equal(out["tokens"][0], out["tokens"][2])
     got = out["tokens"][0].cpu().tolist()
-    # greedy ids must agree wherever the oracle's top-1/top-2 margin exceeds the measured logit error (bf16
-    # activations vs fp32 oracle); random-init logits are nearly flat, so below that floor the argmax is undecidable
+    from oracle import precision
+    with precision.act_bf16(True):       # bf16 storage points like the engine: what is left is accumulation order / fusion
+        _, ref_step, ref_prompt = OL.generate(sd, cfg, emb, pos, delta, max_new, stop_ids=[], forced=got)
+    assert nerr(out["all_logits"][:L].cpu(), ref_prompt) < 1e-2
+    assert nerr(out["prefill_logits"][0].cpu(), ref_prompt[-1]) < 1e-2
+    assert torch.equal(out["tokens"][0], out["tokens"][2])
+    # the oracle is teacher-forced on the engine's own prefix, so every step is comparable on its own: the engine's token
+    # must be the oracle's argmax wherever the oracle's top-1/top-2 margin exceeds 4x the measured logit error
     floor = 4.0 * float((out["all_logits"][:L].cpu() - ref_prompt).abs().max())
-    top2 = ref_step.topk(2, dim=-1).values
-    margins = top2[:, 0] - top2[:, 1]
+    top2 = ref_step.topk(2, dim=-1)
     compared = 0
-    for s in range(len(ref_toks)):
-        if margins[s] < floor:
-            break
-        assert got[s] == ref_toks[s], (s, got, ref_toks)
-        compared += 1
-    print(f"greedy ids compared: {compared} (margin floor {floor:.3e})")
+    for s in range(max_new):
+        if float(top2.values[s, 0] - top2.values[s, 1]) > floor:
+            assert got[s] == int(top2.indices[s, 0]), (s, got, top2.indices[:, 0].tolist())
+            compared += 1
+    print(f"greedy ids compared: {compared} of {max_new} (margin floor {floor:.3e})")
+    assert compared >= 2, (compared, floor)
     ref2, _, _ = OL.generate(sd, cfg, emb[:L2], pos[:, :L2], delta2, 4, stop_ids=[])
     _ = ref2  # (ids of the ragged entry are covered by the consistency test below; margins are too flat to pin here)
     assert out["lens"].cpu().tolist() == [max_new] * 3

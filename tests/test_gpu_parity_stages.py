@@ -1,0 +1,399 @@
+"""-m gpu: stage-by-stage parity at the REAL layer widths and the BASELINE geometries, through the C ABI.
+
+The oracle runs with ``oracle.precision.act_bf16(True)``: it rounds every tensor that crosses a module boundary to bf16,
+exactly where the reference's CUDA path (and the engine) stores bf16, and is fed the same bf16-rounded weights and inputs.
+What is left between the two is accumulation order and fusion (the engine adds bias / residual in fp32 before its one
+rounding, keeps P of the flash attention in bf16): a pre-rounding difference of a fraction of an ulp flips the bf16 rounding of
+some elements at every storage point (measured: ~1.2e-3 of relative RMS difference per storage point, adding like a random
+walk: sqrt(10) x that for one transformer block).  Three checks per stage:
+  (A) the engine is AS CLOSE TO THE fp32 REFERENCE AS THE REFERENCE'S OWN bf16 PATH: rms(engine, fp32 oracle) <=
+      1.25 x rms(bf16 oracle, fp32 oracle) + 5e-4 -- the criterion that does not depend on how many roundings a stage holds;
+  (B) max-norm  max|engine - bf16 oracle| / max|oracle| <= 1e-3 + k * 2^-8, k = single-ulp flips tolerated at the largest
+      element (stated per test);
+  (C) relative RMS  ||engine - bf16 oracle|| / ||oracle|| <= 1.5e-3 x sqrt(storage points of the stage).
+fp32 outputs (HFRE): 1e-3 max-norm, as north_star states.  Measured values of every run are written to gpurun_out/ and the
+round's are committed under profiles/.
+
+Geometries: C4 -- 640 -> 644 px, grid 46x46 (ragged ViT windows {64, 48, 36}; images straddle the
+128-row attention tiles), DaViT 160/80/40/20 maps (window padding +8/+4/+8/+4), prompt of 244 + 529 tokens; C5 -- 1344 px,
+300 boxes per image (HFRE multi-pass box tiles) and more than 8 images in one HFRE call."""
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from tests.golden_io import nerr, rerr
+
+pytestmark = pytest.mark.gpu
+
+ULP = 2.0 ** -8
+TOL_BF16 = 1e-3 + ULP
+TOL_F32 = 1e-3
+RMS_STAGE = 2e-3
+
+
+def tol(k: float) -> float:
+    return 1e-3 + k * ULP
+
+
+def rms_tol(n_storage_points: float) -> float:
+    return 1.5e-3 * math.sqrt(n_storage_points)
+
+
+def as_accurate_as_bf16_reference(got, ref_bf16, ref_fp32) -> bool:
+    """(A): the engine's distance to the fp32 reference vs the bf16-storage reference's own distance to it."""
+    return rerr(got, ref_fp32) <= 1.25 * rerr(ref_bf16, ref_fp32) + 5e-4
+
+
+def _mods():
+    from importlib import import_module
+    import fo1_b200  # noqa: F401
+    return (import_module("vlm-fo1_b200.engine"), import_module("vlm-fo1_b200.checkpoint"), import_module("vlm-fo1_b200.weights"),
+            import_module("vlm-fo1_b200.pipeline"), import_module("vlm-fo1_b200.synthetic"), import_module("vlm-fo1_b200.hfre"))
+
+
+def _cpu(sd):
+    return {k: v.float().cpu() for k, v in sd.items()}
+
+
+def _record(name, payload):
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    if os.path.isdir(out):
+        with open(os.path.join(out, f"parity_{name}.json"), "w") as fh:
+            json.dump(payload, fh, indent=1)
+
+
+def test_vit_blocks_real_width_c4_grid():
+    """One windowed + one full-attention block (+ patch embed, tap, merger) at hidden 1280 / 16 heads / MLP 3420 on the
+    46x46 grid of C4 (windows of 64 / 48 / 36 tokens; 2116-token images packed back to back) next to a 32x32 image."""
+    from oracle import precision, vit as OV
+    E, CK, W, P, SY, HF = _mods()
+    cfg = E.EngineConfig()
+    cfg.use_davit = cfg.use_llm = False
+    cfg.proj_aux_layers = 0
+    cfg.fpn_out = 0
+    cfg.vit = dict(cfg.vit, depth=2, fullatt_block_indexes=[1])
+    sd = CK.random_vit(cfg.vit, torch.Generator(device="cuda").manual_seed(11), "cuda")
+    eng = E.Engine(cfg)
+    eng.set_weights(W.prepare_vit(sd, cfg.vit, eng.device))
+    eng.finalize()
+    g = torch.Generator().manual_seed(5)
+    grids = [(46, 46), (32, 32), (46, 46)]
+    px = [torch.randn(gh * gw, 1176, generator=g).bfloat16().float() for gh, gw in grids]
+    px[2] = px[0]                                  # the same image at two batch slots
+    feats, taps = eng.vit_forward(px, grids)
+    torch.cuda.synchronize()
+    sdc = _cpu(sd)
+    tok = cell = 0
+    errs = []
+    tri = []
+    for b, (gh, gw) in enumerate(grids):
+        with precision.act_bf16(True):
+            ref_m, ref_t = OV.vit_forward(sdc, cfg.vit, px[b], gh, gw)
+        f32_m, f32_t = OV.vit_forward(sdc, cfg.vit, px[b], gh, gw)
+        n, nm = gh * gw, gh * gw // 4
+        got_t, got_m = taps[0][tok:tok + n].reshape(gh, gw, -1).cpu(), feats[cell:cell + nm].cpu()
+        errs.append((nerr(got_t, ref_t[0]), nerr(got_m, ref_m), rerr(got_t, ref_t[0]), rerr(got_m, ref_m)))
+        tri.append((rerr(got_t, f32_t[0]), rerr(ref_t[0], f32_t[0]), rerr(got_m, f32_m), rerr(ref_m, f32_m)))
+        assert as_accurate_as_bf16_reference(got_t, ref_t[0], f32_t[0]) and as_accurate_as_bf16_reference(got_m, ref_m, f32_m), tri
+        tok += n; cell += nm
+    # the same image at two batch slots: tiling restarts at every image, so the bits are identical
+    n0 = 46 * 46
+    assert torch.equal(taps[0][:n0], taps[0][n0 + 1024:n0 + 1024 + n0])
+    _record("vit_blocks", {"engine_vs_bf16oracle(max tap, max merged, rms tap, rms merged)": errs,
+                           "vs_fp32(rms engine tap, rms bf16oracle tap, rms engine merged, rms bf16oracle merged)": tri})
+    for e_tap, e_m, r_tap, r_m in errs:
+        assert e_tap < tol(3) and e_m < tol(3), errs          # two blocks (20 storage points) + merger (5)
+        assert r_tap < rms_tol(20) and r_m < rms_tol(25), errs
+
+
+def test_davit_blocks_real_width_c4_size():
+    """DaViT-large, one Spatial + one Channel block per stage, 640x640 input (160/80/40/20 maps: every stage pads its 12x12
+    windows) -- the 3x3 conv embeds, depth-wise convs, window attention (head_dim 32), channel attention and MLPs at
+    their real widths 256 / 512 / 1024 / 2048."""
+    from oracle import davit as OD, precision
+    E, CK, W, P, SY, HF = _mods()
+    cfg = E.EngineConfig()
+    cfg.use_vit = cfg.use_llm = False
+    cfg.proj_aux_layers = 0
+    cfg.fpn_out = 0
+    cfg.davit = dict(cfg.davit, depths=[1, 1, 1, 1])
+    sd = CK.random_davit(cfg.davit, torch.Generator(device="cuda").manual_seed(12), "cuda")
+    eng = E.Engine(cfg)
+    eng.set_weights(W.prepare_davit(sd, cfg.davit, eng.device))
+    eng.finalize()
+    g = torch.Generator().manual_seed(6)
+    img = torch.randn(3, 640, 640, generator=g).bfloat16().float()
+    outs = eng.davit_forward([img, img])
+    torch.cuda.synchronize()
+    full = dict(cfg.davit, patch_prenorm=[False, True, True, True], patch_stride=[4, 2, 2, 2], patch_padding=[3, 1, 1, 1])
+    with precision.act_bf16(True):
+        ref = OD.davit_forward(_cpu(sd), full, img)
+    f32 = OD.davit_forward(_cpu(sd), full, img)
+    errs = [nerr(outs[i][0].cpu(), r) for i, r in enumerate(ref)]
+    rms = [rerr(outs[i][0].cpu(), r) for i, r in enumerate(ref)]
+    tri = [(rerr(outs[i][0].cpu(), f32[i]), rerr(ref[i], f32[i])) for i in range(4)]
+    _record("davit_blocks", {"max": errs, "rms": rms, "vs_fp32(rms engine, rms bf16oracle)": tri})
+    for i in range(4):
+        assert as_accurate_as_bf16_reference(outs[i][0].cpu(), ref[i], f32[i]), tri
+    for i in range(4):
+        assert torch.equal(outs[i][0], outs[i][1])            # batch entries are independent and deterministic
+    # four stages in sequence: stage s carries the noise of the stages before it (8 storage points of the residual stream per block)
+    for i in range(4):        # conv embed + Spatial + Channel block = 20 storage points per stage
+        assert errs[i] < tol(5) and rms[i] < rms_tol(20 * (i + 1)), (errs, rms)
+
+
+def test_fpn_and_projector_real_width():
+    """SimpleFPN on a 46x46 last-tap map (1280 -> 512 channels, 4 levels incl. the two deconv levels and the max-pool level)
+    and the mlp2x_gelu region projector 5888 -> 2048 -> 2048."""
+    from oracle import davit as OD, precision
+    E, CK, W, P, SY, HF = _mods()
+    cfg = E.EngineConfig()
+    cfg.use_davit = cfg.use_llm = False
+    cfg.vit = dict(cfg.vit, depth=0, fullatt_block_indexes=[])
+    g = torch.Generator(device="cuda").manual_seed(13)
+    fpn = CK.random_fpn(1280, 512, g, "cuda")
+    proj = CK.random_projector(cfg.region_dim, 2048, 2, g, "cuda")
+    eng = E.Engine(cfg)
+    eng.set_weights(W.prepare_fpn(fpn, eng.device))
+    eng.set_weights(W.prepare_projector(proj, "proj_aux", eng.device))
+    eng.finalize()
+    tap = torch.randn(46, 46, 1280, generator=torch.Generator().manual_seed(3)).bfloat16()
+    levels = eng.fpn_forward(tap.cuda().unsqueeze(0))
+    x = torch.randn(300, cfg.region_dim, generator=torch.Generator().manual_seed(4)).bfloat16()
+    y = eng.region_project(x.cuda())
+    torch.cuda.synchronize()
+    with precision.act_bf16(True):
+        ref_l = OD.fpn_forward(_cpu(fpn), tap.float())
+        ref_y = OD.projector_forward(_cpu(proj), x.float())
+    f32_l = OD.fpn_forward(_cpu(fpn), tap.float())
+    f32_y = OD.projector_forward(_cpu(proj), x.float())
+    got = [levels[i][0].cpu() for i in range(4)] + [y.cpu()]
+    refs, f32s = list(ref_l) + [ref_y], list(f32_l) + [f32_y]
+    errs = [nerr(g, r) for g, r in zip(got, refs)]
+    rms = [rerr(g, r) for g, r in zip(got, refs)]
+    tri = [(rerr(g, f), rerr(r, f)) for g, r, f in zip(got, refs, f32s)]
+    _record("fpn_projector", {"max": errs, "rms": rms, "vs_fp32(rms engine, rms bf16oracle)": tri})
+    for g, r, f in zip(got, refs, f32s):
+        assert as_accurate_as_bf16_reference(g, r, f), tri
+    for e, r in zip(errs, rms):           # <= 8 storage points per level; the projector's 3 sit behind a 5888-wide contraction
+        assert e < tol(2) and r < rms_tol(8), (errs, rms)
+
+
+def test_llm_layers_real_width_c4_prompt():
+    """Two decoder layers at the 3B widths (2048 hidden, 16 q / 2 kv heads of 128, MLP 11008) on the C4 prompt geometry
+    (244 text/region tokens + 529 image tokens with M-RoPE grid positions), ragged batch; logits at EVERY prompt position
+    and through 6 decode steps (teacher-forced on the engine's own tokens)."""
+    from oracle import llm as OL, precision
+    E, CK, W, P, SY, HF = _mods()
+    cfg = E.EngineConfig()
+    cfg.use_vit = cfg.use_davit = False
+    cfg.proj_aux_layers = 0
+    cfg.llm = dict(cfg.llm, num_hidden_layers=2, vocab_size=20000)
+    sd = CK.random_llm(cfg.llm, torch.Generator(device="cuda").manual_seed(14), "cuda")
+    eng = E.Engine(cfg)
+    eng.set_weights(W.prepare_llm(sd, cfg.llm, eng.device))
+    eng.finalize()
+    # ids: text, <vision_start>, 529 x image token, text + 100 region slots -- positions from the splice plan itself
+    ids = [(19998 if t == 151652 else (t % 19990 if t >= 0 else t)) for t in SY.synthetic_prompt(0, 100)]
+    plan = E.splice_plan(ids, [(46, 46)], 100, image_token_id=19999, vision_start_token_id=19998)
+    L = len(plan["kind"])
+    assert L == len(ids) - 1 + 529
+    g = torch.Generator().manual_seed(8)
+    emb = (torch.randn(L, 2048, generator=g) * 0.05).bfloat16()
+    pos = torch.from_numpy(plan["position_ids"]).to(torch.int32)
+    L2 = L - 37
+    embs = torch.cat([emb, emb[:L2]]).cuda()
+    poss = torch.cat([pos, pos[:, :L2]], dim=1)
+    delta, delta2 = plan["rope_delta"], int(pos[:, :L2].max()) + 1 - L2
+    T = 6
+    out = eng.generate(embs, poss, [L, L2], [delta, delta2], T, stop_ids=[], pad_id=0, want_prefill_logits=True, want_all_logits=True,
+                       early_exit_interval=0)
+    torch.cuda.synchronize()
+    toks = out["tokens"][0].cpu().tolist()
+    with precision.act_bf16(True):
+        _, ref_step, ref_prompt = OL.generate(_cpu(sd), cfg.llm, emb.float(), pos.long(), delta, T, stop_ids=[], forced=toks)
+    _, _, f32_prompt = OL.generate(_cpu(sd), cfg.llm, emb.float(), pos.long(), delta, 1, stop_ids=[], forced=toks[:1])
+    got_all = out["all_logits"][:L].cpu()
+    e_all = nerr(got_all, ref_prompt)
+    e_last = nerr(out["prefill_logits"][0].cpu(), ref_prompt[-1])
+    r_all = rerr(got_all, ref_prompt)
+    tri = (rerr(got_all, f32_prompt), rerr(ref_prompt, f32_prompt))
+    _record("llm_layers", {"all_logits_max": e_all, "last_max": e_last, "all_logits_rms": r_all, "vs_fp32(rms engine, rms bf16oracle)": tri})
+    assert as_accurate_as_bf16_reference(got_all, ref_prompt, f32_prompt), tri
+    # two layers = 2 x 12 storage points + final norm; the logits are a zero-mean vector, so the relative RMS is taken of it whole
+    assert e_all < tol(3) and e_last < tol(3) and r_all < 2.0 * rms_tol(26), (e_all, e_last, r_all)
+    # decode path: the token the engine chose at step s must be the oracle's argmax whenever the oracle's margin is decidable
+    # (6 sigma of the measured per-logit error: the error of the two candidates' difference is sqrt(2) sigma)
+    floor = 6.0 * float((out["prefill_logits"][0].cpu() - ref_prompt[-1]).pow(2).mean().sqrt())
+    top2 = ref_step.topk(2, dim=-1)
+    compared = 0
+    for s in range(T):
+        if float(top2.values[s, 0] - top2.values[s, 1]) > floor:
+            assert toks[s] == int(top2.indices[s, 0]), (s, toks, top2.indices[:, 0].tolist())
+            compared += 1
+    assert compared >= 3, (compared, floor)
+
+
+def test_hfre_c5_geometry_many_boxes_many_images():
+    """C5: 1344x1344 (DaViT maps 336/168/84/42, FPN 384/192/96/48), 300 boxes per image (19 box tiles of 16 per region pass)
+    and 10 images in one call (more than one launch group); fp32 output vs the oracle on a subset of the boxes."""
+    from oracle import hfre as O
+    E, CK, W, P, SY, HF = _mods()
+    g = torch.Generator().manual_seed(21)
+    S, N, B = 1344, 300, 10
+    chans = (256, 512, 1024, 2048)
+    gh = S // 14
+    aux = [torch.randn(S // (4 << i), S // (4 << i), c, generator=g).to(torch.bfloat16) for i, c in enumerate(chans)]
+    pyr = [torch.randn(int(gh * f), int(gh * f), 512, generator=g).to(torch.bfloat16) for f in (4, 2, 1, 0.5)]
+    aux_d = [a.cuda() for a in aux]; pyr_d = [p.cuda() for p in pyr]
+    boxes = [SY.synthetic_boxes(50 + b, S, N if b % 3 else N - 7 * b) for b in range(B)]
+    cfg = HF.HfreConfig(region_dim=5888, vt_mode="fpn")
+    outs = HF.hfre_forward([aux_d] * B, [pyr_d] * B, [b.cuda() for b in boxes], [b.cuda() for b in boxes], cfg, [(gh, gh)] * B)
+    torch.cuda.synchronize()
+    errs = []
+    for b in (0, 4, 9):
+        sel = torch.tensor([0, 1, 17, 150, boxes[b].shape[0] - 1])
+        ref = O.hfre_forward([a.float().permute(2, 0, 1) for a in aux], boxes[b][sel], [p.float().permute(2, 0, 1) for p in pyr],
+                             boxes[b][sel], vt_mode="fpn", region_dim=5888, vt_grid_hw=(gh, gh))
+        errs.append(nerr(outs[b][sel].cpu(), ref))
+    _record("hfre_c5", {"errs": errs})
+    assert max(errs) < TOL_F32, errs
+    # same maps, same boxes at two batch slots -> identical bits (fp32 atomics are order-free per (box, channel) here: one writer per pass)
+    outs2 = HF.hfre_forward([aux_d] * 2, [pyr_d] * 2, [boxes[1].cuda()] * 2, [boxes[1].cuda()] * 2, cfg, [(gh, gh)] * 2)
+    torch.cuda.synchronize()
+    assert nerr(outs2[0].cpu(), outs2[1].cpu()) < 1e-6
+
+
+def test_int_cache_is_trimmed_only_between_forwards():
+    """the handle's cache of device integer tables used to be flushed in the middle of a forward.  Drive it
+    past the trim threshold with many differently sized images; every forward must stay correct (same image -> same bits
+    before and after a trim) and the cache must stay bounded."""
+    import ctypes as C
+    E, CK, W, P, SY, HF = _mods()
+    cfg = E.EngineConfig()
+    cfg.use_davit = cfg.use_llm = False
+    cfg.proj_aux_layers = 0
+    cfg.fpn_out = 0
+    cfg.vit = dict(cfg.vit, depth=2, hidden_size=128, num_heads=4, intermediate_size=256, out_hidden_size=64, fullatt_block_indexes=[1])
+    sd = CK.random_vit(cfg.vit, torch.Generator(device="cuda").manual_seed(1), "cuda")
+    eng = E.Engine(cfg)
+    eng.set_weights(W.prepare_vit(sd, cfg.vit, eng.device))
+    eng.finalize()
+    L = E.lib()
+    L.fo1_int_cache_entries.restype = C.c_int
+    L.fo1_int_cache_entries.argtypes = [C.c_void_p]
+    g = torch.Generator().manual_seed(2)
+    probe = torch.randn(8 * 10, 1176, generator=g)
+    first, _ = eng.vit_forward([probe], [(8, 10)])
+    first = first.clone()
+    seen_max = 0
+    for i in range(40):                                         # 40 distinct grid lists x 7 tables each > the 192-entry threshold
+        gh, gw = 4 + 2 * (i % 7), 6 + 2 * (i // 7)
+        eng.vit_forward([torch.randn(gh * gw, 1176, generator=g), probe], [(gh, gw), (8, 10)])
+        seen_max = max(seen_max, L.fo1_int_cache_entries(eng._h))
+    again, _ = eng.vit_forward([probe], [(8, 10)])
+    torch.cuda.synchronize()
+    assert torch.equal(first, again)
+    assert 0 < seen_max < 192 + 16, seen_max
+
+
+def _mem_available_gb():
+    try:
+        with open("/proc/meminfo") as fh:
+            for line in fh:
+                if line.startswith("MemAvailable"):
+                    return int(line.split()[1]) / (1 << 20)
+    except OSError:
+        pass
+    return 0.0
+
+
+FULL_DEPTH_CASES = [pytest.param(448, 16, 32, id="full_depth_448px"),
+                    pytest.param(896, 64, 24, id="full_depth_c3_896px",
+                                 marks=pytest.mark.skipif(not os.environ.get("FO1_PARITY_C3"),
+                                                          reason="~15 min of fp32 CPU oracle: run with FO1_PARITY_C3=1 (result committed in profiles/)"))]
+
+
+@pytest.mark.parametrize("S,n_boxes,T", FULL_DEPTH_CASES)
+def test_full_depth_sample_drift_and_token_ids(S, n_boxes, T):
+    """ONE sample at FULL depth -- ViT 32 blocks, DaViT 1/1/9/1, SimpleFPN, HFRE, projector, 36-layer 3B decoder, real vocabulary
+    -- on the engine vs the whole oracle pipeline (bf16 storage points), with the drift printed stage by stage; then T greedy
+    tokens, each checked against the oracle teacher-forced on the engine's own prefix: ids must be equal wherever the oracle's
+    top-1 / top-2 margin is decidable, and at least 8 must be decidable.  The 896 px / 64 box case is the benchmarked C3
+    sample (opt-in: the fp32 oracle needs a quarter of an hour of host time); the 448 px case runs by default."""
+    if _mem_available_gb() < 60:
+        pytest.skip("needs ~50 GB of host memory for the fp32 oracle weights")
+    from oracle import llm as OL, pipeline as OP, precision
+    E, CK, W, P, SY, HF = _mods()
+    cfg = E.EngineConfig()
+    sds = CK.random_state_dicts(cfg, "cuda", 0)
+    eng = CK.load_engine(cfg, sds)
+    sds_cpu = {k: _cpu(v) for k, v in sds.items()}
+    del sds
+    torch.cuda.empty_cache()
+    s = SY.synthetic_sample(0, S, n_boxes)
+    pipe = P.Fo1Pipeline(eng)
+    dsm = P.SampleInputs(s.input_ids, s.pixel_values.cuda(), s.grid_hw, s.image_aux.cuda(), s.boxes.cuda())
+    stages = pipe.encode_stages([dsm])
+    out = pipe.generate([dsm], T, stop_ids=[], early_exit_interval=0, want_prefill_logits=True)
+    torch.cuda.synchronize()
+    toks = out["tokens"][0].cpu().tolist()
+    torch.set_num_threads(min(os.cpu_count() or 8, 64))
+    with precision.act_bf16(True), torch.no_grad():
+        ref = OP.run_sample(sds_cpu, cfg.vit, cfg.davit, cfg.llm, input_ids=s.input_ids, pixel_values=s.pixel_values, grid_hw=s.grid_hw,
+                            image_aux=s.image_aux, boxes=s.boxes, region_dim=cfg.region_dim, max_new_tokens=T, forced=toks, keep_stages=True)
+    with torch.no_grad():      # the fp32 reference (what tests/golden pins the oracle to): the yardstick of check (A)
+        f32 = OP.run_sample(sds_cpu, cfg.vit, cfg.davit, cfg.llm, input_ids=s.input_ids, pixel_values=s.pixel_values, grid_hw=s.grid_hw,
+                            image_aux=s.image_aux, boxes=s.boxes, region_dim=cfg.region_dim, max_new_tokens=1, forced=toks[:1], keep_stages=True,
+                            round_towers=False)
+    gh, gw = s.grid_hw
+    f32_of = {"vit_merged": f32["image_features"], "region_features": f32["region_features"], "region_tokens": f32["region_tokens"],
+              "prompt_last_logits": f32["prompt_last_logits"]}
+    for i in range(4):
+        f32_of[f"vit_tap{i}"] = f32["taps"][i]; f32_of[f"davit_stage{i}"] = f32["davit"][i]; f32_of[f"fpn_level{i}"] = f32["fpn"][i]
+    pairs = {}
+    for i, t in enumerate(ref["taps"]):
+        pairs[f"vit_tap{i}"] = (stages["taps"][i].reshape(gh, gw, -1).cpu(), t)
+    pairs["vit_merged"] = (stages["image_features"].cpu(), ref["image_features"])
+    for i, t in enumerate(ref["davit"]):
+        pairs[f"davit_stage{i}"] = (stages["davit"][i][0].cpu(), t)
+    for i, t in enumerate(ref["fpn"]):
+        pairs[f"fpn_level{i}"] = (stages["fpn"][i][0].cpu(), t)
+    pairs["region_features"] = (stages["region_f32"][0].cpu(), ref["region_features"])
+    pairs["region_tokens"] = (stages["region_tokens"][0].cpu(), ref["region_tokens"])
+    pairs["prompt_last_logits"] = (out["prefill_logits"][0].cpu(), ref["prompt_last_logits"])
+    drift = {k: {"max": nerr(g, r), "rms": rerr(g, r), "rms_engine_vs_fp32": rerr(g, f32_of[k]), "rms_bf16oracle_vs_fp32": rerr(r, f32_of[k])}
+             for k, (g, r) in pairs.items()}
+    d = out["prefill_logits"][0].cpu() - ref["prompt_last_logits"]
+    floor = 6.0 * float(d.pow(2).mean().sqrt())          # 6 sigma of the per-logit error (the difference of two logits carries sqrt(2) sigma)
+    top2 = ref["step_logits"].topk(2, dim=-1)
+    compared, mismatched = 0, []
+    for st in range(len(toks)):
+        if float(top2.values[st, 0] - top2.values[st, 1]) > floor:
+            compared += 1
+            if toks[st] != int(top2.indices[st, 0]):
+                mismatched.append(st)
+    drift["token_ids"] = {"steps": len(toks), "decidable": compared, "mismatched": mismatched, "margin_floor": floor,
+                          "logit_err_max": float(d.abs().max()), "logit_range": float(ref["prompt_last_logits"].abs().max())}
+    print("full-depth drift:", json.dumps(drift, indent=1))
+    _record(f"full_depth_{S}", drift)
+    assert out["prompt_lens"][0] == ref["prompt_len"] == 44 + 2 * n_boxes - 1 + gh * gw // 4
+    # (A) at every stage: the engine sits as close to the fp32 reference as the reference's own bf16 path does
+    for k, v in drift.items():
+        if k != "token_ids":
+            assert v["rms_engine_vs_fp32"] <= 1.25 * v["rms_bf16oracle_vs_fp32"] + 5e-4, (k, v)
+    # (B) / (C) depth-compounded: ~10 bf16 storage points per block, flips add like a random walk over 32 / 12 / 36 blocks
+    mx = lambda k: drift[k]["max"]
+    rm = lambda k: drift[k]["rms"]
+    for i in range(4):
+        assert mx(f"vit_tap{i}") < 4e-2 and rm(f"vit_tap{i}") < rms_tol(10 * 8 * (i + 1)), drift
+        assert mx(f"davit_stage{i}") < 4e-2 and mx(f"fpn_level{i}") < 4e-2, drift
+    assert rm("vit_merged") < rms_tol(330) and mx("vit_merged") < 4e-2, drift
+    assert max(rm(f"davit_stage{i}") for i in range(4)) < rms_tol(250) and max(rm(f"fpn_level{i}") for i in range(4)) < rms_tol(340), drift
+    assert mx("region_features") < 2e-2 and mx("region_tokens") < 2e-2, drift
+    assert mx("prompt_last_logits") < 6e-2 and rm("prompt_last_logits") < 2.0 * rms_tol(36 * 12 + 330), drift
+    assert compared >= 8 and not mismatched, drift["token_ids"]

@@ -117,72 +117,6 @@ __global__ void __launch_bounds__(256) maxpool2x2_kernel(const bf16* __restrict_
   }
 }
 
-// ---- DaViT channel-group attention (modeling_davit.py:151-172), group width 32 -----------------------------
-// pass 1: G[b][g][c1][c2] += sum_n q[n][c1] * k[n][c2] over a chunk of tokens (fp32 atomics into a zeroed buffer)
-__global__ void __launch_bounds__(256) chanattn_gram_kernel(const bf16* __restrict__ qkv, float* __restrict__ gram, int N, int C,
-                                                            int groups, int chunk) {
-  const int g = blockIdx.x, b = blockIdx.z;
-  const int n0 = blockIdx.y * chunk, n1 = min(N, n0 + chunk);
-  __shared__ float qs[32][33], ks[32][33];
-  const int c1 = threadIdx.x >> 3, c2b = (threadIdx.x & 7) * 4;
-  float acc[4] = {0, 0, 0, 0};
-  const bf16* base = qkv + (long long)b * N * 3 * C;
-  for (int n = n0; n < n1; n += 32) {
-    for (int i = threadIdx.x; i < 32 * 32; i += 256) {
-      const int tk = i >> 5, c = i & 31;
-      float qv = 0.f, kv = 0.f;
-      if (n + tk < n1) {
-        const bf16* row = base + (long long)(n + tk) * 3 * C + g * 32 + c;
-        qv = __bfloat162float(row[0]);
-        kv = __bfloat162float(row[C]);
-      }
-      qs[tk][c] = qv; ks[tk][c] = kv;
-    }
-    __syncthreads();
-#pragma unroll 8
-    for (int tk = 0; tk < 32; ++tk) {
-      const float qv = qs[tk][c1];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) acc[j] = fmaf(qv, ks[tk][c2b + j], acc[j]);
-    }
-    __syncthreads();
-  }
-  float* gp = gram + (((long long)b * groups + g) * 32 + c1) * 32 + c2b;
-#pragma unroll
-  for (int j = 0; j < 4; ++j) atomicAdd(gp + j, acc[j]);
-}
-
-// pass 2: A = softmax_c2(G * N^-0.5); out[n][g*32+c1] = sum_c2 A[c1][c2] v[n][g*32+c2]
-__global__ void __launch_bounds__(256) chanattn_apply_kernel(const bf16* __restrict__ qkv, const float* __restrict__ gram,
-                                                             bf16* __restrict__ out, int N, int C, int groups, int chunk, float scale) {
-  const int g = blockIdx.x, b = blockIdx.z;
-  const int n0 = blockIdx.y * chunk, n1 = min(N, n0 + chunk);
-  __shared__ float A[32][33];
-  const float* gp = gram + ((long long)b * groups + g) * 1024;
-  for (int i = threadIdx.x; i < 1024; i += 256) A[i >> 5][i & 31] = gp[i] * scale;
-  __syncthreads();
-  if (threadIdx.x < 32) {
-    const int r = threadIdx.x;
-    float m = -INFINITY;
-    for (int c = 0; c < 32; ++c) m = fmaxf(m, A[r][c]);
-    float s = 0.f;
-    for (int c = 0; c < 32; ++c) { const float e = __expf(A[r][c] - m); A[r][c] = e; s += e; }
-    const float inv = 1.0f / s;
-    for (int c = 0; c < 32; ++c) A[r][c] *= inv;
-  }
-  __syncthreads();
-  const int c1 = threadIdx.x & 31;
-  for (int n = n0 + (threadIdx.x >> 5); n < n1; n += 8) {
-    const bf16* vrow = qkv + ((long long)b * N + n) * 3 * C + 2 * C + g * 32;
-    const float vv = __bfloat162float(vrow[c1]);
-    float acc = 0.f;
-#pragma unroll
-    for (int c2 = 0; c2 < 32; ++c2) acc = fmaf(A[c1][c2], __shfl_sync(0xffffffffu, vv, c2), acc);
-    out[((long long)b * N + n) * C + g * 32 + c1] = __float2bfloat16_rn(acc);
-  }
-}
-
-
 // DaViT window attention bookkeeping (modeling_davit.py:246-280): zero-pad H, W up to multiples of the
 // window AFTER the LayerNorm, partition into ws x ws windows (rows of one window contiguous) ...
 __global__ void __launch_bounds__(256) window_partition_kernel(const bf16* __restrict__ x, bf16* __restrict__ dst, int B, int H, int W,
@@ -262,19 +196,6 @@ int maxpool2x2(const bf16* x, bf16* y, int B, int H, int W, int C, cudaStream_t 
   return FO1_OK;
 }
 // qkv: [B][N][3C] (q | k | v, each group-major with 32 channels per group); gram: [B][groups][32][32] fp32 scratch
-int channel_attention(const bf16* qkv, float* gram, bf16* out, int B, int N, int C, int groups, cudaStream_t s) {
-  FO1_CHECK_ARG(groups * 32 == C, "channel_attention: needs 32 channels per group (C=%d groups=%d)", C, groups);
-  if (B == 0 || N == 0) return FO1_OK;
-  FO1_CUDA(cudaMemsetAsync(gram, 0, (size_t)B * groups * 1024 * sizeof(float), s));
-  const int chunk = 1024;
-  dim3 grid(groups, ceil_div(N, chunk), B);
-  chanattn_gram_kernel<<<grid, 256, 0, s>>>(qkv, gram, N, C, groups, chunk);
-  FO1_LAUNCH_CHECK();
-  chanattn_apply_kernel<<<grid, 256, 0, s>>>(qkv, gram, out, N, C, groups, chunk, 1.0f / sqrtf((float)N));
-  FO1_LAUNCH_CHECK();
-  return FO1_OK;
-}
-
 int window_partition(const bf16* x, bf16* dst, int B, int H, int W, int C, int ws, cudaStream_t s) {
   FO1_CHECK_ARG(C % 8 == 0 && ws > 0, "window_partition: C=%d ws=%d", C, ws);
   const int nwh = ceil_div(H, ws), nww = ceil_div(W, ws);

@@ -72,9 +72,9 @@ static int davit_forward_impl(Model* m, const float* const* images, int H0, int 
   bf16* qkv = A.alloc<bf16>(std::max(max_wtc, max_tc) * 3);
   bf16* hb = A.alloc<bf16>(max_tc * 4);
   bf16* col = A.alloc<bf16>(max_col);
-  int max_groups = 0;
-  for (int i = 0; i < 4; ++i) max_groups = std::max(max_groups, c.davit_groups[i]);
-  float* gram = A.alloc<float>((size_t)B * max_groups * 1024);
+  size_t gram_floats = 0;                  // partial Gram matrices of the channel attention (per token chunk, summed in fixed order)
+  for (int i = 0; i < 4; ++i) gram_floats = std::max(gram_floats, channel_attention_ws_floats(B, Hs[i] * Ws[i], c.davit_dims[i]));
+  float* gram = A.alloc<float>(gram_floats);
 
   bf16* x = xa;      // current token map
   bf16* xalt = xb;

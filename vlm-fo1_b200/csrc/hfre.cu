@@ -10,10 +10,13 @@
 // mean_{7x7}(roi_align(U))[c] = a^T U[c] b with 1-D weight vectors that depend only on the box, and
 // because the up-sampling is linear and separable too, U[c] = Mh L[c] Mw^T, the whole thing is
 //        out[c] = (Mh^T a)^T L[c] (Mw^T b)
-// over the NATIVE-resolution bf16 level L (channels-last).  Kernel 1 builds the two weight vectors
-// per (box, level, axis) with torchvision's exact per-sample rules; kernel 3 is a pure memory-bound
-// weighted window sum: coalesced 16-byte channel-vector loads, fp32 accumulation, shared-memory
-// cross-warp reduction.  No tensor cores: 2 FLOP per loaded bf16 element.
+// over the NATIVE-resolution bf16 level L (channels-last).  hfre_axis_weights_kernel builds the two weight vectors
+// per (box, level, axis) with torchvision's exact per-sample rules.  Three interchangeable reductions follow
+// (fo1_hfre_params.algo): the per-box gather (coalesced 16-byte channel vectors, fp32 FMA), the SIMT map sweep (every
+// cell read once, FMA per covering box) and -- the default above a handful of boxes -- the map sweep whose row sums
+// run as mma.sync m16n8k16 tiles (boxes x cells, column weights split hi + lo in bf16): the bytes are still read
+// exactly once with coalesced accesses, the legacy tensor path only replaces the FMA issue slots that capped the SIMT
+// sweep at 10 % of the HBM roofline.
 #include "common.cuh"
 
 namespace fo1 {

@@ -77,7 +77,9 @@ int dwconv3x3_residual(const bf16* x, const bf16* w9, const bf16* bias, bf16* y,
 int im2col3x3(const bf16* x, bf16* col, int B, int H, int W, int C, int stride, cudaStream_t s);
 int im2col_stem(const float* img, bf16* col, int H, int W, int kpad, cudaStream_t s);
 int maxpool2x2(const bf16* x, bf16* y, int B, int H, int W, int C, cudaStream_t s);
-int channel_attention(const bf16* qkv, float* gram, bf16* out, int B, int N, int C, int groups, cudaStream_t s);
+// ---- chanattn_tc.cu: DaViT channel-group attention as two tcgen05 contractions; ws = channel_attention_ws_floats() floats
+size_t channel_attention_ws_floats(int B, int N, int C);
+int channel_attention(const bf16* qkv, float* ws, bf16* out, int B, int N, int C, int groups, cudaStream_t s);
 int window_partition(const bf16* x, bf16* dst, int B, int H, int W, int C, int ws, cudaStream_t s);
 int window_reverse_add(const bf16* x, const bf16* p, bf16* y, int B, int H, int W, int C, int ws, cudaStream_t s);
 int pixel_shuffle2x(const bf16* src, bf16* dst, int B, int H, int W, int C, cudaStream_t s);

@@ -275,3 +275,75 @@ def _engine_generate(self, inputs_embeds: torch.Tensor, position_ids: torch.Tens
 
 Engine.build_embeds = _engine_build_embeds
 Engine.generate = _engine_generate
+
+
+def splice_plan_batch(prompts: Sequence[Sequence[int]], image_grids: Sequence[Sequence[Tuple[int, int]]], n_regions: Sequence[int], device,
+                      image_token_id: int = 151655, video_token_id: int = 151656, vision_start_token_id: int = 151652, merge: int = 2,
+                      image_placeholder: int = -200, region_placeholder: int = -300):
+    """The splice + M-RoPE bookkeeping of a whole batch in ONE launch on the device (fo1_splice_plan_batch).  Per sample b:
+    ``prompts[b]`` ids with placeholders, ``image_grids[b]`` its images' (gh, gw), ``n_regions[b]`` region rows.  Image rows /
+    region rows of the batch are assumed packed back to back in sample order (what Fo1Pipeline.encode produces).
+    -> dict(kind, index, new_ids int32 [T]; position_ids int32 [3, T]; rope_delta int32 [B]) on the device, lens (host list)."""
+    import numpy as np
+    B = len(prompts)
+    unit = merge * merge
+    id_off = np.zeros(B + 1, np.int32); img_off = np.zeros(B + 1, np.int32); out_off = np.zeros(B + 1, np.int32)
+    img_row = np.zeros(B, np.int32); reg_row = np.zeros(B, np.int32)
+    rows_i = rows_r = 0
+    for b in range(B):
+        toks = sum(gh * gw // unit for gh, gw in image_grids[b])
+        n_img_ph = sum(1 for t in prompts[b] if t == image_placeholder)
+        id_off[b + 1] = id_off[b] + len(prompts[b]); img_off[b + 1] = img_off[b] + len(image_grids[b])
+        # every image placeholder expands to its image's rows; more placeholders than images is reported per sample by the kernel
+        exp = sum(gh * gw // unit for gh, gw in list(image_grids[b])[:n_img_ph])
+        out_off[b + 1] = out_off[b] + len(prompts[b]) - min(n_img_ph, len(image_grids[b])) + exp
+        img_row[b] = rows_i; reg_row[b] = rows_r
+        rows_i += toks; rows_r += int(n_regions[b])
+    T = int(out_off[B])
+    host = np.concatenate([np.asarray([t for p in prompts for t in p], np.int32), id_off,
+                           np.asarray([x for g in image_grids for hw in g for x in hw], np.int32).reshape(-1), img_off,
+                           np.asarray(n_regions, np.int32), out_off, img_row, reg_row])
+    d = torch.from_numpy(host).to(device, non_blocking=True)      # one H2D for every table
+    cuts = np.cumsum([0, int(id_off[B]), B + 1, 2 * int(img_off[B]), B + 1, B, B + 1, B, B])
+    v = [d[cuts[i]:cuts[i + 1]] for i in range(8)]
+    out = torch.empty(6 * T + 2 * B, dtype=torch.int32, device=device)
+    new_ids, kind, index, pos = out[:T], out[T:2 * T], out[2 * T:3 * T], out[3 * T:6 * T].view(3, T)
+    delta, status = out[6 * T:6 * T + B], out[6 * T + B:]
+    cfg = SpliceCfgC(image_token_id, video_token_id, vision_start_token_id, merge, image_placeholder, region_placeholder)
+    L = lib()
+    L.fo1_splice_plan_batch.restype = C.c_int
+    L.fo1_splice_plan_batch.argtypes = [C.c_void_p] * 8 + [C.c_int32, C.c_int64, C.POINTER(SpliceCfgC)] + [C.c_void_p] * 7
+    P = lambda t: C.c_void_p(t.data_ptr())
+    check(L.fo1_splice_plan_batch(P(v[0]), P(v[1]), P(v[2]), P(v[3]), P(v[4]), P(v[5]), P(v[6]), P(v[7]), B, T, C.byref(cfg),
+                                  P(new_ids), P(kind), P(index), P(pos), P(delta), P(status), _stream()), "fo1_splice_plan_batch")
+    return dict(new_ids=new_ids, kind=kind, index=index, position_ids=pos, rope_delta=delta, status=status,
+                lens=[int(out_off[b + 1] - out_off[b]) for b in range(B)])
+
+
+def parse_predictions(tokens: torch.Tensor, lens: torch.Tensor, ground_ids: Tuple[int, int], objects_ids: Tuple[int, int],
+                      region_ids: Sequence[int], newline_token_ids: Sequence[int] = (), vocab: int = 0, max_records: int = 256):
+    """fo1_parse_predictions over a batch of decoded ids (device int32 [B, T], lens [B]) -> per sample list of
+    (label first token, label end token, N or -1)."""
+    import numpy as np
+    B, T = tokens.shape
+    dev = tokens.device
+    rid = torch.tensor(list(region_ids), dtype=torch.int32, device=dev)
+    bm = None
+    if vocab > 0 and len(newline_token_ids):
+        words = np.zeros((vocab + 31) // 32, np.uint32)
+        for t in newline_token_ids:
+            words[t >> 5] |= np.uint32(1 << (t & 31))
+        bm = torch.from_numpy(words.view(np.int32)).to(dev)
+    rec = torch.empty((B, max_records, 3), dtype=torch.int32, device=dev)
+    cnt = torch.zeros((B,), dtype=torch.int32, device=dev)
+    L = lib()
+    L.fo1_parse_predictions.restype = C.c_int
+    L.fo1_parse_predictions.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p,
+                                        C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p]
+    tokens = tokens.contiguous(); lens = lens.to(torch.int32).contiguous()
+    check(L.fo1_parse_predictions(C.c_void_p(tokens.data_ptr()), tokens.stride(0), C.c_void_p(lens.data_ptr()), B, ground_ids[0], ground_ids[1],
+                                  objects_ids[0], objects_ids[1], C.c_void_p(rid.data_ptr()), rid.numel(),
+                                  C.c_void_p(bm.data_ptr()) if bm is not None else None, vocab, C.c_void_p(rec.data_ptr()), max_records,
+                                  C.c_void_p(cnt.data_ptr()), _stream()), "fo1_parse_predictions")
+    rec_h, cnt_h = rec.cpu().numpy(), cnt.cpu().numpy()
+    return [[tuple(int(x) for x in rec_h[b, i]) for i in range(int(cnt_h[b]))] for b in range(B)]

@@ -110,3 +110,22 @@ def decode_attention(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tens
     d.out, d.ldo, d.workspace, d.workspace_bytes = out.data_ptr(), out.stride(0), ws.data_ptr(), ws.numel()
     check(L.fo1_decode_attention(C.byref(d), C.c_void_p(_stream())), "fo1_decode_attention")
     return out
+
+
+def channel_attention(qkv: torch.Tensor, groups: int) -> torch.Tensor:
+    """DaViT channel-group attention: qkv bf16 [B, N, 3C] -> bf16 [B, N, C] (fo1_channel_attention)."""
+    _require_cuda(qkv)
+    assert qkv.dtype == torch.bfloat16 and qkv.dim() == 3 and qkv.is_contiguous() and qkv.shape[2] % 3 == 0
+    B, N, C3 = qkv.shape
+    Cc = C3 // 3
+    out = torch.empty((B, N, Cc), dtype=torch.bfloat16, device=qkv.device)
+    L = lib()
+    L.fo1_channel_attention_workspace_bytes.restype = C.c_size_t
+    L.fo1_channel_attention_workspace_bytes.argtypes = [C.c_int32, C.c_int32, C.c_int32]
+    L.fo1_channel_attention.restype = C.c_int
+    L.fo1_channel_attention.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    need = L.fo1_channel_attention_workspace_bytes(B, N, Cc)
+    ws = torch.empty(max(need, 16), dtype=torch.uint8, device=qkv.device)
+    check(L.fo1_channel_attention(C.c_void_p(qkv.data_ptr()), B, N, Cc, groups, C.c_void_p(out.data_ptr()), C.c_void_p(ws.data_ptr()), ws.numel(),
+                                  C.c_void_p(_stream())), "fo1_channel_attention")
+    return out

@@ -21,10 +21,11 @@ from .engine import Engine, splice_plan
 @dataclass
 class SampleInputs:
     input_ids: Sequence[int]            # prompt ids with -200 (image) / -300 (region) placeholders (mm_utils.py:83-135)
-    pixel_values: torch.Tensor          # fp32 [gh*gw, 1176]  (Qwen2VLImageProcessor)
-    grid_hw: Tuple[int, int]
-    image_aux: torch.Tensor             # fp32 [3, H, W]      (CLIPImageProcessor, 'dynamic' mode)
+    pixel_values: Optional[torch.Tensor]  # fp32 [gh*gw, 1176]  (Qwen2VLImageProcessor); None with image_u8
+    grid_hw: Optional[Tuple[int, int]]
+    image_aux: Optional[torch.Tensor]   # fp32 [3, H, W]      (CLIPImageProcessor, 'dynamic' mode); None with image_u8
     boxes: torch.Tensor                 # fp32 [N, 4] xyxy in aux-tensor pixels
+    image_u8: Optional[torch.Tensor] = None   # uint8 [H, W, 3] RGB: pre-processed on the device by Fo1Pipeline.preprocess()
 
 
 class Fo1Pipeline:
@@ -37,6 +38,8 @@ class Fo1Pipeline:
         self.ws = HF.HfreWorkspace()
         self.profile_stages = False          # when set, CUDA events bracket every stage (read with stage_ms())
         self._marks = []
+        self._keep_stages = None
+        self._pre = None
 
     def _mark(self, name: str) -> None:
         if self.profile_stages:
@@ -52,14 +55,36 @@ class Fo1Pipeline:
             out[n1] = out.get(n1, 0.0) + e0.elapsed_time(e1)
         return out
 
+    # ---- device-side pre-processing -----------------------------------------------
+    def preprocess(self, samples: Sequence[SampleInputs]) -> List[SampleInputs]:
+        """Samples that carry a uint8 image instead of the processors' tensors get them from the GPU (both towers;
+        the aux tower in 'dynamic' mode, as the released checkpoint is configured)."""
+        if all(s.image_u8 is None for s in samples):
+            return list(samples)
+        if self._pre is None:
+            from .preprocess import DevicePreprocessor
+            v = self.eng.cfg.vit
+            self._pre = DevicePreprocessor(self.eng.device, v["patch_size"], v["spatial_merge_size"], v["temporal_patch_size"])
+        out = []
+        for s in samples:
+            if s.image_u8 is None:
+                out.append(s); continue
+            img = s.image_u8.to(self.eng.device, non_blocking=True)
+            px, grid = self._pre.primary(img)
+            out.append(SampleInputs(s.input_ids, px, grid, self._pre.aux(img, 0), s.boxes))
+        return out
+
     # ---- vision side -------------------------------------------------------------------------------------
     def encode(self, samples: Sequence[SampleInputs]):
         """-> (img_feats [sum merged tokens, hidden] bf16, per-sample row offsets, region tokens list of [N_b, hidden] bf16,
         region features fp32 list)."""
         eng, dev = self.eng, self.eng.device
-        grids = [s.grid_hw for s in samples]
         self._marks = []
         self._mark("start")
+        samples = self.preprocess(samples)
+        if any(s.image_u8 is not None for s in samples) or self._pre is not None:
+            self._mark("preprocess")
+        grids = [s.grid_hw for s in samples]
         feats, taps = eng.vit_forward([s.pixel_values for s in samples], grids)
         feats = eng.image_project(feats)                                             # mm_projector (:58-66); identity for the released checkpoint
         self._mark("vit")
@@ -110,12 +135,31 @@ class Fo1Pipeline:
         region_tokens = list(torch.split(tokens, counts, 0))
         unit = eng.cfg.vit["spatial_merge_size"] ** 2
         img_off = np.cumsum([0] + [gh * gw // unit for gh, gw in grids])
+        if self._keep_stages is not None:
+            self._keep_stages.update(image_features=feats, taps=taps, davit=aux, fpn=vt if self.vt_mode == "fpn" else None,
+                                     region_f32=region_f32, region_tokens=region_tokens)
         return feats, img_off, region_tokens, region_f32
+
+    def encode_stages(self, samples: Sequence[SampleInputs]) -> dict:
+        """encode() that also hands back every intermediate map for the stage-drift test: 'taps' (list over the tap layers of
+        [sum gh*gw, hidden]), 'davit' / 'fpn' as [level][image] maps, 'image_features', 'region_f32', 'region_tokens'."""
+        self._keep_stages = {}
+        try:
+            self.encode(samples)
+            out = self._keep_stages
+        finally:
+            self._keep_stages = None
+        B = len(samples)
+        out["davit"] = [[out["davit"][b][l] for b in range(B)] for l in range(4)]
+        if out["fpn"] is not None:
+            out["fpn"] = [[out["fpn"][b][l] for b in range(B)] for l in range(4)]
+        return out
 
     # ---- language side -----------------------------------------------------------------------------------
     def generate(self, samples: Sequence[SampleInputs], max_new_tokens: int, stop_ids: Sequence[int], pad_id: int = 151643,
                  early_exit_interval: int = 8, want_prefill_logits: bool = False):
         eng, dev = self.eng, self.eng.device
+        samples = self.preprocess(samples)           # uint8 images -> the towers' input tensors, on the device
         feats, img_off, region_tokens, _ = self.encode(samples)
         kinds, idxs, poss, lens, deltas = [], [], [], [], []
         reg_off = 0

@@ -69,3 +69,12 @@ def synthetic_sample(i: int, S: int, n_boxes: int) -> SampleInputs:
 
 def synthetic_batch(start: int, count: int, S: int, n_boxes: int) -> List[SampleInputs]:
     return [synthetic_sample(start + k, S, n_boxes) for k in range(count)]
+
+
+def synthetic_sample_u8(i: int, S: int, n_boxes: int) -> SampleInputs:
+    """The same seeded image / boxes / prompt as synthetic_sample, handed over as the raw uint8 image: the pipeline's device-side
+    pre-processing then does what the two host processors do (incl. the bicubic smart-resize when S is not a multiple of 28)."""
+    rng = np.random.default_rng(1000 + i)
+    img = rng.integers(0, 256, size=(S, S, 3), dtype=np.uint8)
+    return SampleInputs(input_ids=synthetic_prompt(i, n_boxes), pixel_values=None, grid_hw=None, image_aux=None,
+                        boxes=synthetic_boxes(i, S, n_boxes), image_u8=torch.from_numpy(img))

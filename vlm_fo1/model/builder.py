@@ -120,6 +120,8 @@ def load_pretrained_model(model_path, load_8bit=False, load_4bit=False, device="
     eos = json.load(open(gen_path)).get("eos_token_id", []) if os.path.exists(gen_path) else g("eos_token_id", [])
     stop_ids = [int(e) for e in (eos if isinstance(eos, list) else [eos]) if e is not None]
     model = Fo1ForCausalLM(engine, config, "fpn" if use_fpn else "concat", stop_ids, roi_size=roi_size, apply_pos_embed=apply_pos)
-    primary = PrimaryImageProcessor(cfg.vit["patch_size"], cfg.vit["spatial_merge_size"], cfg.vit["temporal_patch_size"], 56 * 56, 2048 * 2048)
-    aux = AuxImageProcessor(int(g("aux_image_size", 768)), str(g("aux_image_aspect_ratio", "squash")))
+    # the processors run on the engine's GPU (uint8 over PCIe; bit-identical to the host processors); FO1_HOST_PREPROCESS=1 keeps PIL / numpy
+    pdev = None if os.environ.get("FO1_HOST_PREPROCESS") else engine.device
+    primary = PrimaryImageProcessor(cfg.vit["patch_size"], cfg.vit["spatial_merge_size"], cfg.vit["temporal_patch_size"], 56 * 56, 2048 * 2048, device=pdev)
+    aux = AuxImageProcessor(int(g("aux_image_size", 768)), str(g("aux_image_aspect_ratio", "squash")), device=pdev)
     return tokenizer, model, (primary, aux)

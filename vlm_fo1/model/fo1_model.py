@@ -34,9 +34,9 @@ class Fo1ForCausalLM:
     def get_model(self):
         return self
 
-    @torch.no_grad()
-    def generate(self, inputs=None, images=None, images_aux=None, image_grid_thws=None, bbox_list=None, do_sample=False, temperature=0.0,
-                 max_new_tokens=512, streamer=None, top_p=1.0, use_cache=True, stopping_criteria=None, pad_token_id=None, **kwargs):
+    def _sample(self, inputs=None, images=None, images_aux=None, image_grid_thws=None, bbox_list=None, do_sample=False, temperature=0.0,
+                stopping_criteria=None, **kwargs):
+        """One ``prepare_inputs`` dict -> (SampleInputs, stop ids): the argument checks of the reference's call contract."""
         if do_sample or (temperature or 0.0) != 0.0:
             raise NotImplementedError("the fo1-b200 engine decodes greedily (the reference's callers all pass temperature=0.0)")
         if inputs is None or inputs.dim() != 2 or inputs.shape[0] != 1:
@@ -60,6 +60,12 @@ class Fo1ForCausalLM:
                     # the device-side stop list, and silently ignoring it would change where generation ends
                     raise NotImplementedError(f"multi-token stop keyword {kw.tolist()} is not supported by the device-side stop test "
                                               "(every caller in the reference stops on the single token <|im_end|>)")
+        return sample, stop
+
+    @torch.no_grad()
+    def generate(self, inputs=None, images=None, images_aux=None, image_grid_thws=None, bbox_list=None, do_sample=False, temperature=0.0,
+                 max_new_tokens=512, streamer=None, top_p=1.0, use_cache=True, stopping_criteria=None, pad_token_id=None, **kwargs):
+        sample, stop = self._sample(inputs, images, images_aux, image_grid_thws, bbox_list, do_sample, temperature, stopping_criteria)
         pad = pad_token_id if pad_token_id is not None else (stop[0] if stop else 0)
         out = self.pipeline.generate([sample], int(max_new_tokens), sorted(set(stop)), pad_id=int(pad), early_exit_interval=8)
         n = int(out["lens"][0].item())
@@ -72,3 +78,24 @@ class Fo1ForCausalLM:
             streamer.put(new.cpu())
             streamer.end()
         return full
+
+    @torch.no_grad()
+    def generate_batch(self, batch, max_new_tokens=None):
+        """``batch``: a list of the dicts ``prepare_inputs`` returns (one sample each, mm_utils.py:640-654).  All samples run as ONE
+        packed batch through the engine (what the reference's evaluation loops do one image at a time, eval_coco.py:36-88).
+        -> list of LongTensor [1, P_b + T_b], each exactly what ``generate(**batch[b])`` returns."""
+        if not batch:
+            return []
+        samples, stops = zip(*(self._sample(**{k: v for k, v in kw.items() if k in (
+            "inputs", "images", "images_aux", "image_grid_thws", "bbox_list", "do_sample", "temperature", "stopping_criteria")}) for kw in batch))
+        stop = sorted(set(x for s in stops for x in s))
+        T = int(max_new_tokens if max_new_tokens is not None else max(int(kw.get("max_new_tokens", 512)) for kw in batch))
+        pads = [kw.get("pad_token_id") for kw in batch]
+        pad = pads[0] if pads[0] is not None else (stop[0] if stop else 0)
+        out = self.pipeline.generate(list(samples), T, stop, pad_id=int(pad), early_exit_interval=8)
+        lens = out["lens"].cpu().tolist()
+        res = []
+        for b, kw in enumerate(batch):
+            new = out["tokens"][b, :lens[b]].to(torch.long)
+            res.append(torch.cat([kw["inputs"][0].to(new.device), new]).unsqueeze(0))
+        return res

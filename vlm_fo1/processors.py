@@ -35,16 +35,29 @@ def smart_resize(height: int, width: int, factor: int = 28, min_pixels: int = 56
     return h_bar, w_bar
 
 
+def _device_preprocessor(device, *args):
+    """``device`` given -> the CUDA pre-processing of the engine (fo1_preprocess_*); None -> the PIL / numpy host path."""
+    if device is None:
+        return None
+    from importlib import import_module
+    import fo1_b200  # noqa: F401
+    return import_module("vlm-fo1_b200.preprocess").DevicePreprocessor(device, *args)
+
+
 class PrimaryImageProcessor:
     """-> {'pixel_values': fp32 [gh*gw, 3*2*14*14], 'image_grid_thw': int64 [1, 3]}"""
 
     def __init__(self, patch_size: int = 14, merge_size: int = 2, temporal_patch_size: int = 2, min_pixels: int = 56 * 56,
-                 max_pixels: int = 2048 * 2048):
+                 max_pixels: int = 2048 * 2048, device=None):
         self.patch_size, self.merge_size, self.temporal_patch_size = patch_size, merge_size, temporal_patch_size
         self.min_pixels, self.max_pixels = min_pixels, max_pixels
+        self._dev = _device_preprocessor(device, patch_size, merge_size, temporal_patch_size, min_pixels, max_pixels)
 
     def preprocess(self, images, videos=None, return_tensors="pt", **kwargs) -> Dict[str, torch.Tensor]:
         img = images.convert("RGB")
+        if self._dev is not None:     # uint8 over PCIe, resize / normalise / patchify on the GPU (bit-identical, tests/test_gpu_preprocess.py)
+            px, (gh, gw) = self._dev.primary(torch.from_numpy(np.asarray(img)).to(self._dev.device))
+            return {"pixel_values": px, "image_grid_thw": torch.tensor([[1, gh, gw]], dtype=torch.int64)}
         p, m, t = self.patch_size, self.merge_size, self.temporal_patch_size
         h, w = smart_resize(img.height, img.width, p * m, self.min_pixels, self.max_pixels)
         if (h, w) != (img.height, img.width):
@@ -62,12 +75,16 @@ class PrimaryImageProcessor:
 class AuxImageProcessor:
     """-> {'pixel_values': fp32 [1, 3, H, W]}; ``dynamic`` keeps the image size, otherwise a bicubic squash to size x size."""
 
-    def __init__(self, image_size: int = 768, aspect_ratio: str = "squash"):
+    def __init__(self, image_size: int = 768, aspect_ratio: str = "squash", device=None):
         self.image_size, self.aspect_ratio = image_size, aspect_ratio
         self.do_resize = aspect_ratio != "dynamic"
+        self._dev = _device_preprocessor(device)
 
     def preprocess(self, images, return_tensors="pt", **kwargs) -> Dict[str, torch.Tensor]:
         img = images.convert("RGB")
+        if self._dev is not None:
+            x = self._dev.aux(torch.from_numpy(np.asarray(img)).to(self._dev.device), self.image_size if self.do_resize else 0)
+            return {"pixel_values": x[None]}
         if self.do_resize and img.size != (self.image_size, self.image_size):
             img = img.resize((self.image_size, self.image_size), Image.Resampling.BICUBIC)
         x = (np.asarray(img, dtype=np.float32) * np.float32(1 / 255) - IMNET_MEAN) / IMNET_STD

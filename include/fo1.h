@@ -339,6 +339,7 @@ typedef struct {
   float* all_logits;              /* optional device fp32 [sum L_b][vocab]: logits at every prompt position */
   int32_t early_exit_interval;    /* host polls "all sequences stopped" every k decode steps (0 = never) */
   int32_t steps_run;              /* out: decode iterations actually executed */
+  const int32_t* rope_deltas_device; /* optional DEVICE [n_seqs] (what fo1_splice_plan_batch wrote); overrides rope_deltas when set */
 } fo1_generate_desc;
 
 /* Prefill + greedy decode (replaces OmChatQwen25VLForCausalLM.forward / HF generate's greedy loop /

@@ -262,10 +262,11 @@ def test_hfre_c5_geometry_many_boxes_many_images():
         errs.append(nerr(outs[b][sel].cpu(), ref))
     _record("hfre_c5", {"errs": errs})
     assert max(errs) < TOL_F32, errs
-    # same maps, same boxes at two batch slots -> identical bits (fp32 atomics are order-free per (box, channel) here: one writer per pass)
+    # same maps, same boxes at two batch slots, and the same call again -> identical bits: the region CTAs' partial sums meet in
+    # 64-bit fixed-point accumulators (integer atomics commute), so the result does not depend on their arrival order
     outs2 = HF.hfre_forward([aux_d] * 2, [pyr_d] * 2, [boxes[1].cuda()] * 2, [boxes[1].cuda()] * 2, cfg, [(gh, gh)] * 2)
     torch.cuda.synchronize()
-    assert nerr(outs2[0].cpu(), outs2[1].cpu()) < 1e-6
+    assert torch.equal(outs2[0], outs2[1]) and torch.equal(outs2[0], outs[1])
 
 
 def test_int_cache_is_trimmed_only_between_forwards():

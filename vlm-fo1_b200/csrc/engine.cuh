@@ -64,8 +64,17 @@ struct FpnW {
   bool ok = false;
 };
 struct ProjW { std::vector<const bf16*> w, b; std::vector<int> in_dim, out_dim; bool ok = false; };
-struct LlmLayerW { const bf16 *ln1, *qkv_w, *qkv_b, *o_w, *ln2, *gateup_w, *down_w; };
-struct LlmW { const bf16 *embed = nullptr, *norm = nullptr, *lm_head = nullptr; std::vector<LlmLayerW> layer; bool ok = false; };
+struct LlmLayerW {
+  const bf16 *ln1, *qkv_w, *qkv_b, *o_w, *ln2, *gateup_w, *down_w;
+  const bf16 *qkv_dec = nullptr, *gu_dec = nullptr;   // decode copies with the RMSNorm gains folded in (persistent decode kernel)
+};
+struct LlmW {
+  const bf16 *embed = nullptr, *norm = nullptr, *lm_head = nullptr, *head_dec = nullptr;
+  std::vector<LlmLayerW> layer;
+  bool ok = false;
+  bool mega_ok = false;        // every decode copy is present: the greedy loop runs as one persistent kernel
+  void* mega_layers = nullptr; // device array of MegaLayer (decode_mega.cuh), owned by llm.cu
+};
 
 struct Model {
   fo1_model_config cfg;

@@ -21,7 +21,7 @@
 
 namespace fo1 {
 
-constexpr int kMaxBatch = 8;           // images per launch (kernel-parameter budget: < 4 KB)
+constexpr int kMaxBatch = 32;          // images per launch: the batch descriptor travels as a kernel parameter (< 32 KB)
 constexpr int kGatherThreads = 256;
 constexpr int kChunk = 256;            // channels per gather block: 32 lanes x 8 bf16 (16 B) each
 constexpr int kRegion = 32;            // sweep: a CTA owns a kRegion x kRegion block of cells of one level
@@ -47,6 +47,8 @@ struct ImageDev {
   const float* boxes[2];
   float* out;
   __nv_bfloat16* out_bf16;
+  long long* acc;    // sweeps: [n_boxes][out_dim] fixed-point (2^-32) accumulators -- integer atomics commute, so the sum does
+                     // not depend on the order in which the region CTAs arrive (bit-reproducible, unlike fp32 atomics)
   long long ws_ofs;  // float offset of this image's workspace slice
   long long ls_ofs;  // int offset of this image's region-list slice (after all weight records)
   int lstride;       // ints per region list: 1 count + n_boxes ids, rounded up to 4
@@ -180,6 +182,11 @@ __global__ void __launch_bounds__(128) hfre_axis_weights_kernel(const BatchDev B
     hdr[axis * 2 + 0] = r_min;
     hdr[axis * 2 + 1] = r_max - r_min + 1;
   }
+}
+
+// order-independent accumulation of the region CTAs' partial sums: value * 2^32 as a 64-bit integer (|sum| < 2^31, step 2.3e-10)
+__device__ __forceinline__ void acc_add(long long* p, float v) {
+  atomicAdd(reinterpret_cast<unsigned long long*>(p), (unsigned long long)__float2ll_rn(v * 4294967296.0f));
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -495,7 +502,7 @@ __global__ void __launch_bounds__(kSweepThreads) hfre_sweep_kernel(const BatchDe
     // ---- flush: one fp32 reduction per (box, channel) of this region ----
     for (int i = threadIdx.x; i < ns * kSweepCh; i += kSweepThreads) {
       const int sl = i / kSweepCh, c = cgroup * kSweepCh + (i % kSweepCh);
-      if (c < L.C) atomicAdd(im.out + (long long)s_box[sl] * B.out_dim + L.out_off + c, s_acc[sl][i % kSweepCh]);
+      if (c < L.C) acc_add(im.acc + (long long)s_box[sl] * B.out_dim + L.out_off + c, s_acc[sl][i % kSweepCh]);
     }
     __syncthreads();
   }
@@ -708,25 +715,32 @@ __global__ void __launch_bounds__(kSweepThreads, 4) hfre_sweep_mma_kernel(const 
     {
       // thread -> channels (tid, tid + 128) of every box of the pass: one row pointer per box, two coalesced reductions
       const int c0 = cgroup * kSweepCh + threadIdx.x;
-      float* obase = im.out + L.out_off + c0;
+      long long* obase = im.acc + L.out_off + c0;
       for (int sl = 0; sl < ns; ++sl) {
-        float* orow = obase + (long long)s_box[sl] * B.out_dim;
-        if (c0 < L.C) atomicAdd(orow, s_acc[sl * kMmaAccPitch + threadIdx.x]);
-        if (c0 + kSweepThreads < L.C) atomicAdd(orow + kSweepThreads, s_acc[sl * kMmaAccPitch + threadIdx.x + kSweepThreads]);
+        long long* orow = obase + (long long)s_box[sl] * B.out_dim;
+        if (c0 < L.C) acc_add(orow, s_acc[sl * kMmaAccPitch + threadIdx.x]);
+        if (c0 + kSweepThreads < L.C) acc_add(orow + kSweepThreads, s_acc[sl * kMmaAccPitch + threadIdx.x + kSweepThreads]);
       }
     }
     __syncthreads();
   }
 }
 
-// Kernel 4: optional bf16 copy of the region features (the reference casts to the tower dtype
-// before mm_projector_aux, omchat_qwen2_5_vl.py:106).
-__global__ void __launch_bounds__(256) hfre_to_bf16_kernel(const BatchDev B) {
+// Kernel 4: finish -- sweeps: out = box embedding (already in out) + pooled feature (the fixed-point sum, rounded to fp32 once:
+// the reference adds the embedding to the finished feature, hybrid_finegrained_region_encoder.py:464-467); then the optional
+// bf16 copy (the reference casts to the tower dtype before mm_projector_aux, omchat_qwen2_5_vl.py:106).
+__global__ void __launch_bounds__(256) hfre_finish_kernel(const BatchDev B, int from_acc) {
   const ImageDev& im = B.img[blockIdx.z];
-  if (im.out_bf16 == nullptr) return;
+  if (!from_acc && im.out_bf16 == nullptr) return;
   const long long n = (long long)im.n_boxes * B.out_dim;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-    im.out_bf16[i] = __float2bfloat16_rn(im.out[i]);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float v = im.out[i];
+    if (from_acc) {
+      v = __fadd_rn((float)((double)im.acc[i] * (1.0 / 4294967296.0)), v);
+      im.out[i] = v;
+    }
+    if (im.out_bf16 != nullptr) im.out_bf16[i] = __float2bfloat16_rn(v);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------- host
@@ -750,10 +764,16 @@ static size_t image_list_ints(const fo1_hfre_image& im) {
 
 using namespace fo1;
 
-extern "C" size_t fo1_hfre_workspace_bytes(const fo1_hfre_image* images, int32_t n_images, const fo1_hfre_params*) {
+static size_t acc_bytes(const fo1_hfre_image* images, int n_images, const fo1_hfre_params* p) {
+  size_t n = 0;
+  for (int i = 0; i < n_images; ++i) n += (size_t)(images[i].n_boxes > 0 ? images[i].n_boxes : 0) * (size_t)(p ? p->out_dim : 0);
+  return n * sizeof(long long);
+}
+
+extern "C" size_t fo1_hfre_workspace_bytes(const fo1_hfre_image* images, int32_t n_images, const fo1_hfre_params* p) {
   size_t f = 0;
   for (int i = 0; i < n_images; ++i) f += image_ws_floats(images[i]) + image_list_ints(images[i]);
-  return f * sizeof(float) + 256;
+  return ((f * sizeof(float) + 255) & ~(size_t)255) + acc_bytes(images, n_images, p) + 256;
 }
 
 extern "C" int fo1_hfre_forward(const fo1_hfre_image* images, int32_t n_images, const fo1_hfre_params* p,
@@ -774,6 +794,11 @@ extern "C" int fo1_hfre_forward(const fo1_hfre_image* images, int32_t n_images, 
   for (int i = 0; i < n_images; ++i) total_w += image_ws_floats(images[i]);
   int* lists = reinterpret_cast<int*>(ws + total_w);   // region box lists live after all weight records
   size_t ls_ofs = 0;
+  size_t total_f = 0;
+  for (int i = 0; i < n_images; ++i) total_f += image_ws_floats(images[i]) + image_list_ints(images[i]);
+  long long* acc_base = reinterpret_cast<long long*>(static_cast<char*>(workspace) + ((total_f * sizeof(float) + 255) & ~(size_t)255));
+  size_t acc_ofs = 0;
+  bool acc_zeroed = false;
 
   size_t ws_ofs = 0;
   for (int base = 0; base < n_images; base += kMaxBatch) {
@@ -803,6 +828,8 @@ extern "C" int fo1_hfre_forward(const fo1_hfre_image* images, int32_t n_images, 
       d.boxes[1] = src.boxes_vt;
       d.out = src.out;
       d.out_bf16 = static_cast<__nv_bfloat16*>(src.out_bf16);
+      d.acc = acc_base + acc_ofs;
+      acc_ofs += (size_t)(src.n_boxes > 0 ? src.n_boxes : 0) * (size_t)p->out_dim;
       d.pos_w = src.pos_img_w;
       d.pos_h = src.pos_img_h;
       d.pos_box_set = src.pos_box_set ? 1 : 0;
@@ -858,6 +885,10 @@ extern "C" int fo1_hfre_forward(const fo1_hfre_image* images, int32_t n_images, 
       FO1_LAUNCH_CHECK();
     }
     if (sweep) {
+      if (!acc_zeroed) {   // one memset for every image of the call
+        FO1_CUDA(cudaMemsetAsync(acc_base, 0, acc_bytes(images, n_images, p), stream));
+        acc_zeroed = true;
+      }
       {
         dim3 grid(max_regions, max_levels, B.n_images);
         if (tensor) hfre_region_records_kernel<<<grid, 128, 0, stream>>>(B, ws, lists);
@@ -885,9 +916,9 @@ extern "C" int fo1_hfre_forward(const fo1_hfre_image* images, int32_t n_images, 
     }
     bool any_bf16 = false;
     for (int i = 0; i < B.n_images; ++i) any_bf16 |= (B.img[i].out_bf16 != nullptr);
-    if (any_bf16) {
+    if (any_bf16 || sweep) {
       dim3 grid(ceil_div(max_boxes * p->out_dim, 256 * 8), 1, B.n_images);
-      hfre_to_bf16_kernel<<<grid, 256, 0, stream>>>(B);
+      hfre_finish_kernel<<<grid, 256, 0, stream>>>(B, sweep ? 1 : 0);
       FO1_LAUNCH_CHECK();
     }
   }

@@ -12,7 +12,7 @@
 // prompt position only.
 #include <algorithm>
 
-#include "engine.cuh"
+#include "decode_mega.cuh"
 
 namespace fo1 {
 
@@ -382,11 +382,38 @@ static int llm_resolve(Model* m) {
   }
   if (!g.err.empty()) { set_error("LLM weights: %s", g.err.c_str()); return FO1_ERR_NOT_FOUND; }
   w.ok = true;
+  // optional decode copies (weights.py::prepare_llm): W diag(g) for the two normed projections and the LM head, gate / up in the
+  // decode kernel's 8 + 8 row interleave.  All present -> the persistent decode kernel is used.
+  w.mega_ok = m->find("llm.head_dec") != nullptr;
+  for (int i = 0; i < c.llm_layers && w.mega_ok; ++i) {
+    const std::string p = "llm.l" + std::to_string(i) + ".";
+    w.mega_ok = m->find(p + "qkv_dec.w") != nullptr && m->find(p + "gu_dec.w") != nullptr;
+  }
+  if (w.mega_ok) {
+    WeightGetter g2{m, ""};
+    w.head_dec = g2.bf("llm.head_dec", {V, H});
+    std::vector<MegaLayer> ml(c.llm_layers);
+    for (int i = 0; i < c.llm_layers; ++i) {
+      const std::string p = "llm.l" + std::to_string(i) + ".";
+      LlmLayerW& L = w.layer[i];
+      L.qkv_dec = g2.bf(p + "qkv_dec.w", {QD + 2 * KD, H});
+      L.gu_dec = g2.bf(p + "gu_dec.w", {2 * (int64_t)c.llm_inter, H});
+      ml[i].qkv_w = L.qkv_dec; ml[i].qkv_b = L.qkv_b; ml[i].o_w = L.o_w; ml[i].gu_w = L.gu_dec; ml[i].down_w = L.down_w;
+    }
+    if (!g2.err.empty()) { set_error("LLM decode weights: %s", g2.err.c_str()); return FO1_ERR_NOT_FOUND; }
+    if (c.llm_inter != Ip) w.mega_ok = false;      // the decode kernel reads down_w with K = intermediate size (no padding)
+    if (w.mega_ok) {
+      if (w.mega_layers) cudaFree(w.mega_layers);
+      FO1_CUDA(cudaMalloc(&w.mega_layers, ml.size() * sizeof(MegaLayer)));
+      FO1_CUDA(cudaMemcpy(w.mega_layers, ml.data(), ml.size() * sizeof(MegaLayer), cudaMemcpyHostToDevice));
+    }
+  }
   return FO1_OK;
 }
 int llm_finalize(Model* m) { return m->cfg.llm_layers > 0 ? llm_resolve(m) : FO1_OK; }
 
 void llm_destroy_state(Model* m) {
+  if (m->llm.mega_layers) { cudaFree(m->llm.mega_layers); m->llm.mega_layers = nullptr; }
   LlmState* s = static_cast<LlmState*>(m->llm_state);
   if (!s) return;
   if (s->ints) cudaFree(s->ints);
@@ -503,6 +530,12 @@ static int llm_generate_impl(Model* m, fo1_generate_desc* d, cudaStream_t s, boo
   bf16* alln = d->all_logits ? A.alloc<bf16>((size_t)T * H) : nullptr;
   int* d_lens = A.alloc<int>(B);
   int* d_deltas = A.alloc<int>(B);
+  // persistent decode kernel (decode_mega.cu): per-CTA slots + the grid barrier
+  const int mega_grid = (m->llm.mega_ok && B <= 32 && getenv("FO1_NO_MEGA") == nullptr) ? decode_mega_grid() : 0;
+  float* mg_ssq = A.alloc<float>((size_t)2 * std::max(mega_grid, 1) * 32);
+  float* mg_amax_v = A.alloc<float>((size_t)std::max(mega_grid, 1) * 32);
+  int* mg_amax_i = A.alloc<int>((size_t)std::max(mega_grid, 1) * 32);
+  int* mg_sync = A.alloc<int>((size_t)B * c.llm_kv_heads + 8);      // [0]: grid barrier counter, [8..]: attention arrival counters
 
   // ---- integer tables of the packed batch ----
   const int *d_cu = nullptr, *d_row_seq = nullptr, *d_row_t = nullptr, *d_last = nullptr;
@@ -524,7 +557,8 @@ static int llm_generate_impl(Model* m, fo1_generate_desc* d, cudaStream_t s, boo
     FO1_TRY(cached_ints(m, key + ":til", tiles, &buf.tiles, s));
     buf.n_tiles = (int)tiles.size() / 2;
     FO1_CUDA(cudaMemcpyAsync(d_lens, d->seq_lens, B * sizeof(int), cudaMemcpyHostToDevice, s));
-    FO1_CUDA(cudaMemcpyAsync(d_deltas, d->rope_deltas, B * sizeof(int), cudaMemcpyHostToDevice, s));
+    if (d->rope_deltas_device != nullptr) FO1_CUDA(cudaMemcpyAsync(d_deltas, d->rope_deltas_device, B * sizeof(int), cudaMemcpyDeviceToDevice, s));
+    else FO1_CUDA(cudaMemcpyAsync(d_deltas, d->rope_deltas, B * sizeof(int), cudaMemcpyHostToDevice, s));
     if (d->n_stop_ids > 0) FO1_CUDA(cudaMemcpyAsync(st.stop_ids, d->stop_ids, d->n_stop_ids * sizeof(int), cudaMemcpyHostToDevice, s));
   }
 
@@ -579,6 +613,70 @@ static int llm_generate_impl(Model* m, fo1_generate_desc* d, cudaStream_t s, boo
     FO1_LAUNCH_CHECK();
     return FO1_OK;
   };
+  if (mega_grid > 0 && d->max_new_tokens > 1) {
+    // ---- the whole greedy loop as ONE cooperative launch ----
+    MegaArgs a;
+    memset(&a, 0, sizeof(a));
+    a.B = B; a.layers = c.llm_layers; a.H = H; a.QD = QD; a.KD = KD; a.hd = hd; a.q_heads = c.llm_heads; a.kv_heads = c.llm_kv_heads;
+    a.I = c.llm_inter; a.V = V; a.eps = c.rms_eps; a.theta = c.rope_theta; a.sec_t = c.mrope_section[0]; a.sec_h = c.mrope_section[1];
+    a.layer = static_cast<const MegaLayer*>(m->llm.mega_layers);
+    a.head_w = m->llm.head_dec; a.embed = m->llm.embed;
+    a.kv_layer_stride = (long long)m->kv_batch * m->kv_cap * KD;
+    a.kc = static_cast<bf16*>(m->kv_cache);
+    a.vc = static_cast<bf16*>(m->kv_cache) + (size_t)c.llm_layers * a.kv_layer_stride;
+    a.cap = m->kv_cap;
+    a.x = xa; a.x_mid = buf.x_mid; a.qkv = buf.qkv; a.att = buf.att; a.h = buf.h;
+    a.ssq = mg_ssq; a.cs = cs_dec; a.att_part = buf.dec_part; a.att_count = mg_sync + 8;
+    a.amax_val = mg_amax_v; a.amax_idx = mg_amax_i;
+    a.cache_len = st.cache_len; a.pos3 = st.pos3; a.cur_tok = st.cur_tok; a.finished = st.finished; a.n_active = st.n_active; a.step = st.step;
+    a.stop_ids = st.stop_ids; a.n_stop = d->n_stop_ids; a.pad_id = d->pad_id; a.max_new = d->max_new_tokens;
+    a.out_tokens = d->out_tokens; a.out_lens = d->out_lens;
+    a.n_steps = d->max_new_tokens - 1;
+    a.bar = reinterpret_cast<unsigned*>(mg_sync);
+    const int pairs = B * c.llm_kv_heads;
+    a.n_splits = std::max(1, std::min(kMgMaxSplits, mega_grid / std::max(1, pairs)));
+    FO1_CUDA(cudaMemsetAsync(mg_sync, 0, ((size_t)pairs + 8) * sizeof(int), s));
+    unsigned long long* d_prof = nullptr;
+    const int prof_slots = 5 * c.llm_layers + 3;
+    if (getenv("FO1_MEGA_PROF") != nullptr) {       // diagnostic: where a decode iteration spends its time (stderr)
+      FO1_CUDA(cudaMalloc(reinterpret_cast<void**>(&d_prof), (size_t)mega_grid * prof_slots * 2 * sizeof(unsigned long long)));
+      FO1_CUDA(cudaMemsetAsync(d_prof, 0, (size_t)mega_grid * prof_slots * 2 * sizeof(unsigned long long), s));
+      a.prof = d_prof; a.prof_slots = prof_slots;
+    }
+    FO1_TRY(decode_mega_run(a, s));
+    if (d_prof != nullptr) {
+      std::vector<unsigned long long> h((size_t)mega_grid * prof_slots * 2);
+      FO1_CUDA(cudaStreamSynchronize(s));
+      FO1_CUDA(cudaMemcpy(h.data(), d_prof, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+      cudaFree(d_prof);
+      // per slot: the last CTA to enter the barrier ends the phase; release = when CTA 0 leaves.  work = last_enter - previous release,
+      // skew = last_enter - first_enter, barrier = release - last_enter
+      const char* names[5] = {"qkv", "attn", "oproj", "gateup", "down"};
+      double tot[5][3] = {{0}}, misc = 0;
+      unsigned long long prev_release = 0;
+      for (int sl = 0; sl < prof_slots; ++sl) {
+        unsigned long long first = ~0ull, last = 0, rel = 0;
+        for (int cta = 0; cta < mega_grid; ++cta) {
+          const unsigned long long e = h[((size_t)cta * prof_slots + sl) * 2], l = h[((size_t)cta * prof_slots + sl) * 2 + 1];
+          if (e < first) first = e;
+          if (e > last) last = e;
+          if (l > rel) rel = l;
+        }
+        if (sl >= 1 && sl <= 5 * c.llm_layers) {
+          const int ph = (sl - 1) % 5;
+          tot[ph][0] += (double)(last - prev_release); tot[ph][1] += (double)(last - first); tot[ph][2] += (double)(rel - last);
+        } else if (sl > 0) misc += (double)(rel - prev_release);
+        prev_release = rel;
+      }
+      fprintf(stderr, "[decode_mega profile, first iteration, B=%d, %d CTAs] per layer (us): ", B, mega_grid);
+      for (int ph = 0; ph < 5; ++ph)
+        fprintf(stderr, "%s work %.1f (skew %.1f) barrier %.1f | ", names[ph], tot[ph][0] / c.llm_layers / 1e3, tot[ph][1] / c.llm_layers / 1e3,
+                tot[ph][2] / c.llm_layers / 1e3);
+      fprintf(stderr, "head+update %.1f us\n", misc / 1e3);
+    }
+    d->steps_run = d->max_new_tokens - 1;
+    return FO1_OK;
+  }
   cudaGraphExec_t gexec = nullptr;
   const bool want_graph = !g_prof_on && d->max_new_tokens > 3 && getenv("FO1_NO_GRAPH") == nullptr;
   d->steps_run = 0;
@@ -626,7 +724,8 @@ static int llm_generate_impl(Model* m, fo1_generate_desc* d, cudaStream_t s, boo
 int llm_generate(Model* m, fo1_generate_desc* d, cudaStream_t s) {
   FO1_CHECK_ARG(m->llm.ok, "fo1_llm_generate: model not finalized (LLM weights unresolved)");
   const fo1_model_config& c = m->cfg;
-  FO1_CHECK_ARG(d->n_seqs > 0 && d->seq_lens && d->inputs_embeds && d->position_ids && d->rope_deltas, "fo1_llm_generate: null argument");
+  FO1_CHECK_ARG(d->n_seqs > 0 && d->seq_lens && d->inputs_embeds && d->position_ids && (d->rope_deltas || d->rope_deltas_device),
+                "fo1_llm_generate: null argument");
   FO1_CHECK_ARG(d->max_new_tokens == 0 || (d->out_tokens && d->out_lens), "fo1_llm_generate: null outputs");
   FO1_CHECK_ARG(c.llm_head_dim == 128, "fo1_llm_generate: head_dim %d unsupported (128)", c.llm_head_dim);
   int max_len = 0;

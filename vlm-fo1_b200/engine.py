@@ -202,7 +202,7 @@ class GenerateDescC(C.Structure):
                 ("position_ids", C.c_void_p), ("rope_deltas", C.POINTER(C.c_int32)), ("max_new_tokens", C.c_int32),
                 ("stop_ids", C.POINTER(C.c_int32)), ("n_stop_ids", C.c_int32), ("pad_id", C.c_int32),
                 ("out_tokens", C.c_void_p), ("out_lens", C.c_void_p), ("prefill_logits", C.c_void_p),
-                ("all_logits", C.c_void_p), ("early_exit_interval", C.c_int32), ("steps_run", C.c_int32)]
+                ("all_logits", C.c_void_p), ("early_exit_interval", C.c_int32), ("steps_run", C.c_int32), ("rope_deltas_device", C.c_void_p)]
 
 
 def splice_plan(input_ids: Sequence[int], image_grids: Sequence[Tuple[int, int]], n_regions: int,
@@ -258,7 +258,12 @@ def _engine_generate(self, inputs_embeds: torch.Tensor, position_ids: torch.Tens
     al = torch.empty((T, V), dtype=torch.float32, device=self.device) if want_all_logits else None
     d = GenerateDescC()
     d.n_seqs = B
-    sl = (C.c_int32 * B)(*[int(x) for x in seq_lens]); rd = (C.c_int32 * B)(*[int(x) for x in rope_deltas])
+    sl = (C.c_int32 * B)(*[int(x) for x in seq_lens])
+    dev_deltas = rope_deltas if isinstance(rope_deltas, torch.Tensor) else None       # device int32 [B] from splice_plan_batch
+    rd = (C.c_int32 * B)(*([0] * B if dev_deltas is not None else [int(x) for x in rope_deltas]))
+    if dev_deltas is not None:
+        assert dev_deltas.is_cuda and dev_deltas.dtype == torch.int32 and dev_deltas.numel() == B
+        d.rope_deltas_device = dev_deltas.data_ptr()
     st = (C.c_int32 * max(len(stop_ids), 1))(*[int(x) for x in stop_ids])
     d.seq_lens, d.rope_deltas, d.stop_ids, d.n_stop_ids = sl, rd, st, len(stop_ids)
     d.inputs_embeds, d.position_ids = inputs_embeds.data_ptr(), position_ids.data_ptr()

@@ -15,7 +15,7 @@ import numpy as np
 import torch
 
 from . import hfre as HF
-from .engine import Engine, splice_plan
+from .engine import Engine, splice_plan, splice_plan_batch
 
 
 @dataclass
@@ -40,6 +40,7 @@ class Fo1Pipeline:
         self._marks = []
         self._keep_stages = None
         self._pre = None
+        self.check_plan = True
 
     def _mark(self, name: str) -> None:
         if self.profile_stages:
@@ -161,21 +162,19 @@ class Fo1Pipeline:
         eng, dev = self.eng, self.eng.device
         samples = self.preprocess(samples)           # uint8 images -> the towers' input tensors, on the device
         feats, img_off, region_tokens, _ = self.encode(samples)
-        kinds, idxs, poss, lens, deltas = [], [], [], [], []
-        reg_off = 0
+        # splice + M-RoPE bookkeeping of the whole batch in one launch on the device (fo1_splice_plan_batch); the per-sample host
+        # function fo1_splice_plan stays the bit-exact reference of it (tests/test_gpu_prompt.py)
         merge = eng.cfg.vit["spatial_merge_size"]
-        for b, s in enumerate(samples):
-            n_reg = region_tokens[b].shape[0]
-            plan = splice_plan(s.input_ids, [s.grid_hw], n_reg, merge=merge, **self.ids)
-            k, ix = plan["kind"], plan["index"].copy()
-            ix[k == 1] += int(img_off[b])
-            ix[k == 2] += reg_off
-            reg_off += n_reg
-            kinds.append(k); idxs.append(ix); poss.append(plan["position_ids"]); lens.append(len(k)); deltas.append(plan["rope_delta"])
-        kind = torch.from_numpy(np.concatenate(kinds)).to(dev)
-        index = torch.from_numpy(np.concatenate(idxs)).to(dev)
-        pos = torch.from_numpy(np.concatenate(poss, axis=1)).to(dev)
-        embeds = eng.build_embeds(kind, index, feats, torch.cat(region_tokens, 0))
+        plan = splice_plan_batch([s.input_ids for s in samples], [[s.grid_hw] for s in samples], [r.shape[0] for r in region_tokens], dev,
+                                 merge=merge, **self.ids)
+        lens = plan["lens"]
+        embeds = eng.build_embeds(plan["kind"], plan["index"], feats, torch.cat(region_tokens, 0))
+        pos = plan["position_ids"]
+        if self.check_plan:                                      # opt-in: surface a malformed prompt as an exception (one D2H sync)
+            st = plan["status"].cpu().tolist()
+            if any(st):
+                raise ValueError(f"fo1_splice_plan_batch: per-sample status {st} (placeholders and features disagree)")
+        deltas = plan["rope_delta"]
         self._mark("splice")
         out = eng.generate(embeds, pos, lens, deltas, max_new_tokens, stop_ids, pad_id, want_prefill_logits=want_prefill_logits,
                            early_exit_interval=early_exit_interval)

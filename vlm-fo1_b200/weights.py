@@ -135,7 +135,7 @@ def prepare_projector(sd: Dict[str, torch.Tensor], prefix: str, device) -> Dict[
     return out
 
 
-def prepare_llm(sd: Dict[str, torch.Tensor], cfg: dict, device) -> Dict[str, torch.Tensor]:
+def prepare_llm(sd: Dict[str, torch.Tensor], cfg: dict, device, decode_copies: bool = True) -> Dict[str, torch.Tensor]:
     """sd keys: 'embed_tokens.weight', 'layers.N.*', 'norm.weight', 'lm_head.weight' (optional when tied)."""
     out = {"llm.embed": _dev(sd["embed_tokens.weight"], device), "llm.norm.w": _dev(sd["norm.weight"], device)}
     if "lm_head.weight" in sd:
@@ -153,4 +153,16 @@ def prepare_llm(sd: Dict[str, torch.Tensor], cfg: dict, device) -> Dict[str, tor
         out[d + "ln2.w"] = _dev(sd[s + "post_attention_layernorm.weight"], device)
         out[d + "gateup.w"] = interleave_gate_up(_dev(sd[s + "mlp.gate_proj.weight"], device), _dev(sd[s + "mlp.up_proj.weight"], device))
         out[d + "down.w"] = pad_cols(_dev(sd[s + "mlp.down_proj.weight"], device), vit_inter_pad(cfg["intermediate_size"]))
+    if decode_copies and cfg["intermediate_size"] % 64 == 0 and cfg["hidden_size"] % 64 == 0:
+        # persistent decode kernel (csrc/decode_mega.cu): RMSNorm folded into the consumer, y = rsqrt(mean x^2 + eps) * (W diag(g)) x;
+        # gate / up rows interleaved 8 + 8 so that a 16-row tile yields 8 finished SwiGLU columns
+        for i in range(cfg["num_hidden_layers"]):
+            s, d = f"layers.{i}.", f"llm.l{i}."
+            g1 = _dev(sd[s + "input_layernorm.weight"], device).float()
+            g2 = _dev(sd[s + "post_attention_layernorm.weight"], device).float()
+            out[d + "qkv_dec.w"] = (out[d + "qkv.w"].float() * g1[None, :]).to(torch.bfloat16).contiguous()
+            gate = (_dev(sd[s + "mlp.gate_proj.weight"], device).float() * g2[None, :]).to(torch.bfloat16)
+            up = (_dev(sd[s + "mlp.up_proj.weight"], device).float() * g2[None, :]).to(torch.bfloat16)
+            out[d + "gu_dec.w"] = interleave_gate_up(gate, up, block=8)
+        out["llm.head_dec"] = (out["llm.lm_head"].float() * out["llm.norm.w"].float()[None, :]).to(torch.bfloat16).contiguous()
     return out

@@ -1,4 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
-FO1_MEGA_PROF=1 timeout 600 python scripts/mega_prof.py 32 1195 > gpurun_out/mega_prof.log 2>&1; echo "rc=$?"; grep -E "decode_mega profile|decode ms" gpurun_out/mega_prof.log | tail -12
-FO1_MEGA_PROF=1 timeout 600 python scripts/mega_prof.py 8 1195 > gpurun_out/mega_prof8.log 2>&1; grep -E "decode_mega profile|decode ms" gpurun_out/mega_prof8.log | tail -6
+timeout 900 python -m pytest tests/test_gpu_decode_mega.py tests/test_gpu_llm.py -x -q 2>&1 | tail -4
+for cfg in "32 1195" "16 773" "8 2647" "8 600" "1 600"; do
+set -- $cfg
+FO1_MEGA_PROF=1 timeout 600 python scripts/mega_prof.py $1 $2 > gpurun_out/mega_prof_$1_$2.log 2>&1; grep -E "ms/step|decode_mega profile, first" gpurun_out/mega_prof_$1_$2.log | tail -3
+done

@@ -1,6 +1,7 @@
 """FO1_MEGA_PROF=1 python scripts/mega_prof.py [B] [L]: one generate() of the LLM alone at the 3B widths, prints the per-phase profile
 of the persistent decode kernel (stderr) and the decode step time with / without it."""
 import os, sys, time
+os.environ.setdefault("FO1_MEGA_MAX_B", "32")
 import torch
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, REPO)
@@ -18,7 +19,21 @@ def run(T):
     torch.cuda.synchronize(); e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     e0.record(); eng.generate(emb, pos, [L] * B, [0] * B, T, stop_ids=[], pad_id=0, early_exit_interval=0); e1.record(); torch.cuda.synchronize()
     return e0.elapsed_time(e1)
-for tag in ("mega", "per-kernel"):
-    if tag == "per-kernel": os.environ["FO1_NO_MEGA"] = "1"
-    run(4); a = run(2); b = run(34)
-    print(tag, "decode ms/step", (b - a) / 32, flush=True)
+# clocks ramp up from idle over hundreds of milliseconds: warm the GPU first, then alternate the two paths and keep the best of each
+wa = torch.randn(8192, 8192, device="cuda", dtype=torch.bfloat16)
+t0 = time.time()
+while time.time() - t0 < 3.0:
+    for _ in range(20): wa @ wa
+    torch.cuda.synchronize()
+best = {"mega": 1e9, "per-kernel": 1e9}
+prof = os.environ.pop("FO1_MEGA_PROF", None)
+for rep in range(3):
+    for tag in ("mega", "per-kernel"):
+        if tag == "per-kernel": os.environ["FO1_NO_MEGA"] = "1"
+        else: os.environ.pop("FO1_NO_MEGA", None)
+        run(4); a = run(2); b = run(34)
+        best[tag] = min(best[tag], (b - a) / 32)
+for tag, v in best.items(): print(tag, "decode ms/step %.3f" % v, flush=True)
+if prof:
+    os.environ.pop("FO1_NO_MEGA", None); os.environ["FO1_MEGA_PROF"] = prof
+    run(4)

@@ -32,23 +32,33 @@ namespace fo1 {
 
 constexpr int kMgThreads = 256;
 constexpr int kMgWarps = 8;
-constexpr int kMgRows = 32;                 // batch rows (two m16 tiles)
+constexpr int kMgRows = 32;                 // batch rows at most (MT = 1: 16, MT = 2: 32 -- one or two m16 tiles)
 constexpr int kMgTileN = 16;                // output columns per tile
 constexpr int kMgChunkK = 64;               // k per ring stage
-constexpr int kMgStages = 4;
-constexpr int kMgStageBytes = kMgTileN * kMgChunkK * 2;            // 2 KB
-constexpr int kMgRingBytes = kMgWarps * kMgStages * kMgStageBytes; // 64 KB
-constexpr int kMgAK = 2048;                 // resident A width; wider A (down-proj) streams in halves of kMgAHalf
-constexpr int kMgAHalf = 1024;
-constexpr int kMgAPitch = kMgAK * 2 + 16;   // bytes per A row in shared memory (+16: ldmatrix rows fall on different banks)
-constexpr int kMgAHalfPitch = kMgAHalf * 2 + 16;
-constexpr int kMgABytes = 2 * kMgRows * kMgAHalfPitch;             // 132 096: two streamed halves (>= one resident tile of 32 x 4112 B)
-static_assert(kMgABytes >= kMgRows * kMgAPitch, "the resident A tile fits");
-constexpr int kMgRedBytes = kMgWarps * kMgRows * kMgTileN * 4;     // 16 KB of per-warp partial tiles
-constexpr int kMgMiscBytes = 1024;          // rs[32], ssq[32], mbarriers, flags
-constexpr int kMgSmemBytes = kMgABytes + kMgRingBytes + kMgRedBytes + kMgMiscBytes;
+constexpr int kMgWBytes = kMgTileN * kMgChunkK * 2;                // 2 KB of weights per stage
+constexpr int kMgAK = 2048;                 // widest A kept resident in shared memory; wider A (down-proj) travels in the ring stages
+constexpr int kMgAPitch = kMgAK * 2 + 16;   // bytes per resident A row (+16: ldmatrix rows fall on different banks)
+constexpr int kMgSmemBytes = 232448 - 1024; // the 227 KB a CTA may opt into minus the kernel's few static words; laid out per MT below
+constexpr int kMgMiscBytes = 1024;          // rs[32], ssq[32], mbarriers
 constexpr int kMgAttnWarps = 8, kMgAttnStages = 3, kMgAttnTileBytes = 16 * 256 * 2;
-static_assert(kMgAttnWarps * kMgAttnStages * kMgAttnTileBytes <= kMgABytes + kMgRingBytes, "attention ring aliases the A tile and the weight ring");
+// split merge: staging area behind the warp-merge buffers ([8 warps][8 heads][128] floats + m, l), 16-byte loads per thread
+constexpr int kMgCombineOff = 40960, kMgCombineLoads = (8 * kMgMaxSplits * 33 + kMgThreads - 1) / kMgThreads;
+
+// shared-memory layout: [ weight ring | resident A | per-warp partial tiles | misc ].  With 16 batch rows the A tile is half as
+// large and the ring twice as deep: the ring depth (bytes in flight per SM) is what bounds the streaming rate.
+template <int MT>
+struct MgLay {
+  static constexpr int kMisc = kMgSmemBytes - kMgMiscBytes;
+  static constexpr int kRedBytes = kMgWarps * 16 * MT * kMgTileN * 4;
+  static constexpr int kRed = kMisc - kRedBytes;
+  static constexpr int kABytes = 16 * MT * kMgAPitch;
+  static constexpr int kA = kRed - kABytes;                               // ring region of the resident-A phases: [0, kA)
+  static constexpr int kStagesRes = kA / (kMgWarps * kMgWBytes);          // MT 1: 9, MT 2: 5
+  static constexpr int kSelfStage = kMgWBytes + 16 * MT * 128;            // down-proj: the stage carries its A chunk too
+  static constexpr int kStagesSelf = kRed / (kMgWarps * kSelfStage);      // MT 1: 6, MT 2: 4 (the A tile is not live in that phase)
+  static_assert(kStagesRes >= 3 && kStagesSelf >= 3 && kStagesRes <= 9, "ring depth");
+  static_assert(kMgAttnWarps * kMgAttnStages * kMgAttnTileBytes <= kMisc, "the attention ring aliases ring + A + partials");
+};
 
 // ------------------------------------------------------------------------------------------------ small device helpers
 __device__ __forceinline__ void mg_cp16(uint32_t dst, const void* src) {
@@ -96,7 +106,7 @@ __device__ __forceinline__ void mg_grid_sync(unsigned* bar, unsigned& gen) {
   gen += 1;
   if (threadIdx.x == 0) {
     __threadfence();
-    atomicAdd(bar, 1u);
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar) : "memory");     // arrive (no return value to wait for)
     const unsigned target = gen * gridDim.x;
     unsigned spins = 0;
     while (mg_ld_acquire(bar) < target) {
@@ -124,8 +134,10 @@ __device__ __forceinline__ void mg_mbar_wait(uint32_t bar, uint32_t parity) {
 struct MgWork {
   const bf16* W; int K, n_tiles, chunks;      // chunks = K / 64
   int tile, kc;                               // next (tile, chunk) to ISSUE for this warp
-  __device__ void begin(const bf16* w, int k, int n, int warp) {
+  const bf16* A; int lda, B, a_rows;          // self-contained stages (down-proj): the activation matrix the chunk slices come from
+  __device__ void begin(const bf16* w, int k, int n, int warp, const bf16* a = nullptr, int lda_ = 0, int b = 0, int rows = 0) {
     W = w; K = k; n_tiles = n / kMgTileN; chunks = k / kMgChunkK; tile = blockIdx.x; kc = warp;
+    A = a; lda = lda_; B = b; a_rows = rows;
     if (kc >= chunks) { tile = n_tiles; }      // (never: chunks >= 8)
   }
   __device__ bool done() const { return tile >= n_tiles; }
@@ -135,26 +147,47 @@ struct MgWork {
   }
 };
 
+// Per-warp cp.async ring.  (A ring of cp.async.bulk copies from a tile-contiguous weight image was measured too: faster in an empty
+// streaming loop -- scripts/probes/stream_probe.cu, 5.4 vs 4.0 TB/s -- but slower here, because expect_tx + the bulk issue + the
+// mbarrier wait cost this latency-bound loop ~500 cycles more per 2-4 KB stage than four cp.async per lane and a wait_group.)
 struct MgRing {
   uint32_t base;            // shared address of this warp's stages
-  int head, tail;           // stages issued / consumed (mod kMgStages by use)
+  int stage_bytes, n_stages;
+  int head, tail;           // stages issued / consumed
   int inflight;
-  __device__ void init(uint32_t b) { base = b; head = tail = 0; inflight = 0; }
+  // (re)configure: only when nothing is in flight.  `self`: the stage also carries the A chunk (rows x 128 B after the 2 KB of W)
+  __device__ void mode(uint32_t smem0, int warp, int stage_b, int stages) {
+    stage_bytes = stage_b; n_stages = stages; base = smem0 + warp * stages * stage_b; head = tail = 0; inflight = 0;
+  }
   // one stage = 16 weight rows x 64 k (128 B per row, 16-byte chunks XOR-swizzled by row): 4 x 16 B per lane
   __device__ void issue(MgWork& w, int lane) {
-    const uint32_t st = base + (head % kMgStages) * kMgStageBytes;
+    const uint32_t st = base + (head % n_stages) * stage_bytes;
     const bf16* src = w.W + ((long long)w.tile * kMgTileN) * w.K + (long long)w.kc * kMgChunkK;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const int row = i * 4 + (lane >> 3), c16 = lane & 7;
       mg_cp16(st + row * 128 + ((c16 ^ (row & 7)) << 4), src + (long long)row * w.K + c16 * 8);
     }
+    if (w.A != nullptr) {     // self-contained stage: this chunk's slice of A (rows beyond the batch read as zero)
+      const bf16* asrc = w.A + (long long)w.kc * kMgChunkK;
+      for (int i = lane; i < w.a_rows * 8; i += 32) {
+        const int row = i >> 3, c16 = i & 7;
+        mg_cp16z(st + kMgWBytes + row * 128 + ((c16 ^ (row & 7)) << 4), asrc + (long long)(row < w.B ? row : 0) * w.lda + c16 * 8, row < w.B);
+      }
+    }
     mg_commit();
     ++head; ++inflight;
     w.advance();
   }
   __device__ void fill(MgWork& w, int lane) {
-    while (inflight < kMgStages - 1 && !w.done()) issue(w, lane);
+    while (inflight < n_stages - 1 && !w.done()) issue(w, lane);
+  }
+  // wait until the OLDEST group in flight has landed (at most inflight - 1 newer groups may stay pending)
+  __device__ void wait_oldest() {
+    switch (inflight - 1) {
+      case 0: mg_wait<0>(); break; case 1: mg_wait<1>(); break; case 2: mg_wait<2>(); break; case 3: mg_wait<3>(); break;
+      case 4: mg_wait<4>(); break; case 5: mg_wait<5>(); break; case 6: mg_wait<6>(); break; default: mg_wait<7>(); break;
+    }
   }
 };
 
@@ -169,95 +202,74 @@ struct MgEpi {
   bool scale_rows;                    // multiply by rs[row] (folded RMSNorm)
 };
 
-template <int EPI>
-__device__ __forceinline__ void mg_gemm_phase(const MegaArgs& a, uint8_t* smem, const bf16* A, int lda, int K, const bf16* W, int N, MgWork& work,
-                                             MgRing& ring, const MgEpi& e, uint32_t (&par)[2], float* best_val, int* best_idx) {
+// SELF = false: A [B][K <= 2048] is bulk-copied once per phase into the resident tile and shared by the 8 warps.
+// SELF = true (down-proj, K = 11008): every ring stage carries its own [rows][64] slice of A next to the 16 x 64 weight chunk, so a
+// warp never waits for anybody else inside the phase.
+template <int EPI, int MT, bool SELF>
+__device__ __forceinline__ void mg_gemm_phase(const MegaArgs& a, uint8_t* smem, const bf16* A, int lda, int K, int N, MgWork& work, MgRing& ring,
+                                             const MgEpi& e, uint32_t& a_parity, float* best_val, int* best_idx) {
+  using Lay = MgLay<MT>;
+  constexpr int ROWS = 16 * MT;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  uint8_t* sA = smem;
-  float* sRed = reinterpret_cast<float*>(smem + kMgABytes + kMgRingBytes);
-  float* sRs = reinterpret_cast<float*>(smem + kMgABytes + kMgRingBytes + kMgRedBytes);     // [32]
-  float* sSsq = sRs + 32;                                                                   // [32]
-  uint64_t* sBar = reinterpret_cast<uint64_t*>(sSsq + 32);                                  // [2]
-  const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(sBar);
-  const bool streamed = K > kMgAK;
+  uint8_t* sA = smem + Lay::kA;
+  float* sRed = reinterpret_cast<float*>(smem + Lay::kRed);
+  float* sRs = reinterpret_cast<float*>(smem + Lay::kMisc);      // [32]
+  float* sSsq = sRs + 32;                                        // [32]
+  const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(sSsq + 32);
   const int n_tiles = N / kMgTileN, chunks = K / kMgChunkK;
   const bool has_work = (int)blockIdx.x < n_tiles;
   if (threadIdx.x < 32) sSsq[threadIdx.x] = 0.f;
-
-  // ---- A: bulk-copied rows (async proxy).  K <= 2048: the whole [B][K] tile once per phase (barrier 0).  Wider (down-proj):
-  // 1024-wide halves, double buffered (barriers 0 / 1); the halves of all of this CTA's tiles form one stream q = 0, 1, 2, ... ----
-  const int pitch = streamed ? kMgAHalfPitch : kMgAPitch;
-  const int n_super = streamed ? (K + kMgAHalf - 1) / kMgAHalf : 1;
-  const int my_tiles = has_work ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
-  const int q_total = my_tiles * n_super;
-  auto load_a = [&](int q) {          // thread 0: (half-)tile q of the stream into buffer q & 1 (resident: buffer 0)
-    const int hf = streamed ? (q & 1) : 0;
-    const int k0 = streamed ? (q % n_super) * kMgAHalf : 0;
-    const int cols = streamed ? min(kMgAHalf, K - k0) : K;
-    const uint32_t bar = bar0 + hf * 8;
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(a.B * cols * 2)) : "memory");
-    for (int r = 0; r < a.B; ++r)
-      mg_bulk_row((uint32_t)__cvta_generic_to_shared(sA + hf * kMgRows * kMgAHalfPitch + r * pitch), A + (long long)r * lda + k0, cols * 2, bar);
-  };
-  if (has_work && threadIdx.x == 0) {
+  if (!SELF && has_work && threadIdx.x == 0) {
     asm volatile("fence.proxy.async;" ::: "memory");      // rows were written with ordinary stores by other CTAs (ordered by the grid barrier)
-    load_a(0);
-    if (streamed && q_total > 1) load_a(1);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar0), "r"((uint32_t)(a.B * K * 2)) : "memory");
+    for (int r = 0; r < a.B; ++r)
+      mg_bulk_row((uint32_t)__cvta_generic_to_shared(sA + r * kMgAPitch), A + (long long)r * lda, K * 2, bar0);
   }
   __syncthreads();
+  if (!SELF && has_work) {
+    mg_mbar_wait(bar0, a_parity);
+    a_parity ^= 1;
+  }
+  const uint32_t a_base = (uint32_t)__cvta_generic_to_shared(sA);
 
-  float acc[2][2][4];
-  int q = 0;                                              // index into the stream of A (half-)tiles
+  float acc[MT][2][4];
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
 #pragma unroll
-    for (int m = 0; m < 2; ++m)
+    for (int m = 0; m < MT; ++m)
 #pragma unroll
       for (int n = 0; n < 2; ++n) acc[m][n][0] = acc[m][n][1] = acc[m][n][2] = acc[m][n][3] = 0.f;
-    for (int sc = 0; sc < n_super; ++sc, ++q) {
-      const int hf = streamed ? (q & 1) : 0;
-      if (streamed || q == 0) {                            // resident A: waited for once per phase
-        mg_mbar_wait(bar0 + hf * 8, par[hf]);
-        par[hf] ^= 1;
-      }
-      const uint32_t a_base = (uint32_t)__cvta_generic_to_shared(sA + hf * kMgRows * kMgAHalfPitch);
-      const int kc_lo = streamed ? sc * (kMgAHalf / kMgChunkK) : 0;
-      const int kc_hi = streamed ? min(chunks, kc_lo + kMgAHalf / kMgChunkK) : chunks;
-      for (int kc = kc_lo + warp; kc < kc_hi; kc += kMgWarps) {
-        ring.fill(work, lane);
-        // the oldest group in flight carries (tile, kc): wait until at most (inflight - 1) groups are pending
-        if (ring.inflight >= 3) mg_wait<2>(); else if (ring.inflight == 2) mg_wait<1>(); else mg_wait<0>();
-        __syncwarp();
-        const uint32_t st = ring.base + (ring.tail % kMgStages) * kMgStageBytes;
-        const int kcol = (kc - kc_lo) * kMgChunkK;         // column of this chunk inside the A buffer
+    for (int kc = warp; kc < chunks; kc += kMgWarps) {
+      ring.fill(work, lane);
+      ring.wait_oldest();
+      __syncwarp();
+      const uint32_t st = ring.base + (ring.tail % ring.n_stages) * ring.stage_bytes;
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-          uint32_t af[2][4], bf[4];
-          const int jm = lane >> 3, r = lane & 7;
+      for (int ks = 0; ks < 4; ++ks) {
+        uint32_t af[MT][4], bf[4];
+        const int jm = lane >> 3, r = lane & 7;
 #pragma unroll
-          for (int m = 0; m < 2; ++m)
-            mg_ldsm(af[m], a_base + (m * 16 + (jm & 1) * 8 + r) * pitch + (kcol + ks * 16 + (jm >> 1) * 8) * 2);
-          const int nrow = (jm >> 1) * 8 + r, c16 = ks * 2 + (jm & 1);
-          mg_ldsm(bf, st + nrow * 128 + ((c16 ^ (nrow & 7)) << 4));
-#pragma unroll
-          for (int m = 0; m < 2; ++m) {
-            mg_mma(acc[m][0], af[m], bf[0], bf[1]);
-            mg_mma(acc[m][1], af[m], bf[2], bf[3]);
-          }
+        for (int m = 0; m < MT; ++m) {
+          const int row = m * 16 + (jm & 1) * 8 + r;
+          if (SELF) mg_ldsm(af[m], st + kMgWBytes + row * 128 + (((ks * 2 + (jm >> 1)) ^ (row & 7)) << 4));
+          else mg_ldsm(af[m], a_base + row * kMgAPitch + (kc * kMgChunkK + ks * 16 + (jm >> 1) * 8) * 2);
         }
-        __syncwarp();
-        ++ring.tail; --ring.inflight;
+        const int nrow = (jm >> 1) * 8 + r, c16 = ks * 2 + (jm & 1);
+        mg_ldsm(bf, st + nrow * 128 + ((c16 ^ (nrow & 7)) << 4));
+#pragma unroll
+        for (int m = 0; m < MT; ++m) {
+          mg_mma(acc[m][0], af[m], bf[0], bf[1]);
+          mg_mma(acc[m][1], af[m], bf[2], bf[3]);
+        }
       }
-      if (streamed) {
-        __syncthreads();                                   // every warp is done with this half: refill it with the one after next
-        if (q + 2 < q_total && threadIdx.x == 0) load_a(q + 2);
-      }
+      __syncwarp();
+      ++ring.tail; --ring.inflight;
     }
     // ---- cross-warp reduction (fixed order) + epilogue ----
     {
       const int g = lane >> 2, t = lane & 3;
-      float* mine = sRed + warp * (kMgRows * kMgTileN);
+      float* mine = sRed + warp * (ROWS * kMgTileN);
 #pragma unroll
-      for (int m = 0; m < 2; ++m)
+      for (int m = 0; m < MT; ++m)
 #pragma unroll
         for (int n = 0; n < 2; ++n) {
           *reinterpret_cast<float2*>(mine + (m * 16 + g) * kMgTileN + n * 8 + 2 * t) = make_float2(acc[m][n][0], acc[m][n][1]);
@@ -265,14 +277,15 @@ __device__ __forceinline__ void mg_gemm_phase(const MegaArgs& a, uint8_t* smem, 
         }
     }
     __syncthreads();
-    {
-      const int row = threadIdx.x >> 3, q = threadIdx.x & 7;      // 32 rows x 8 threads
+    if ((int)threadIdx.x < ROWS * 8) {
+      constexpr int WS = ROWS * kMgTileN;                          // floats per warp partial
+      const int row = threadIdx.x >> 3, q = threadIdx.x & 7;      // ROWS rows x 8 threads
       const int n0 = tile * kMgTileN;
       if (EPI == MG_EPI_GATEUP) {
         // tile rows = [8 gate | 8 up]: thread -> output column q
         float gsum = 0.f, usum = 0.f;
 #pragma unroll
-        for (int w = 0; w < kMgWarps; ++w) { gsum += sRed[w * 512 + row * 16 + q]; usum += sRed[w * 512 + row * 16 + 8 + q]; }
+        for (int w = 0; w < kMgWarps; ++w) { gsum += sRed[w * WS + row * 16 + q]; usum += sRed[w * WS + row * 16 + 8 + q]; }
         if (row < a.B) {
           const float rs = sRs[row];
           e.out[(long long)row * e.ldo + tile * 8 + q] = __float2bfloat16_rn(silu(gsum * rs) * (usum * rs));
@@ -280,7 +293,7 @@ __device__ __forceinline__ void mg_gemm_phase(const MegaArgs& a, uint8_t* smem, 
       } else {
         float v0 = 0.f, v1 = 0.f;
 #pragma unroll
-        for (int w = 0; w < kMgWarps; ++w) { v0 += sRed[w * 512 + row * 16 + 2 * q]; v1 += sRed[w * 512 + row * 16 + 2 * q + 1]; }
+        for (int w = 0; w < kMgWarps; ++w) { v0 += sRed[w * WS + row * 16 + 2 * q]; v1 += sRed[w * WS + row * 16 + 2 * q + 1]; }
         const int c = n0 + 2 * q;
         if (EPI == MG_EPI_QKV) {
           if (row < a.B) {
@@ -320,7 +333,7 @@ __device__ __forceinline__ void mg_gemm_phase(const MegaArgs& a, uint8_t* smem, 
 
 // rs[row] = rsqrt(mean(x^2) + eps) from the per-CTA partial slots, identical in every CTA (fixed summation order)
 __device__ __forceinline__ void mg_row_scale(const MegaArgs& a, uint8_t* smem, const float* slots) {
-  float* sRs = reinterpret_cast<float*>(smem + kMgABytes + kMgRingBytes + kMgRedBytes);
+  float* sRs = reinterpret_cast<float*>(smem + kMgSmemBytes - kMgMiscBytes);
   const int row = threadIdx.x >> 3, q = threadIdx.x & 7;
   float s = 0.f;
   for (int c = q; c < (int)gridDim.x; c += 8) s += slots[c * 32 + row];
@@ -334,7 +347,8 @@ __device__ __forceinline__ void mg_row_scale(const MegaArgs& a, uint8_t* smem, c
 // ------------------------------------------------------------------------------------------------------ attention
 // item = (sequence b, kv head, key split): M-RoPE of q (and, in the last split, of the new k + cache append), then the
 // split-KV tile loop of llm.cu::decode_attn_kernel with 8 warps; the last split of a (b, kv head) to arrive merges.
-__device__ __forceinline__ void mg_attention_phase(const MegaArgs& a, uint8_t* smem, int layer) {
+__device__ __forceinline__ void mg_attention_phase(const MegaArgs& a, uint8_t* smem, int layer, int it) {
+#define MG_ASTAMP(k) do { if (a.prof != nullptr && it == 0 && layer == 1 && threadIdx.x == 0 && item == (int)blockIdx.x && (int)blockIdx.x == a.n_splits - 1) a.prof[((long long)0 * a.prof_slots + a.prof_slots - 8 + (k)) * 2] = mg_now(); } while (0)
   constexpr int HD = 128;
   const int G = a.q_heads / a.kv_heads;
   const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -347,6 +361,7 @@ __device__ __forceinline__ void mg_attention_phase(const MegaArgs& a, uint8_t* s
   const float sc = rsqrtf((float)HD) * 1.4426950408889634f;
   for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
     const int sp = item % a.n_splits, kvh = (item / a.n_splits) % a.kv_heads, b = item / (a.n_splits * a.kv_heads);
+    MG_ASTAMP(0);
     const int n = a.cache_len[b] + 1;
     const int chunk = ((n + a.n_splits - 1) / a.n_splits + 15) & ~15;
     const int t_begin = sp * chunk, t_end = min(n, t_begin + chunk);
@@ -371,29 +386,7 @@ __device__ __forceinline__ void mg_attention_phase(const MegaArgs& a, uint8_t* s
       __threadfence();
     }
     __syncthreads();
-    // ---- Q fragments of the group's heads (rows g < G), rotated: dims d and d + 64 sit in qa[ks] / qa[ks + 4] of the same lane ----
-    uint32_t qa[8][2];
-#pragma unroll
-    for (int ks = 0; ks < 8; ++ks) { qa[ks][0] = 0u; qa[ks][1] = 0u; }
-    if (g < G) {
-      const bf16* qp = a.qkv + (long long)b * ldq + (long long)(kvh * G + g) * HD + 2 * t;
-      uint32_t raw[8][2];
-#pragma unroll
-      for (int ks = 0; ks < 8; ++ks) {
-        raw[ks][0] = *reinterpret_cast<const uint32_t*>(qp + ks * 16);
-        raw[ks][1] = *reinterpret_cast<const uint32_t*>(qp + ks * 16 + 8);
-      }
-#pragma unroll
-      for (int ks = 0; ks < 4; ++ks)
-#pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
-          const int d = ks * 16 + hh * 8 + 2 * t;          // < 64
-          const float c0 = cosv[d], c1 = cosv[d + 1], s0 = sinv[d], s1 = sinv[d + 1];
-          const float x1l = bf16_lo(raw[ks][hh]), x1h = bf16_hi(raw[ks][hh]), x2l = bf16_lo(raw[ks + 4][hh]), x2h = bf16_hi(raw[ks + 4][hh]);
-          qa[ks][hh] = pack_bf16(x1l * c0 - x2l * s0, x1h * c1 - x2h * s1);
-          qa[ks + 4][hh] = pack_bf16(x2l * c0 + x1l * s0, x2h * c1 + x1h * s1);
-        }
-    }
+    MG_ASTAMP(1);
     float m = -INFINITY, l = 0.f, o[16][4];
 #pragma unroll
     for (int j = 0; j < 16; ++j) { o[j][0] = o[j][1] = o[j][2] = o[j][3] = 0.f; }
@@ -421,6 +414,31 @@ __device__ __forceinline__ void mg_attention_phase(const MegaArgs& a, uint8_t* s
     };
     issue_tile();
     issue_tile();
+    // (the first key tiles are in flight while q is fetched and rotated)
+    // ---- Q fragments of the group's heads (rows g < G), rotated: dims d and d + 64 sit in qa[ks] / qa[ks + 4] of the same lane ----
+    uint32_t qa[8][2];
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks) { qa[ks][0] = 0u; qa[ks][1] = 0u; }
+    if (g < G) {
+      const bf16* qp = a.qkv + (long long)b * ldq + (long long)(kvh * G + g) * HD + 2 * t;
+      uint32_t raw[8][2];
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks) {
+        raw[ks][0] = *reinterpret_cast<const uint32_t*>(qp + ks * 16);
+        raw[ks][1] = *reinterpret_cast<const uint32_t*>(qp + ks * 16 + 8);
+      }
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          const int d = ks * 16 + hh * 8 + 2 * t;          // < 64
+          const float c0 = cosv[d], c1 = cosv[d + 1], s0 = sinv[d], s1 = sinv[d + 1];
+          const float x1l = bf16_lo(raw[ks][hh]), x1h = bf16_hi(raw[ks][hh]), x2l = bf16_lo(raw[ks + 4][hh]), x2h = bf16_hi(raw[ks + 4][hh]);
+          qa[ks][hh] = pack_bf16(x1l * c0 - x2l * s0, x1h * c1 - x2h * s1);
+          qa[ks + 4][hh] = pack_bf16(x2l * c0 + x1l * s0, x2h * c1 + x1h * s1);
+        }
+    }
+    MG_ASTAMP(2);
     const int lr = lane & 7, lm = lane >> 3;
     for (int t0 = t_begin + w * 16; t0 < t_end; t0 += kMgAttnWarps * 16) {
       issue_tile();
@@ -467,9 +485,11 @@ __device__ __forceinline__ void mg_attention_phase(const MegaArgs& a, uint8_t* s
       st_done = (st_done == (kMgAttnStages - 1) * kMgAttnTileBytes) ? 0u : st_done + kMgAttnTileBytes;
     }
     mg_wait<0>();
+    MG_ASTAMP(3);
     l += __shfl_xor_sync(0xffffffffu, l, 1);
     l += __shfl_xor_sync(0xffffffffu, l, 2);
     __syncthreads();
+    MG_ASTAMP(4);
     float* sm_o = reinterpret_cast<float*>(smem);              // [warps][8][HD]
     float* sm_m = sm_o + kMgAttnWarps * 8 * HD;
     float* sm_l = sm_m + kMgAttnWarps * 8;
@@ -478,26 +498,32 @@ __device__ __forceinline__ void mg_attention_phase(const MegaArgs& a, uint8_t* s
     for (int j = 0; j < 16; ++j)
       *reinterpret_cast<float2*>(&sm_o[(w * 8 + g) * HD + j * 8 + 2 * t]) = make_float2(o[j][0], o[j][1]);
     __syncthreads();
-    // merge the 8 warps: thread -> (head r = tid / 128 ... ), 256 threads = 2 heads x 128 dims per pass
-    for (int r = threadIdx.x >> 7; r < G; r += 2) {
-      const int d = threadIdx.x & 127;
-      float mm = -INFINITY;
+    // merge the 8 warps: thread -> (head r = tid / 32, dims 4 * (tid % 32) ..), warps in index order
+    {
+      const int r = threadIdx.x >> 5, d4 = (threadIdx.x & 31) * 4;
+      if (r < G) {
+        float mm = -INFINITY;
 #pragma unroll
-      for (int ww = 0; ww < kMgAttnWarps; ++ww) mm = fmaxf(mm, sm_m[ww * 8 + r]);
-      float num = 0.f, den = 0.f;
+        for (int ww = 0; ww < kMgAttnWarps; ++ww) mm = fmaxf(mm, sm_m[ww * 8 + r]);
+        float4 num = make_float4(0.f, 0.f, 0.f, 0.f);
+        float den = 0.f;
 #pragma unroll
-      for (int ww = 0; ww < kMgAttnWarps; ++ww) {
-        const float f = (sm_m[ww * 8 + r] == -INFINITY) ? 0.f : exp2f(sm_m[ww * 8 + r] - mm);
-        num += sm_o[(ww * 8 + r) * HD + d] * f;
-        den += sm_l[ww * 8 + r] * f;
+        for (int ww = 0; ww < kMgAttnWarps; ++ww) {
+          const float f = (sm_m[ww * 8 + r] == -INFINITY) ? 0.f : exp2f(sm_m[ww * 8 + r] - mm);
+          const float4 v = *reinterpret_cast<const float4*>(&sm_o[(ww * 8 + r) * HD + d4]);
+          num.x += v.x * f; num.y += v.y * f; num.z += v.z * f; num.w += v.w * f;
+          den += sm_l[ww * 8 + r] * f;
+        }
+        float* rec = a.att_part + (((long long)b * a.q_heads + kvh * G + r) * kMgMaxSplits + sp) * (HD + 4);
+        if (d4 == 0) { rec[0] = mm; rec[1] = den; }
+        *reinterpret_cast<float4*>(rec + 4 + d4) = num;
       }
-      float* rec = a.att_part + (((long long)b * a.q_heads + kvh * G + r) * kMgMaxSplits + sp) * (HD + 4);
-      if (d == 0) { rec[0] = mm; rec[1] = den; }
-      rec[4 + d] = num;
     }
     // ---- last split of this (b, kv head) to arrive merges the splits in index order ----
+    MG_ASTAMP(5);
     __threadfence();
     __syncthreads();
+    MG_ASTAMP(6);
     if (threadIdx.x == 0) {
       const int prev = atomicAdd(a.att_count + b * a.kv_heads + kvh, 1);
       s_last = (prev == a.n_splits - 1) ? 1 : 0;
@@ -506,40 +532,70 @@ __device__ __forceinline__ void mg_attention_phase(const MegaArgs& a, uint8_t* s
     __syncthreads();
     if (s_last) {
       __threadfence();
-      for (int r = threadIdx.x >> 7; r < G; r += 2) {
-        const int d = threadIdx.x & 127;
-        const float* rec = a.att_part + (((long long)b * a.q_heads + kvh * G + r) * kMgMaxSplits) * (HD + 4);
-        float mm = -INFINITY;
-        for (int s2 = 0; s2 < a.n_splits; ++s2) mm = fmaxf(mm, __ldcg(rec + s2 * (HD + 4)));
-        float num = 0.f, den = 0.f;
-        for (int s2 = 0; s2 < a.n_splits; ++s2) {
-          const float ms = __ldcg(rec + s2 * (HD + 4));
-          const float f = (ms == -INFINITY) ? 0.f : exp2f(ms - mm);
-          num += __ldcg(rec + s2 * (HD + 4) + 4 + d) * f;
-          den += __ldcg(rec + s2 * (HD + 4) + 1) * f;
+      // stage the G x n_splits records in shared memory with independent 16-byte loads (one L2 round trip instead of a
+      // dependent chain per head), then merge from there in split order
+      constexpr int kRecF4 = (HD + 4) / 4;
+      float* st = reinterpret_cast<float*>(smem + kMgCombineOff);
+      const int total = G * a.n_splits * kRecF4;
+      float4 v[kMgCombineLoads];
+#pragma unroll
+      for (int k = 0; k < kMgCombineLoads; ++k) {
+        const int i = threadIdx.x + k * kMgThreads;
+        if (i < total) {
+          const int rc = i / kRecF4, c = i - rc * kRecF4;
+          const int r = rc / a.n_splits, s2 = rc - r * a.n_splits;
+          v[k] = __ldcg(reinterpret_cast<const float4*>(a.att_part + (((long long)b * a.q_heads + kvh * G + r) * kMgMaxSplits + s2) * (HD + 4)) + c);
         }
-        a.att[(long long)b * a.QD + (long long)(kvh * G + r) * HD + d] = __float2bfloat16_rn(num / den);
+      }
+#pragma unroll
+      for (int k = 0; k < kMgCombineLoads; ++k) {
+        const int i = threadIdx.x + k * kMgThreads;
+        if (i < total) reinterpret_cast<float4*>(st)[i] = v[k];
+      }
+      __syncthreads();                                           // (s_last is uniform over the block)
+      const int r = threadIdx.x >> 5, d4 = (threadIdx.x & 31) * 4;
+      if (r < G) {
+        const float* rec = st + (long long)r * a.n_splits * (HD + 4);
+        float mm = -INFINITY;
+        for (int s2 = 0; s2 < a.n_splits; ++s2) mm = fmaxf(mm, rec[s2 * (HD + 4)]);
+        float4 num = make_float4(0.f, 0.f, 0.f, 0.f);
+        float den = 0.f;
+        for (int s2 = 0; s2 < a.n_splits; ++s2) {
+          const float ms = rec[s2 * (HD + 4)];
+          const float f = (ms == -INFINITY) ? 0.f : exp2f(ms - mm);
+          const float4 v = *reinterpret_cast<const float4*>(rec + s2 * (HD + 4) + 4 + d4);
+          num.x += v.x * f; num.y += v.y * f; num.z += v.z * f; num.w += v.w * f;
+          den += rec[s2 * (HD + 4) + 1] * f;
+        }
+        uint2 o2;
+        o2.x = pack_bf16(num.x / den, num.y / den);
+        o2.y = pack_bf16(num.z / den, num.w / den);
+        *reinterpret_cast<uint2*>(a.att + (long long)b * a.QD + (long long)(kvh * G + r) * HD + d4) = o2;
       }
     }
     __syncthreads();
+    MG_ASTAMP(7);
   }
 }
 
 // ----------------------------------------------------------------------------------------------------------- kernel
+template <int MT>
 __global__ void __launch_bounds__(kMgThreads, 1) decode_mega_kernel(const MegaArgs a) {
+  using Lay = MgLay<MT>;
   extern __shared__ __align__(128) uint8_t mg_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   unsigned gen = 0;
-  uint64_t* sBar = reinterpret_cast<uint64_t*>(mg_smem + kMgABytes + kMgRingBytes + kMgRedBytes + 256);
+  const uint32_t smem0 = (uint32_t)__cvta_generic_to_shared(mg_smem);
+  uint64_t* sBar = reinterpret_cast<uint64_t*>(mg_smem + Lay::kMisc + 256);
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 2; ++i) asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(sBar + i)) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(sBar)) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
   MgRing ring;
-  ring.init((uint32_t)__cvta_generic_to_shared(mg_smem + kMgABytes) + warp * kMgStages * kMgStageBytes);
+  ring.mode(smem0, warp, kMgWBytes, Lay::kStagesRes);
   MgWork work;
-  uint32_t a_par[2] = {0, 0};         // phase parities of the two A barriers (0: resident tile / even halves, 1: odd halves)
+  uint32_t a_par = 0;                 // phase parity of the resident-A barrier
   float* ssq_x = a.ssq;                                   // [grid][32]
   float* ssq_mid = a.ssq + (long long)gridDim.x * 32;
   const int ldq = a.QD + 2 * a.KD;
@@ -590,32 +646,35 @@ __global__ void __launch_bounds__(kMgThreads, 1) decode_mega_kernel(const MegaAr
       // ---- qkv = rs * (W' x) + b ----
       mg_row_scale(a, mg_smem, ssq_x);
       e.out = a.qkv; e.ldo = ldq; e.bias = W.qkv_b; e.resid = nullptr; e.ssq_slot = nullptr; e.scale_rows = true;
-      mg_gemm_phase<MG_EPI_QKV>(a, mg_smem, a.x, a.H, a.H, W.qkv_w, ldq, work, ring, e, a_par, nullptr, nullptr);
-      mg_wait<0>();
-      ring.inflight = 0; ring.head = ring.tail = 0;          // the attention ring aliases the weight ring: drain it first
+      mg_gemm_phase<MG_EPI_QKV, MT, false>(a, mg_smem, a.x, a.H, a.H, ldq, work, ring, e, a_par, nullptr, nullptr);
+      mg_wait<0>();                                          // (nothing is in flight: the attention ring aliases the weight ring)
       MG_STAMP(slot, 0); mg_grid_sync(a.bar, gen); MG_STAMP(slot, 1); ++slot;
       // ---- attention (rope, cache append, split-KV tiles, combine) ----
-      mg_attention_phase(a, mg_smem, L);
+      mg_attention_phase(a, mg_smem, L, it);
       __syncthreads();
+      ring.mode(smem0, warp, kMgWBytes, Lay::kStagesRes);
       work.begin(W.o_w, a.QD, a.H, warp);
       ring.fill(work, lane);
       MG_STAMP(slot, 0); mg_grid_sync(a.bar, gen); MG_STAMP(slot, 1); ++slot;
       // ---- x_mid = x + att . Wo^T ----
       e.out = a.x_mid; e.ldo = a.H; e.bias = nullptr; e.resid = a.x; e.ssq_slot = ssq_mid + blockIdx.x * 32; e.scale_rows = false;
-      mg_gemm_phase<MG_EPI_RESID>(a, mg_smem, a.att, a.QD, a.QD, W.o_w, a.H, work, ring, e, a_par, nullptr, nullptr);
+      mg_gemm_phase<MG_EPI_RESID, MT, false>(a, mg_smem, a.att, a.QD, a.QD, a.H, work, ring, e, a_par, nullptr, nullptr);
       work.begin(W.gu_w, a.H, 2 * a.I, warp);
       ring.fill(work, lane);
       MG_STAMP(slot, 0); mg_grid_sync(a.bar, gen); MG_STAMP(slot, 1); ++slot;
       // ---- h = silu(rs * Wg' x_mid) * (rs * Wu' x_mid) ----
       mg_row_scale(a, mg_smem, ssq_mid);
       e.out = a.h; e.ldo = a.I; e.resid = nullptr; e.ssq_slot = nullptr; e.scale_rows = true;
-      mg_gemm_phase<MG_EPI_GATEUP>(a, mg_smem, a.x_mid, a.H, a.H, W.gu_w, 2 * a.I, work, ring, e, a_par, nullptr, nullptr);
-      work.begin(W.down_w, a.I, a.H, warp);
-      ring.fill(work, lane);
+      mg_gemm_phase<MG_EPI_GATEUP, MT, false>(a, mg_smem, a.x_mid, a.H, a.H, 2 * a.I, work, ring, e, a_par, nullptr, nullptr);
+      // down-proj: self-contained stages (weights + the A slice); only the WEIGHT half could be prefetched before the barrier, so the
+      // ring is re-configured here and filled after it (h is complete only then)
+      ring.mode(smem0, warp, Lay::kSelfStage, Lay::kStagesSelf);
+      work.begin(W.down_w, a.I, a.H, warp, a.h, a.I, a.B, 16 * MT);
       MG_STAMP(slot, 0); mg_grid_sync(a.bar, gen); MG_STAMP(slot, 1); ++slot;
       // ---- x = x_mid + h . Wd^T ----
       e.out = a.x; e.ldo = a.H; e.resid = a.x_mid; e.ssq_slot = ssq_x + blockIdx.x * 32; e.scale_rows = false;
-      mg_gemm_phase<MG_EPI_RESID>(a, mg_smem, a.h, a.I, a.I, W.down_w, a.H, work, ring, e, a_par, nullptr, nullptr);
+      mg_gemm_phase<MG_EPI_RESID, MT, true>(a, mg_smem, a.h, a.I, a.I, a.H, work, ring, e, a_par, nullptr, nullptr);
+      ring.mode(smem0, warp, kMgWBytes, Lay::kStagesRes);
       if (L + 1 < a.layers) work.begin(a.layer[L + 1].qkv_w, a.H, ldq, warp);
       else work.begin(a.head_w, a.H, a.V, warp);
       ring.fill(work, lane);
@@ -628,7 +687,7 @@ __global__ void __launch_bounds__(kMgThreads, 1) decode_mega_kernel(const MegaAr
       MgEpi e;
       e.out = nullptr; e.ldo = 0; e.bias = nullptr; e.resid = nullptr; e.ssq_slot = nullptr; e.scale_rows = true;
       mg_row_scale(a, mg_smem, ssq_x);
-      mg_gemm_phase<MG_EPI_HEAD>(a, mg_smem, a.x, a.H, a.H, a.head_w, a.V, work, ring, e, a_par, &best_val, &best_idx);
+      mg_gemm_phase<MG_EPI_HEAD, MT, false>(a, mg_smem, a.x, a.H, a.H, a.V, work, ring, e, a_par, &best_val, &best_idx);
       // the 8 threads of a row hold disjoint columns: merge (lowest index among equal maxima)
 #pragma unroll
       for (int o2 = 1; o2 < 8; o2 <<= 1) {
@@ -693,9 +752,13 @@ int decode_mega_grid() {
     grid = 0;
     int dev = 0, coop = 0, per_sm = 0;
     if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev) == cudaSuccess && coop &&
-        cudaFuncSetAttribute(decode_mega_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kMgSmemBytes) == cudaSuccess &&
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_mega_kernel, kMgThreads, kMgSmemBytes) == cudaSuccess && per_sm >= 1)
+        cudaFuncSetAttribute(decode_mega_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMgSmemBytes) == cudaSuccess &&
+        cudaFuncSetAttribute(decode_mega_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMgSmemBytes) == cudaSuccess &&
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, decode_mega_kernel<2>, kMgThreads, kMgSmemBytes) == cudaSuccess && per_sm >= 1)
       grid = device_sm_count();
+    else
+      fprintf(stderr, "[fo1] decode_mega: cooperative launch with %d B of shared memory is not available (%s); using the per-kernel decode path\n",
+              kMgSmemBytes, cudaGetErrorString(cudaGetLastError()));
     cudaGetLastError();
   }
   return grid;
@@ -706,13 +769,14 @@ int decode_mega_run(const MegaArgs& a, cudaStream_t s) {
   const int grid = decode_mega_grid();
   FO1_CHECK_ARG(grid > 0, "decode_mega: cooperative launch of a %d-byte-smem CTA per SM is not available on this device", kMgSmemBytes);
   FO1_CHECK_ARG(a.B >= 1 && a.B <= kMgRows && a.hd == 128 && a.q_heads % a.kv_heads == 0 && a.q_heads / a.kv_heads <= 8, "decode_mega: unsupported shape");
-  FO1_CHECK_ARG(a.H % kMgChunkK == 0 && a.H <= kMgAK && a.QD <= kMgAK && a.I % kMgChunkK == 0 && (a.QD + 2 * a.KD) % kMgTileN == 0 &&
-                a.H % kMgTileN == 0 && (2 * a.I) % kMgTileN == 0 && a.V % kMgTileN == 0 && (a.H / kMgChunkK) >= kMgWarps,
+  FO1_CHECK_ARG(a.H % kMgChunkK == 0 && a.QD % kMgChunkK == 0 && a.H <= kMgAK && a.QD <= kMgAK && a.I % kMgChunkK == 0 && (a.QD + 2 * a.KD) % kMgTileN == 0 &&
+                a.H % kMgTileN == 0 && (2 * a.I) % kMgTileN == 0 && a.V % kMgTileN == 0 && (a.H / kMgChunkK) >= kMgWarps && (a.QD / kMgChunkK) >= kMgWarps,
                 "decode_mega: widths must be multiples of the 16 x 64 tile (H %d, QD %d, I %d, V %d)", a.H, a.QD, a.I, a.V);
   MegaArgs args = a;
   void* params[] = {&args};
   ProfScope prof("decode_mega", 0.0, 0.0, s);
-  FO1_CUDA(cudaLaunchCooperativeKernel(reinterpret_cast<void*>(decode_mega_kernel), dim3(grid), dim3(kMgThreads), params, kMgSmemBytes, s));
+  void* fn = a.B <= 16 ? reinterpret_cast<void*>(decode_mega_kernel<1>) : reinterpret_cast<void*>(decode_mega_kernel<2>);
+  FO1_CUDA(cudaLaunchCooperativeKernel(fn, dim3(grid), dim3(kMgThreads), params, kMgSmemBytes, s));
   count_launch();
   return FO1_OK;
 }

@@ -531,7 +531,12 @@ static int llm_generate_impl(Model* m, fo1_generate_desc* d, cudaStream_t s, boo
   int* d_lens = A.alloc<int>(B);
   int* d_deltas = A.alloc<int>(B);
   // persistent decode kernel (decode_mega.cu): per-CTA slots + the grid barrier
-  const int mega_grid = (m->llm.mega_ok && B <= 32 && getenv("FO1_NO_MEGA") == nullptr) ? decode_mega_grid() : 0;
+  // measured with warm clocks, alternating the two paths (scripts/mega_prof.py, profiles/README.md round 2): the persistent kernel
+  // beats the per-kernel graph at every batch it supports (1..32 sequences: -8 % .. -19 % per step).  FO1_MEGA_MAX_B lowers the
+  // threshold, FO1_NO_MEGA disables the kernel.
+  int mega_max_b = 32;
+  if (const char* e = getenv("FO1_MEGA_MAX_B")) mega_max_b = std::max(0, std::min(32, atoi(e)));
+  const int mega_grid = (m->llm.mega_ok && B <= mega_max_b && getenv("FO1_NO_MEGA") == nullptr) ? decode_mega_grid() : 0;
   float* mg_ssq = A.alloc<float>((size_t)2 * std::max(mega_grid, 1) * 32);
   float* mg_amax_v = A.alloc<float>((size_t)std::max(mega_grid, 1) * 32);
   int* mg_amax_i = A.alloc<int>((size_t)std::max(mega_grid, 1) * 32);
@@ -637,7 +642,7 @@ static int llm_generate_impl(Model* m, fo1_generate_desc* d, cudaStream_t s, boo
     a.n_splits = std::max(1, std::min(kMgMaxSplits, mega_grid / std::max(1, pairs)));
     FO1_CUDA(cudaMemsetAsync(mg_sync, 0, ((size_t)pairs + 8) * sizeof(int), s));
     unsigned long long* d_prof = nullptr;
-    const int prof_slots = 5 * c.llm_layers + 3;
+    const int prof_slots = 5 * c.llm_layers + 3 + 8;     // + 8 sub-stamps of one attention item (CTA 0, layer 1)
     if (getenv("FO1_MEGA_PROF") != nullptr) {       // diagnostic: where a decode iteration spends its time (stderr)
       FO1_CUDA(cudaMalloc(reinterpret_cast<void**>(&d_prof), (size_t)mega_grid * prof_slots * 2 * sizeof(unsigned long long)));
       FO1_CUDA(cudaMemsetAsync(d_prof, 0, (size_t)mega_grid * prof_slots * 2 * sizeof(unsigned long long), s));
@@ -654,7 +659,7 @@ static int llm_generate_impl(Model* m, fo1_generate_desc* d, cudaStream_t s, boo
       const char* names[5] = {"qkv", "attn", "oproj", "gateup", "down"};
       double tot[5][3] = {{0}}, misc = 0;
       unsigned long long prev_release = 0;
-      for (int sl = 0; sl < prof_slots; ++sl) {
+      for (int sl = 0; sl < prof_slots - 8; ++sl) {
         unsigned long long first = ~0ull, last = 0, rel = 0;
         for (int cta = 0; cta < mega_grid; ++cta) {
           const unsigned long long e = h[((size_t)cta * prof_slots + sl) * 2], l = h[((size_t)cta * prof_slots + sl) * 2 + 1];
@@ -673,6 +678,21 @@ static int llm_generate_impl(Model* m, fo1_generate_desc* d, cudaStream_t s, boo
         fprintf(stderr, "%s work %.1f (skew %.1f) barrier %.1f | ", names[ph], tot[ph][0] / c.llm_layers / 1e3, tot[ph][1] / c.llm_layers / 1e3,
                 tot[ph][2] / c.llm_layers / 1e3);
       fprintf(stderr, "head+update %.1f us\n", misc / 1e3);
+      {   // distribution over CTAs of the time spent in layer 1's attention phase (slot 7: enter of the barrier after it; slot 6: leave before it)
+        std::vector<std::pair<double, int>> dur;
+        for (int cta = 0; cta < mega_grid; ++cta)
+          dur.push_back({(double)(h[((size_t)cta * prof_slots + 7) * 2] - h[((size_t)cta * prof_slots + 6) * 2 + 1]) / 1e3, cta});
+        std::sort(dur.begin(), dur.end());
+        fprintf(stderr, "[decode_mega profile] attention phase per CTA (us): min %.1f p25 %.1f median %.1f p75 %.1f max %.1f; slowest CTAs:", dur[0].first,
+                dur[mega_grid / 4].first, dur[mega_grid / 2].first, dur[3 * mega_grid / 4].first, dur.back().first);
+        for (int k = 0; k < 6; ++k) fprintf(stderr, " %d(%.1f)", dur[mega_grid - 1 - k].second, dur[mega_grid - 1 - k].first);
+        fprintf(stderr, "\n");
+      }
+      fprintf(stderr, "[decode_mega profile] attention item of CTA 0, layer 1 (us since its start): ");
+      const unsigned long long a0 = h[((size_t)0 * prof_slots + prof_slots - 8) * 2];
+      const char* an[8] = {"start", "append+fence", "q rotated", "tiles done", "warps synced", "partials written", "fence+sync", "combined"};
+      for (int k = 0; k < 8; ++k) fprintf(stderr, "%s %.1f | ", an[k], (double)(h[((size_t)0 * prof_slots + prof_slots - 8 + k) * 2] - a0) / 1e3);
+      fprintf(stderr, "\n");
     }
     d->steps_run = d->max_new_tokens - 1;
     return FO1_OK;

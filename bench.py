@@ -424,7 +424,10 @@ def main():
             torch.cuda.synchronize()
             dms = (e1.elapsed_time(e2) - e0.elapsed_time(e1)) / (T - 2)
             ach = (wbytes + kv) / dms / 1e6
-            line["roofline_decode"] = {"kernel": "one greedy decode step (CUDA graph of the per-layer kernels)", "bound": "hbm", "achieved": ach,
+            path = pipe.eng.last_decode_path()
+            kname = ("decode_mega_kernel (persistent cooperative kernel: the whole greedy loop in one launch), per decode step" if path == 1
+                     else "one greedy decode step (CUDA graph of the per-layer kernels)")
+            line["roofline_decode"] = {"kernel": kname, "bound": "hbm", "achieved": ach,
                                        "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"], "traffic": None,
                                        "algorithmic_bytes": wbytes + kv, "weight_bytes": wbytes, "kv_bytes": kv, "ms_per_step": dms,
                                        "share_of_step": dms * (T - 1) / step_ms}

@@ -157,6 +157,12 @@ size_t fo1_channel_attention_workspace_bytes(int32_t n_images, int32_t n_tokens,
 int fo1_channel_attention(const void* qkv, int32_t n_images, int32_t n_tokens, int32_t channels, int32_t groups, void* out,
                           void* workspace, size_t workspace_bytes, void* stream);
 
+/* DaViT conditional position encoding (PreNorm(None, DepthWiseConv2d), modeling_davit.py:29-48, 72-99): y = x + dwconv3x3(x) + bias over
+ * NHWC bf16 maps [n_images][height][width][channels]; w9 bf16 [9][channels] (tap-major repack of [channels][1][3][3]), bias bf16
+ * [channels].  channels % 8 == 0; x and y must not alias.  Exposed for the parity test of the kernel; fo1_davit_forward runs the same code. */
+int fo1_dwconv3x3_residual(const void* x, const void* w9, const void* bias, void* y, int32_t n_images, int32_t height, int32_t width,
+                           int32_t channels, void* stream);
+
 /* Single-query GQA attention of one decode step over the K/V cache (the per-step attention of the HF generate loop,
  * modeling_qwen2_5_vl.py:731-780 with past_key_values; mm_utils.py:640-654 drives it).  The step's own K/V must already
  * sit in the cache at index cache_len[b].  head_dim 128, q_heads / kv_heads <= 8.  Exposed so the parity tests can
@@ -207,6 +213,9 @@ int fo1_model_create(const fo1_model_config* cfg, fo1_model** out);
 /* Entries of the handle's cache of device-side integer tables (window indices, cu_seqlens ...).  The cache is trimmed
  * only at the entry of a forward, never while one is using its tables; exposed for the test of that rule. */
 int fo1_int_cache_entries(fo1_model* m);
+/* Which decode path the handle's last fo1_generate took: 1 = the persistent kernel (decode_mega.cu, the whole greedy loop as one
+ * cooperative launch), 0 = the per-kernel CUDA graph, -1 = no generate yet.  Reported by bench.py next to the decode roofline. */
+int fo1_last_decode_path(fo1_model* m);
 void fo1_model_destroy(fo1_model* m);
 /* Register one prepared weight (device pointer, borrowed).  Names: see DESIGN.md / vlm-fo1_b200/weights.py. */
 int fo1_model_set_weight(fo1_model* m, const char* name, const void* dev_ptr, int32_t dtype, int32_t ndim,

@@ -72,6 +72,8 @@ def lib() -> C.CDLL:
     L.fo1_abi_version.restype = C.c_int
     L.fo1_last_error.restype = C.c_char_p
     L.fo1_launch_count.restype = C.c_uint64
+    L.fo1_last_decode_path.restype = C.c_int
+    L.fo1_last_decode_path.argtypes = [C.c_void_p]
     L.fo1_launch_count_reset.restype = None
     L.fo1_hfre_workspace_bytes.restype = C.c_size_t
     L.fo1_hfre_workspace_bytes.argtypes = [C.POINTER(HfreImage), C.c_int32, C.POINTER(HfreParams)]

@@ -55,6 +55,68 @@ __global__ void __launch_bounds__(256) dwconv3x3_res_kernel(const bf16* __restri
   }
 }
 
+// Same operator, HBM-bound layout (DaViT stages: C = 256 .. 2048, a multiple of 256).  A block is 8 adjacent pixels x 32 channel
+// vectors (one warp = the 512 contiguous bytes of one pixel) and walks a strip of R rows downwards with the 3 x 3 window of every
+// thread in registers: three 16-byte loads per output instead of nine, the horizontal neighbours are loaded by the neighbouring
+// warps of the same block in the same iteration (L1 hits), so DRAM sees each input row once per strip (+ the 2 halo rows).
+// Arithmetic identical to dwconv3x3_res_kernel (bias first, taps in (dy, dx) order, zero padding contributes exact zeros).
+constexpr int kDwTx = 8;
+__global__ void __launch_bounds__(256, 2) dwconv3x3_res_strip_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w9,
+                                                                     const bf16* __restrict__ bias, bf16* __restrict__ y, int H, int W,
+                                                                     int C, int R, int strips_x, int strips_y, int cblocks) {
+  int bid = blockIdx.x;
+  const int cb = bid % cblocks; bid /= cblocks;
+  const int sx = bid % strips_x; bid /= strips_x;
+  const int sy = bid % strips_y;
+  const int b = bid / strips_y;
+  const int c8 = cb * 32 + (threadIdx.x & 31);
+  const int px = sx * kDwTx + (threadIdx.x >> 5);
+  const int y0 = sy * R, y1 = min(H, y0 + R);
+  const bool active = px < W;
+  uint4 wv[9];
+#pragma unroll
+  for (int t = 0; t < 9; ++t) wv[t] = *reinterpret_cast<const uint4*>(w9 + (long long)t * C + c8 * 8);
+  const uint4 bv = *reinterpret_cast<const uint4*>(bias + c8 * 8);
+  const bf16* xb = x + (long long)b * H * W * C + c8 * 8;
+  bf16* yb = y + (long long)b * H * W * C + c8 * 8;
+  const uint4 zero = make_uint4(0, 0, 0, 0);
+  auto load_row = [&](int yy, uint4 (&r)[3]) {
+    if (yy < 0 || yy >= H || !active) { r[0] = r[1] = r[2] = zero; return; }
+    const bf16* row = xb + (long long)yy * W * C;
+    r[0] = px > 0 ? *reinterpret_cast<const uint4*>(row + (long long)(px - 1) * C) : zero;
+    r[1] = *reinterpret_cast<const uint4*>(row + (long long)px * C);
+    r[2] = px + 1 < W ? *reinterpret_cast<const uint4*>(row + (long long)(px + 1) * C) : zero;
+  };
+  uint4 win[3][3];
+  load_row(y0 - 1, win[0]);
+  load_row(y0, win[1]);
+  for (int py = y0; py < y1; ++py) {
+    load_row(py + 1, win[2]);
+    float acc[8] = {bf16_lo(bv.x), bf16_hi(bv.x), bf16_lo(bv.y), bf16_hi(bv.y), bf16_lo(bv.z), bf16_hi(bv.z), bf16_lo(bv.w), bf16_hi(bv.w)};
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) {
+        const uint4 v = win[dy][dx], w = wv[dy * 3 + dx];
+        acc[0] = fmaf(bf16_lo(v.x), bf16_lo(w.x), acc[0]); acc[1] = fmaf(bf16_hi(v.x), bf16_hi(w.x), acc[1]);
+        acc[2] = fmaf(bf16_lo(v.y), bf16_lo(w.y), acc[2]); acc[3] = fmaf(bf16_hi(v.y), bf16_hi(w.y), acc[3]);
+        acc[4] = fmaf(bf16_lo(v.z), bf16_lo(w.z), acc[4]); acc[5] = fmaf(bf16_hi(v.z), bf16_hi(w.z), acc[5]);
+        acc[6] = fmaf(bf16_lo(v.w), bf16_lo(w.w), acc[6]); acc[7] = fmaf(bf16_hi(v.w), bf16_hi(w.w), acc[7]);
+      }
+    if (active) {
+      const uint4 c = win[1][1];
+      uint4 o;   // the conv output is a bf16 tensor in the reference; the residual add happens on bf16 values
+      o.x = pack_bf16(bf16_lo(c.x) + __bfloat162float(__float2bfloat16_rn(acc[0])), bf16_hi(c.x) + __bfloat162float(__float2bfloat16_rn(acc[1])));
+      o.y = pack_bf16(bf16_lo(c.y) + __bfloat162float(__float2bfloat16_rn(acc[2])), bf16_hi(c.y) + __bfloat162float(__float2bfloat16_rn(acc[3])));
+      o.z = pack_bf16(bf16_lo(c.z) + __bfloat162float(__float2bfloat16_rn(acc[4])), bf16_hi(c.z) + __bfloat162float(__float2bfloat16_rn(acc[5])));
+      o.w = pack_bf16(bf16_lo(c.w) + __bfloat162float(__float2bfloat16_rn(acc[6])), bf16_hi(c.w) + __bfloat162float(__float2bfloat16_rn(acc[7])));
+      *reinterpret_cast<uint4*>(yb + ((long long)py * W + px) * C) = o;
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { win[0][k] = win[1][k]; win[1][k] = win[2][k]; }
+  }
+}
+
 // im2col for a 3x3 / pad 1 / stride s convolution over NHWC: dst[(b,oy,ox)][(ky,kx,c)]
 __global__ void __launch_bounds__(256) im2col3x3_kernel(const bf16* __restrict__ x, bf16* __restrict__ col, int B, int H, int W,
                                                         int C, int Ho, int Wo, int stride) {
@@ -169,6 +231,15 @@ static inline int grid_for(long long items) {
 int dwconv3x3_residual(const bf16* x, const bf16* w9, const bf16* bias, bf16* y, int B, int H, int W, int C, cudaStream_t s) {
   FO1_CHECK_ARG(C % 8 == 0, "dwconv3x3: C=%d must be a multiple of 8", C);
   if ((long long)B * H * W == 0) return FO1_OK;
+  if (C % 256 == 0 && getenv("FO1_DWCONV_SIMPLE") == nullptr) {
+    const int R = H >= 48 ? 16 : (H >= 24 ? 12 : H);
+    const int strips_x = ceil_div(W, kDwTx), strips_y = ceil_div(H, R), cblocks = C / 256;
+    const long long blocks = (long long)B * strips_y * strips_x * cblocks;
+    FO1_CHECK_ARG(blocks < (1LL << 31), "dwconv3x3: too many blocks");
+    dwconv3x3_res_strip_kernel<<<(unsigned)blocks, 256, 0, s>>>(x, w9, bias, y, H, W, C, R, strips_x, strips_y, cblocks);
+    FO1_LAUNCH_CHECK();
+    return FO1_OK;
+  }
   dwconv3x3_res_kernel<<<grid_for((long long)B * H * W * (C / 8)), 256, 0, s>>>(x, w9, bias, y, B, H, W, C);
   FO1_LAUNCH_CHECK();
   return FO1_OK;
@@ -242,3 +313,13 @@ int pixel_shuffle2x(const bf16* src, bf16* dst, int B, int H, int W, int C, cuda
   return FO1_OK;
 }
 }  // namespace fo1
+
+extern "C" int fo1_dwconv3x3_residual(const void* x, const void* w9, const void* bias, void* y, int32_t n_images, int32_t height, int32_t width,
+                                      int32_t channels, void* stream) {
+  using namespace fo1;
+  FO1_CHECK_ARG(x && w9 && bias && y && x != y && n_images >= 0 && height >= 0 && width >= 0 && channels > 0, "fo1_dwconv3x3_residual: bad argument");
+  FO1_CHECK_ARG(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(w9) | reinterpret_cast<uintptr_t>(bias)) & 15) == 0,
+                "fo1_dwconv3x3_residual: pointers must be 16-byte aligned");
+  return dwconv3x3_residual(static_cast<const bf16*>(x), static_cast<const bf16*>(w9), static_cast<const bf16*>(bias), static_cast<bf16*>(y), n_images,
+                            height, width, channels, static_cast<cudaStream_t>(stream));
+}

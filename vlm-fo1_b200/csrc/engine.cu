@@ -46,6 +46,7 @@ using namespace fo1;
 
 
 extern "C" int fo1_int_cache_entries(fo1_model* m) { return m ? (int)m->int_cache.size() : 0; }
+extern "C" int fo1_last_decode_path(fo1_model* m) { return m ? m->last_decode_path : -1; }
 
 extern "C" int fo1_model_create(const fo1_model_config* cfg, fo1_model** out) {
   FO1_CHECK_ARG(cfg && out, "fo1_model_create: null argument");

@@ -83,6 +83,7 @@ struct Model {
   bool finalized = false;
   Arena arena;
   std::map<std::string, DeviceInts> int_cache;  // keyed by a shape signature
+  int last_decode_path = -1;                    // fo1_last_decode_path(): 1 persistent kernel, 0 per-kernel graph
   // LLM state (llm.cu)
   void* kv_cache = nullptr;
   size_t kv_bytes = 0;

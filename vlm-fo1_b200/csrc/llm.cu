@@ -649,6 +649,7 @@ static int llm_generate_impl(Model* m, fo1_generate_desc* d, cudaStream_t s, boo
       a.prof = d_prof; a.prof_slots = prof_slots;
     }
     FO1_TRY(decode_mega_run(a, s));
+    m->last_decode_path = 1;
     if (d_prof != nullptr) {
       std::vector<unsigned long long> h((size_t)mega_grid * prof_slots * 2);
       FO1_CUDA(cudaStreamSynchronize(s));
@@ -698,6 +699,7 @@ static int llm_generate_impl(Model* m, fo1_generate_desc* d, cudaStream_t s, boo
     return FO1_OK;
   }
   cudaGraphExec_t gexec = nullptr;
+  m->last_decode_path = 0;
   const bool want_graph = !g_prof_on && d->max_new_tokens > 3 && getenv("FO1_NO_GRAPH") == nullptr;
   d->steps_run = 0;
   int rc = FO1_OK;

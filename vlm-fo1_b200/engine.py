@@ -117,6 +117,10 @@ class Engine:
         except Exception:
             pass
 
+    def last_decode_path(self) -> int:
+        """1: the last generate() ran the persistent decode kernel, 0: the per-kernel CUDA graph, -1: none yet."""
+        return int(lib().fo1_last_decode_path(self._h))
+
     # ---- weights ----
     def set_weights(self, tensors: Dict[str, torch.Tensor]) -> None:
         L = lib()

@@ -112,6 +112,21 @@ def decode_attention(q: torch.Tensor, k_cache: torch.Tensor, v_cache: torch.Tens
     return out
 
 
+def dwconv3x3_residual(x: torch.Tensor, w9: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
+    """DaViT conv position encoding: x bf16 [B, H, W, C] (NHWC), w9 bf16 [9, C], bias bf16 [C] -> x + dwconv3x3(x) + bias (fo1_dwconv3x3_residual)."""
+    _require_cuda(x)
+    assert x.dtype == torch.bfloat16 and x.dim() == 4 and x.is_contiguous() and w9.is_contiguous() and bias.is_contiguous()
+    B, H, W, Cc = x.shape
+    assert tuple(w9.shape) == (9, Cc) and tuple(bias.shape) == (Cc,)
+    y = torch.empty_like(x)
+    L = lib()
+    L.fo1_dwconv3x3_residual.restype = C.c_int
+    L.fo1_dwconv3x3_residual.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
+    check(L.fo1_dwconv3x3_residual(C.c_void_p(x.data_ptr()), C.c_void_p(w9.data_ptr()), C.c_void_p(bias.data_ptr()), C.c_void_p(y.data_ptr()),
+                                   B, H, W, Cc, C.c_void_p(_stream())), "fo1_dwconv3x3_residual")
+    return y
+
+
 def channel_attention(qkv: torch.Tensor, groups: int) -> torch.Tensor:
     """DaViT channel-group attention: qkv bf16 [B, N, 3C] -> bf16 [B, N, C] (fo1_channel_attention)."""
     _require_cuda(qkv)

@@ -173,11 +173,14 @@ def hfre_algorithmic_bytes(HF, cfg, host, size):
     return tot
 
 
-def load_traffic():
+def load_traffic(workload: str, per_gpu_batch: int):
     """DRAM bytes per launch of the roofline kernels from the committed ncu capture of this round (profiles/): the bench
-    cannot run under ncu, so `traffic` is read from the capture of the same command."""
+    cannot run under ncu, so `traffic` is read from the capture of the same command -- one C3 step at 32 images per GPU
+    (profiles/r02_ncu_dram_step.csv).  Any other workload / batch launches other shapes: no figure (null) rather than a wrong one."""
     p = os.path.join(REPO, "profiles", "r02_traffic.json")
-    return json.load(open(p)) if os.path.exists(p) else {}
+    if workload != "c3" or per_gpu_batch != 32 or not os.path.exists(p):
+        return {}
+    return json.load(open(p))
 
 
 def main():
@@ -341,7 +344,7 @@ def main():
     if rank == 0:
         # ---- extra instrumented steps (rank 0 only, no collective: the other ranks are already at the final barrier) ----
         peaks = load_peaks()
-        traffic = load_traffic()
+        traffic = load_traffic(args.workload, B)
         if hfre_only:
             local_step = lambda: pipe.encode(resident)
         else:

@@ -1,7 +1,11 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_decode_mega.py tests/test_gpu_llm.py -x -q 2>&1 | tail -4
-for cfg in "32 1195" "16 773" "8 2647" "8 600" "1 600"; do
-set -- $cfg
-FO1_MEGA_PROF=1 timeout 600 python scripts/mega_prof.py $1 $2 > gpurun_out/mega_prof_$1_$2.log 2>&1; grep -E "ms/step|decode_mega profile, first" gpurun_out/mega_prof_$1_$2.log | tail -3
-done
+timeout 1200 python -m pytest tests/test_gpu_hfre.py tests/test_gpu_dwconv.py tests/test_gpu_pipeline.py tests/test_gpu_boundary.py tests/test_gpu_towers.py -x -q 2>&1 | tail -5
+timeout 600 python scripts/davit_prof.py 32 768 2>&1 | tail -1
+timeout 900 python bench.py --workload c2 --steps 5 --warmup 3 --no-cpu-baseline > gpurun_out/bench_c2.json 2> gpurun_out/bench_c2.err; tail -2 gpurun_out/bench_c2.err
+python - <<'PY'
+import json
+d=json.load(open('gpurun_out/bench_c2.json'))
+print(d['value'], d['unit'], d['ms_per_step'], d['stage_ms'], d['clocks'])
+print(d['roofline'])
+PY

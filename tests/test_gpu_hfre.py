@@ -87,3 +87,31 @@ def test_hfre_empty_and_errors():
     one = torch.tensor([[0.0, 0.0, 4.0, 4.0]], device="cuda")
     with pytest.raises(L.Fo1Error):
         H.hfre_forward([bad], [pyr], [one], [one], H.HfreConfig(region_dim=128), [(2, 2)])
+
+
+def test_hfre_packed_batch_is_the_same_operator():
+    """hfre_forward_packed (batch-contiguous maps, packed boxes, descriptors filled with array arithmetic) must give bit-identical
+    rows to the per-image list form, ragged box counts included."""
+    import fo1_b200  # noqa: F401
+    from importlib import import_module
+    H = import_module("vlm-fo1_b200.hfre")
+    g = torch.Generator().manual_seed(11)
+    B, S, D = 3, 224, 5888
+    aux_b = [torch.randn(B, S // (4 << i), S // (4 << i), c, generator=g).to(torch.bfloat16).cuda() for i, c in enumerate((256, 512, 1024, 2048))]
+    vt_b = [torch.randn(B, int(16 * f), int(16 * f), 512, generator=g).to(torch.bfloat16).cuda() for f in (4, 2, 1, 0.5)]
+    counts = [5, 1, 9]
+    boxes = []
+    for n in counts:
+        xy = torch.rand(n, 2, generator=g) * (S - 40)
+        wh = torch.rand(n, 2, generator=g) * 120 + 2
+        boxes.append(torch.cat([xy, torch.minimum(xy + wh, torch.tensor(float(S)))], 1).cuda())
+    cfg = H.HfreConfig(region_dim=D, vt_mode="fpn")
+    aux = [[aux_b[l][b] for l in range(4)] for b in range(B)]
+    vt = [[vt_b[l][b] for l in range(4)] for b in range(B)]
+    ref32, ref16 = H.hfre_forward(aux, vt, boxes, boxes, cfg, [(16, 16)] * B, want_bf16=True)
+    ba = torch.cat(boxes, 0).contiguous()
+    out32, out16 = H.hfre_forward_packed(aux_b, vt_b, ba, ba.clone(), counts, cfg, (16, 16), want_bf16=True)
+    torch.cuda.synchronize()
+    assert torch.equal(out32, torch.cat(ref32, 0)) and torch.equal(out16, torch.cat(ref16, 0))
+    with pytest.raises(Exception):
+        H.hfre_forward_packed(aux_b, vt_b, ba, ba, [5, 1, 8], cfg, (16, 16))

@@ -64,18 +64,18 @@ constexpr int kDwTx = 8;
 __global__ void __launch_bounds__(256, 2) dwconv3x3_res_strip_kernel(const bf16* __restrict__ x, const bf16* __restrict__ w9,
                                                                      const bf16* __restrict__ bias, bf16* __restrict__ y, int H, int W,
                                                                      int C, int R, int strips_x, int strips_y, int cblocks) {
+  __shared__ uint4 s_w[9][32];     // the block's 9 x 256 weights (the eight warps read the same 512 B per tap)
   int bid = blockIdx.x;
   const int cb = bid % cblocks; bid /= cblocks;
   const int sx = bid % strips_x; bid /= strips_x;
   const int sy = bid % strips_y;
   const int b = bid / strips_y;
-  const int c8 = cb * 32 + (threadIdx.x & 31);
+  const int lane = threadIdx.x & 31;
+  const int c8 = cb * 32 + lane;
   const int px = sx * kDwTx + (threadIdx.x >> 5);
   const int y0 = sy * R, y1 = min(H, y0 + R);
   const bool active = px < W;
-  uint4 wv[9];
-#pragma unroll
-  for (int t = 0; t < 9; ++t) wv[t] = *reinterpret_cast<const uint4*>(w9 + (long long)t * C + c8 * 8);
+  for (int i = threadIdx.x; i < 9 * 32; i += 256) s_w[i >> 5][i & 31] = *reinterpret_cast<const uint4*>(w9 + (long long)(i >> 5) * C + (cb * 32 + (i & 31)) * 8);
   const uint4 bv = *reinterpret_cast<const uint4*>(bias + c8 * 8);
   const bf16* xb = x + (long long)b * H * W * C + c8 * 8;
   bf16* yb = y + (long long)b * H * W * C + c8 * 8;
@@ -87,17 +87,19 @@ __global__ void __launch_bounds__(256, 2) dwconv3x3_res_strip_kernel(const bf16*
     r[1] = *reinterpret_cast<const uint4*>(row + (long long)px * C);
     r[2] = px + 1 < W ? *reinterpret_cast<const uint4*>(row + (long long)(px + 1) * C) : zero;
   };
-  uint4 win[3][3];
+  uint4 win[3][3], nxt[3];
   load_row(y0 - 1, win[0]);
   load_row(y0, win[1]);
+  load_row(y0 + 1, win[2]);
+  __syncthreads();
   for (int py = y0; py < y1; ++py) {
-    load_row(py + 1, win[2]);
+    load_row(py + 2, nxt);         // one row ahead of the window: its latency hides behind this row's arithmetic
     float acc[8] = {bf16_lo(bv.x), bf16_hi(bv.x), bf16_lo(bv.y), bf16_hi(bv.y), bf16_lo(bv.z), bf16_hi(bv.z), bf16_lo(bv.w), bf16_hi(bv.w)};
 #pragma unroll
     for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
       for (int dx = 0; dx < 3; ++dx) {
-        const uint4 v = win[dy][dx], w = wv[dy * 3 + dx];
+        const uint4 v = win[dy][dx], w = s_w[dy * 3 + dx][lane];
         acc[0] = fmaf(bf16_lo(v.x), bf16_lo(w.x), acc[0]); acc[1] = fmaf(bf16_hi(v.x), bf16_hi(w.x), acc[1]);
         acc[2] = fmaf(bf16_lo(v.y), bf16_lo(w.y), acc[2]); acc[3] = fmaf(bf16_hi(v.y), bf16_hi(w.y), acc[3]);
         acc[4] = fmaf(bf16_lo(v.z), bf16_lo(w.z), acc[4]); acc[5] = fmaf(bf16_hi(v.z), bf16_hi(w.z), acc[5]);
@@ -113,7 +115,7 @@ __global__ void __launch_bounds__(256, 2) dwconv3x3_res_strip_kernel(const bf16*
       *reinterpret_cast<uint4*>(yb + ((long long)py * W + px) * C) = o;
     }
 #pragma unroll
-    for (int k = 0; k < 3; ++k) { win[0][k] = win[1][k]; win[1][k] = win[2][k]; }
+    for (int k = 0; k < 3; ++k) { win[0][k] = win[1][k]; win[1][k] = win[2][k]; win[2][k] = nxt[k]; }
   }
 }
 

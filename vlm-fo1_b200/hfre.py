@@ -117,6 +117,75 @@ def hfre_forward(aux_feats: Sequence[Sequence[torch.Tensor]], vt_feats: Sequence
     return (outs, outs16) if want_bf16 else outs
 
 
+_IMG_DTYPE = np.dtype(HfreImage)
+
+
+def hfre_forward_packed(aux_levels: Sequence[torch.Tensor], vt_levels: Sequence[torch.Tensor], boxes_aux: torch.Tensor,
+                        boxes_vt: torch.Tensor, counts: Sequence[int], cfg: HfreConfig, vt_grid_hw: Sequence[int],
+                        want_bf16: bool = False, workspace: Optional[HfreWorkspace] = None):
+    """hfre_forward for a batch whose images share their shapes (the serving case): ``aux_levels[l]`` / ``vt_levels[l]`` are the
+    batch-contiguous maps bf16 [B, H_l, W_l, C_l] the towers emit, ``boxes_*`` fp32 [sum N_b, 4] packed in image order, ``counts[b]``
+    = N_b.  Same operator, same descriptors -- they are filled with array arithmetic instead of a Python loop over images x levels,
+    and the outputs are one packed fp32 [sum N_b, D] tensor (+ its bf16 copy), image b at rows sum(counts[:b]) .. ."""
+    B = len(counts)
+    dev = boxes_aux.device
+    for f in list(aux_levels) + list(vt_levels):
+        if f.dtype != torch.bfloat16 or not f.is_contiguous() or f.dim() != 4 or not f.is_cuda or f.shape[0] != B:
+            raise _lib.Fo1Error("HFRE packed levels must be contiguous channels-last bf16 CUDA tensors [B, H, W, C]")
+    if boxes_aux.dtype != torch.float32 or boxes_vt.dtype != torch.float32 or not boxes_aux.is_contiguous() or not boxes_vt.is_contiguous():
+        raise _lib.Fo1Error("HFRE packed boxes must be contiguous fp32 [sum N, 4]")
+    total = int(sum(counts))
+    if boxes_aux.shape != (total, 4) or boxes_vt.shape != (total, 4):
+        raise _lib.Fo1Error("HFRE packed boxes do not match counts")
+    H0 = max(f.shape[1] for f in aux_levels); W0 = max(f.shape[2] for f in aux_levels)
+    levels = []
+    off = 0
+    for f in aux_levels:
+        levels.append((f, H0, W0, AUX_SCALE, 0, off)); off += f.shape[3]
+    if cfg.vt_mode == "fpn":
+        for i, f in enumerate(vt_levels):
+            levels.append((f, f.shape[1], f.shape[2], 1.0 / FPN_STRIDES[i], 1, off)); off += f.shape[3]
+    elif cfg.vt_mode == "concat":
+        for f in vt_levels:
+            levels.append((f, f.shape[1], f.shape[2], VT_SCALE, 1, off)); off += f.shape[3]
+    else:
+        raise ValueError(f"unknown vt_mode {cfg.vt_mode!r}")
+    if off > cfg.region_dim:
+        raise ValueError(f"levels provide {off} channels > region_dim {cfg.region_dim}")
+    if len(levels) > _lib.FO1_HFRE_MAX_LEVELS:
+        raise ValueError("too many feature levels")
+    out = torch.empty((total, cfg.region_dim), dtype=torch.float32, device=dev)
+    out16 = torch.empty((total, cfg.region_dim), dtype=torch.bfloat16, device=dev) if want_bf16 else None
+    imgs = (HfreImage * B)()
+    a = np.frombuffer(imgs, dtype=_IMG_DTYPE)
+    idx = np.arange(B, dtype=np.uint64)
+    lv = a["levels"]
+    for i, (f, uh, uw, sc, bs, o) in enumerate(levels):
+        lv["data"][:, i] = np.uint64(f.data_ptr()) + idx * np.uint64(f.stride(0) * 2)
+        lv["H"][:, i], lv["W"][:, i], lv["C"][:, i] = f.shape[1], f.shape[2], f.shape[3]
+        lv["up_H"][:, i], lv["up_W"][:, i] = uh, uw
+        lv["spatial_scale"][:, i] = sc; lv["box_set"][:, i] = bs; lv["out_offset"][:, i] = o
+    cnt = np.asarray(counts, dtype=np.uint64)
+    row0 = np.concatenate([[0], np.cumsum(cnt)[:-1]]).astype(np.uint64)
+    a["n_levels"] = len(levels)
+    a["n_boxes"] = cnt.astype(np.int32)
+    a["boxes_aux"] = np.uint64(boxes_aux.data_ptr()) + row0 * np.uint64(16)
+    a["boxes_vt"] = np.uint64(boxes_vt.data_ptr()) + row0 * np.uint64(16)
+    a["out"] = np.uint64(out.data_ptr()) + row0 * np.uint64(cfg.region_dim * 4)
+    a["out_bf16"] = (np.uint64(out16.data_ptr()) + row0 * np.uint64(cfg.region_dim * 2)) if want_bf16 else np.uint64(0)
+    gh, gw = vt_grid_hw
+    a["pos_img_w"] = gw / VT_SCALE      # :447-448 (python float, rounded to fp32 at the division like the reference)
+    a["pos_img_h"] = gh / VT_SCALE
+    a["pos_box_set"] = 1
+    p = HfreParams(cfg.region_dim, cfg.roi_size, 1 if cfg.apply_pos_embed else 0, cfg.algo)
+    L = lib()
+    need = L.fo1_hfre_workspace_bytes(imgs, B, C.byref(p))
+    ws = (workspace or _default_ws).get(need, dev)
+    check(L.fo1_hfre_forward(imgs, B, C.byref(p), C.c_void_p(ws.data_ptr()), ws.numel(),
+                             C.c_void_p(torch.cuda.current_stream().cuda_stream)), "fo1_hfre_forward")
+    return (out, out16) if want_bf16 else out
+
+
 def algorithmic_bytes(level_shapes, level_boxes, level_scales, level_up, n_boxes: int, out_dim: int) -> dict:
     """SURVEY.md section 8d accounting for one image: unique native-resolution bf16 cells inside the
     union of the boxes' sample windows x C x 2 B + fp32 output + the two box arrays; and the no-reuse

@@ -93,9 +93,11 @@ class Fo1Pipeline:
         H0, W0 = samples[0].image_aux.shape[-2:]
         same_aux = all(s.image_aux.shape[-2:] == (H0, W0) for s in samples)
         same_grid = all(g == grids[0] for g in grids)
+        aux_b = vt_b = None                      # batch-contiguous level maps (the packed HFRE path)
         if same_aux:
             st = eng.davit_forward([s.image_aux for s in samples])
-            aux = [[st[l][b] for l in range(4)] for b in range(B)]
+            aux_b = st
+            aux = None
         else:
             aux = []
             for s in samples:
@@ -104,11 +106,11 @@ class Fo1Pipeline:
         self._mark("davit")
         tok_off = np.cumsum([0] + [gh * gw for gh, gw in grids])
         hid = eng.cfg.vit["hidden_size"]
+        vt = None
         if self.vt_mode == "fpn":
             if same_grid:
                 gh, gw = grids[0]
-                pyr = eng.fpn_forward(taps[-1].view(B, gh, gw, hid))            # SimpleFPN on the LAST tap (:82-83)
-                vt = [[pyr[l][b] for l in range(4)] for b in range(B)]
+                vt_b = eng.fpn_forward(taps[-1].view(B, gh, gw, hid))           # SimpleFPN on the LAST tap (:82-83)
             else:
                 vt = []
                 for b, (gh, gw) in enumerate(grids):
@@ -117,21 +119,44 @@ class Fo1Pipeline:
         else:
             vt = [[taps[t][tok_off[b]:tok_off[b + 1]].view(grids[b][0], grids[b][1], hid) for t in range(len(taps))] for b in range(B)]
         self._mark("fpn")
-        boxes_aux, boxes_vt = [], []
+        packed = aux_b is not None and vt_b is not None
+        if not packed or self._keep_stages is not None:
+            if aux is None:
+                aux = [[aux_b[l][b] for l in range(4)] for b in range(B)]
+            if vt is None:
+                vt = [[vt_b[l][b] for l in range(4)] for b in range(B)]
+        # boxes: the aux set in image pixels, the vt set rescaled to the ViT grid (:94-99); one packed array per set
+        p = eng.cfg.vit["patch_size"]
+        host_boxes = all(not s.boxes.is_cuda for s in samples)
+        bl, sl = [], []
         for b, s in enumerate(samples):
-            bx = s.boxes.to(dev, torch.float32)
+            bx = s.boxes
             if bx.numel() == 0:
-                bx = torch.tensor([[0.0, 10.0, 0.0, 10.0]], device=dev)             # the reference's dummy box (:90-91)
+                bx = torch.tensor([[0.0, 10.0, 0.0, 10.0]], device=bx.device)        # the reference's dummy box (:90-91)
             Ha, Wa = s.image_aux.shape[-2:]
             gh, gw = grids[b]
-            p = eng.cfg.vit["patch_size"]
-            scale = torch.tensor([gw * p / Wa, gh * p / Ha, gw * p / Wa, gh * p / Ha], device=dev, dtype=torch.float32)
-            boxes_aux.append(bx)
-            boxes_vt.append(bx * scale)                                              # :94-99
-        region_f32, region_bf16 = HF.hfre_forward(aux, vt, boxes_aux, boxes_vt, self.hcfg, grids, want_bf16=True, workspace=self.ws)
+            bl.append(bx)
+            sl.append(np.tile(np.asarray([gw * p / Wa, gh * p / Ha, gw * p / Wa, gh * p / Ha], dtype=np.float32), (bx.shape[0], 1)))
+        counts = [int(x.shape[0]) for x in bl]
+        scale_rows = torch.from_numpy(np.concatenate(sl, 0))
+        if host_boxes:     # fp32 multiply on the host: the same IEEE product the reference forms on the device; two copies instead of 4 B
+            ba_h = torch.cat([x.to(torch.float32) for x in bl], 0)
+            both = torch.stack([ba_h, ba_h * scale_rows], 0).pin_memory()
+            both_d = both.to(dev, non_blocking=True)
+            boxes_aux_p, boxes_vt_p = both_d[0], both_d[1]
+        else:
+            boxes_aux_p = torch.cat([x.to(dev, torch.float32) for x in bl], 0)
+            boxes_vt_p = boxes_aux_p * scale_rows.to(dev, non_blocking=True)
+        if packed:
+            region_f32_p, region_bf16_p = HF.hfre_forward_packed(aux_b, vt_b, boxes_aux_p, boxes_vt_p, counts, self.hcfg, grids[0],
+                                                                 want_bf16=True, workspace=self.ws)
+        else:
+            ba = list(torch.split(boxes_aux_p, counts, 0)); bv = list(torch.split(boxes_vt_p, counts, 0))
+            rf, rb = HF.hfre_forward(aux, vt, ba, bv, self.hcfg, grids, want_bf16=True, workspace=self.ws)
+            region_f32_p, region_bf16_p = torch.cat(rf, 0), torch.cat(rb, 0)
         self._mark("hfre")
-        counts = [r.shape[0] for r in region_bf16]
-        tokens = eng.region_project(torch.cat(region_bf16, 0))
+        region_f32 = list(torch.split(region_f32_p, counts, 0))
+        tokens = eng.region_project(region_bf16_p)
         self._mark("projector")
         region_tokens = list(torch.split(tokens, counts, 0))
         unit = eng.cfg.vit["spatial_merge_size"] ** 2

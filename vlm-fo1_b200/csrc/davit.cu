@@ -233,15 +233,26 @@ static int fpn_forward_impl(Model* m, const bf16* tap, int gh, int gw, int B, vo
     bf16* t2 = A.alloc<bf16>(pl * O);
     FO1_RUN(linear(feat, Cin, f.lv[l].conv1_w, Cin, t1, O, FO1_BF16, (int)pl, O, Cin, nullptr, 0, FO1_EPI_NONE, nullptr, 0, 0, s));
     FO1_RUN(layernorm(t1, O, f.lv[l].ln1_w, f.lv[l].ln1_b, t2, O, (int)pl, O, eps, s));
-    const size_t per_img_col = (size_t)Hl * Wl * 9 * O * sizeof(bf16);
-    int chunk = (int)std::max<size_t>(1, col_budget / std::max<size_t>(per_img_col, 1));
-    chunk = std::min(chunk, B);
-    bf16* colb = A.alloc<bf16>((size_t)chunk * Hl * Wl * 9 * O);
-    for (int b0 = 0; b0 < B; b0 += chunk) {
-      const int nb = std::min(chunk, B - b0);
-      const size_t o = (size_t)b0 * Hl * Wl;
-      FO1_RUN(im2col3x3(t2 + o * O, colb, nb, Hl, Wl, O, 1, s));
-      FO1_RUN(linear(colb, 9 * O, f.lv[l].conv2_w, 9 * O, t1 + o * O, O, FO1_BF16, nb * Hl * Wl, O, 9 * O, nullptr, 0, FO1_EPI_NONE, nullptr, 0, 0, s));
+    // 3x3 conv: implicit GEMM (the A tiles are TMA patches of t2, zero padding by the out-of-range fill); shapes that do not
+    // tile into 128-pixel patches -- or FO1_FPN_IM2COL, the A/B knob of the parity test -- take im2col + linear
+    const bool force_im2col = getenv("FO1_FPN_IM2COL") != nullptr;
+    int crc = -1000;
+    if (!force_im2col) {
+      if (dry) crc = ((O % 64 == 0) && ((size_t)Hl * Wl) % 128 == 0 && ((Wl % 128 == 0) || (128 % Wl == 0 && Hl % (128 / Wl) == 0))) ? FO1_OK : -1000;
+      else crc = conv3x3_gemm(t2, B, Hl, Wl, O, f.lv[l].conv2_w, t1, O, O, s);
+      if (crc != FO1_OK && crc != -1000) return crc;
+    }
+    if (crc == -1000) {
+      const size_t per_img_col = (size_t)Hl * Wl * 9 * O * sizeof(bf16);
+      int chunk = (int)std::max<size_t>(1, col_budget / std::max<size_t>(per_img_col, 1));
+      chunk = std::min(chunk, B);
+      bf16* colb = A.alloc<bf16>((size_t)chunk * Hl * Wl * 9 * O);
+      for (int b0 = 0; b0 < B; b0 += chunk) {
+        const int nb = std::min(chunk, B - b0);
+        const size_t o = (size_t)b0 * Hl * Wl;
+        FO1_RUN(im2col3x3(t2 + o * O, colb, nb, Hl, Wl, O, 1, s));
+        FO1_RUN(linear(colb, 9 * O, f.lv[l].conv2_w, 9 * O, t1 + o * O, O, FO1_BF16, nb * Hl * Wl, O, 9 * O, nullptr, 0, FO1_EPI_NONE, nullptr, 0, 0, s));
+      }
     }
     FO1_RUN(layernorm(t1, O, f.lv[l].ln2_w, f.lv[l].ln2_b, static_cast<bf16*>(dry ? nullptr : level_out[l]), O, (int)pl, O, eps, s));
     A.release(mark);

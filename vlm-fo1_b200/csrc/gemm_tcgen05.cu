@@ -47,6 +47,9 @@ struct GemmArgs {
   int stage_tx;   // bytes one ring stage receives (A box rows x 128 B + BN x 128 B): skinny problems load only the live A rows
   float* ws;
   int* counters;
+  // implicit 3x3 / pad 1 / stride 1 convolution over an NHWC map (conv_cpb = C / 64 k-blocks per tap; 0: ordinary GEMM): the A tile of
+  // k-block kb is the [Ht][Wt][64] patch of tap kb / conv_cpb, fetched by a 4-D TMA whose out-of-range coordinates read as zero
+  int conv_cpb, conv_H, conv_W, conv_Wt;
 };
 
 constexpr int kMaxStages = 24;
@@ -358,6 +361,19 @@ __device__ __noinline__ void splitk_finish(const GemmArgs& g, int tile, int m0, 
   }
 }
 
+// one A tile into a ring stage: rows m0 .. m0+127 of the [M][K] matrix, or (implicit conv) the shifted pixel patch of the k-block's tap
+__device__ __forceinline__ void load_a_tile(const GemmArgs& g, const CUtensorMap* tmA, uint32_t dst, uint32_t bar, int kb, int m0) {
+  if (g.conv_cpb == 0) {
+    ptx::tma_load_2d(dst, tmA, bar, kb * BK, m0);
+  } else {
+    const int tap = kb / g.conv_cpb, c0 = (kb - tap * g.conv_cpb) * BK;
+    const int hw = g.conv_H * g.conv_W;
+    const int b = m0 / hw, rem = m0 - b * hw;
+    const int y0 = rem / g.conv_W, x0 = rem - y0 * g.conv_W;
+    ptx::tma_load_4d(dst, tmA, bar, c0, x0 + tap % 3 - 1, y0 + tap / 3 - 1, b);
+  }
+}
+
 template <int BN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const __grid_constant__ GemmArgs g) {
@@ -426,7 +442,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           }
           griddep_wait();
           for (int i = 0; i < pre; ++i)
-            ptx::tma_load_2d(ptx::smem_u32(smem_a + i * g.a_stage_bytes), &tmA, ptx::smem_u32(full_bar + i), (kb0 + i) * BK, m0);
+            load_a_tile(g, &tmA, ptx::smem_u32(smem_a + i * g.a_stage_bytes), ptx::smem_u32(full_bar + i), kb0 + i, m0);
           it = pre; kb = kb0 + pre;
         }
         for (; kb < kb1; ++kb, ++it) {
@@ -434,7 +450,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           ptx::mbar_wait(ptx::smem_u32(empty_bar + s), ph ^ 1);
           const uint32_t fb = ptx::smem_u32(full_bar + s);
           ptx::mbar_expect_tx(fb, (uint32_t)g.stage_tx);
-          ptx::tma_load_2d(ptx::smem_u32(smem_a + s * g.a_stage_bytes), &tmA, fb, kb * BK, m0);
+          load_a_tile(g, &tmA, ptx::smem_u32(smem_a + s * g.a_stage_bytes), fb, kb, m0);
           ptx::tma_load_2d(ptx::smem_u32(smem_b + s * g.b_stage_bytes), &tmW, fb, kb * BK, n0);
         }
       }
@@ -658,6 +674,28 @@ int make_tmap_3d_bf16(CUtensorMap* out, const void* ptr, uint64_t d0, uint64_t d
   return FO1_OK;
 }
 
+// 4-D bf16 tensor map over an NHWC map (channel, x, y, image), 128B swizzle; out-of-range coordinates (the conv padding) read as zero.
+int make_tmap_4d_bf16(CUtensorMap* out, const void* ptr, uint64_t C, uint64_t W, uint64_t H, uint64_t B, uint32_t bc, uint32_t bw, uint32_t bh) {
+  PFN_tmapEncodeTiled fn = get_encode_fn();
+  if (fn == nullptr) {
+    set_error("cuTensorMapEncodeTiled is not available from the driver");
+    return FO1_ERR_CUDA;
+  }
+  cuuint64_t dims[4] = {C, W, H, B};
+  cuuint64_t strides[3] = {C * 2, W * C * 2, H * W * C * 2};
+  cuuint32_t box[4] = {bc, bw, bh, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(4d) failed (%d): ptr=%p dims=%llu,%llu,%llu,%llu box=%u,%u,%u", (int)r, ptr, (unsigned long long)C,
+              (unsigned long long)W, (unsigned long long)H, (unsigned long long)B, bc, bw, bh);
+    return FO1_ERR_CUDA;
+  }
+  return FO1_OK;
+}
+
 int device_sm_count() {
   static int sms = 0;
   if (sms == 0) {
@@ -693,8 +731,10 @@ static int splitk_scratch(cudaStream_t stream, size_t need_bytes, int need_count
   return FO1_OK;
 }
 
+struct ConvInfo { int B, H, W, C, Wt; };   // implicit 3x3 conv: d->A is the NHWC map, d->M = B*H*W, d->K = 9*C
+
 template <int BN>
-static int launch_gemm(const fo1_gemm_desc* d, cudaStream_t stream, int ksplit = 1) {
+static int launch_gemm(const fo1_gemm_desc* d, cudaStream_t stream, int ksplit = 1, const ConvInfo* conv = nullptr) {
   using Cfg = GemmCfg<BN>;
   static bool attr_set = false;
   if (!attr_set) {
@@ -705,7 +745,11 @@ static int launch_gemm(const fo1_gemm_desc* d, cudaStream_t stream, int ksplit =
   // one m-tile only (decode: M = batch): fetch just the live rows of A, rounded to the 8-row swizzle atom; the UMMA
   // still multiplies all 128 smem rows, rows >= M hold stale data whose results are never stored
   const int a_rows = d->M < BM ? ((d->M + 7) & ~7) : BM;
-  FO1_TRY(make_tmap_2d_bf16(&tmA, d->A, (uint64_t)d->K, (uint64_t)d->M, (uint64_t)d->lda, BK, a_rows));
+  if (conv != nullptr) {
+    FO1_TRY(make_tmap_4d_bf16(&tmA, d->A, (uint64_t)conv->C, (uint64_t)conv->W, (uint64_t)conv->H, (uint64_t)conv->B, BK, (uint32_t)conv->Wt, (uint32_t)(BM / conv->Wt)));
+  } else {
+    FO1_TRY(make_tmap_2d_bf16(&tmA, d->A, (uint64_t)d->K, (uint64_t)d->M, (uint64_t)d->lda, BK, a_rows));
+  }
   FO1_TRY(make_tmap_2d_bf16(&tmW, d->W, (uint64_t)d->K, (uint64_t)d->N, (uint64_t)d->ldw, BK, BN));
   GemmArgs g;
   g.M = d->M; g.N = d->N; g.K = d->K;
@@ -714,6 +758,7 @@ static int launch_gemm(const fo1_gemm_desc* d, cudaStream_t stream, int ksplit =
   g.act = d->act;
   g.residual = static_cast<const __nv_bfloat16*>(d->residual); g.ldr = d->ldr;
   g.gated = d->gated;
+  g.conv_cpb = conv ? conv->C / BK : 0; g.conv_H = conv ? conv->H : 0; g.conv_W = conv ? conv->W : 0; g.conv_Wt = conv ? conv->Wt : 0;
   g.tiles_m = ceil_div(d->M, BM);
   g.tiles_n = ceil_div(d->N, BN);
   g.stage_tx = (a_rows + BN) * BK * 2;
@@ -747,7 +792,7 @@ static int launch_gemm(const fo1_gemm_desc* d, cudaStream_t stream, int ksplit =
   const int tiles = g.tiles_m * g.tiles_n * g.ksplit;
   const int grid = tiles < device_sm_count() ? tiles : device_sm_count();
   char tag[96] = "gemm";
-  if (g_prof_on) snprintf(tag, sizeof(tag), "%s:%dx%dx%d%s", d->M <= 128 ? "gemm_skinny" : "gemm", d->M, d->N, d->K, d->gated ? ":gated" : "");
+  if (g_prof_on) snprintf(tag, sizeof(tag), "%s:%dx%dx%d%s%s", d->M <= 128 ? "gemm_skinny" : "gemm", d->M, d->N, d->K, d->gated ? ":gated" : "", conv ? ":conv3x3" : "");
   ProfScope prof(tag, 2.0 * d->M * (double)d->N * d->K,
                  2.0 * ((double)d->M * d->K + (double)d->N * d->K + (double)d->M * (d->gated ? d->N / 2 : d->N)), stream);
   launch_k(gemm_bf16_tcgen05_kernel<BN>, dim3(grid), dim3(kGemmThreads), Cfg::kSmemBytes, stream, tmA, tmW, g);
@@ -802,6 +847,26 @@ int gemm_bf16(const fo1_gemm_desc* d, cudaStream_t stream) {
   int ks = 1;
   if (t * 2 <= sms) ks = (int)std::min<long long>(std::min<long long>(8, sms / t), std::max(1, ceil_div(d->K, BK) / 8));
   return bn == 64 ? launch_gemm<64>(d, stream, ks) : launch_gemm<32>(d, stream, ks);
+}
+
+// out[(b, y, x)][n] = sum_{ky, kx, c} x[b][y + ky - 1][x + kx - 1][c] * W[n][(ky * 3 + kx) * C + c]   (3x3, pad 1, stride 1, NHWC, no bias)
+// as an implicit GEMM: no column matrix, the A tiles are shifted patches of the map (zero padding = the TMA's out-of-range fill).
+// Returns FO1_ERR_UNSUPPORTED-like -1000 when the shape does not tile (caller falls back to im2col + linear).
+int conv3x3_gemm(const bf16* x, int B, int H, int W, int C, const bf16* Wm, bf16* out, long long ldo, int N, cudaStream_t stream) {
+  const bool fits = C % BK == 0 && (H * W) % BM == 0 && ((W % BM == 0) || (BM % W == 0 && H % (BM / W) == 0)) && N % 8 == 0;
+  if (!fits) return -1000;
+  if ((long long)B * H * W == 0) return FO1_OK;
+  FO1_CHECK_ARG((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(Wm) & 15) == 0, "conv3x3_gemm: operands must be 16-byte aligned");
+  fo1_gemm_desc d;
+  memset(&d, 0, sizeof(d));
+  d.M = B * H * W; d.N = N; d.K = 9 * C;
+  d.A = x; d.lda = C; d.W = Wm; d.ldw = 9 * C; d.D = out; d.ldd = ldo; d.d_dtype = FO1_BF16;
+  ConvInfo ci{B, H, W, C, W % BM == 0 ? BM : W};
+  const int sms = device_sm_count();
+  const long long tm = ceil_div(d.M, BM);
+  if (N >= 256 && tm * ceil_div(N, 256) >= sms) return launch_gemm<256>(&d, stream, 1, &ci);
+  if (N >= 128 && tm * ceil_div(N, 128) >= sms) return launch_gemm<128>(&d, stream, 1, &ci);
+  return launch_gemm<64>(&d, stream, 1, &ci);
 }
 
 }  // namespace fo1

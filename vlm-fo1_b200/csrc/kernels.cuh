@@ -14,6 +14,7 @@ typedef __nv_bfloat16 bf16;
 int gemm_bf16(const fo1_gemm_desc* d, cudaStream_t stream);
 int device_sm_count();
 // convenience: D = act(A.W^T + bias) + residual, all row-major contiguous unless ld given
+int conv3x3_gemm(const bf16* x, int B, int H, int W, int C, const bf16* Wm, bf16* out, long long ldo, int N, cudaStream_t stream);   // -1000: shape does not tile
 int linear(const bf16* A, long long lda, const bf16* W, long long ldw, void* D, long long ldd, int d_dtype, int M, int N,
            int K, const void* bias, int bias_dtype, int act, const bf16* residual, long long ldr, int gated,
            cudaStream_t stream);

@@ -378,7 +378,7 @@ def main():
         roof_gemm = None
         if g and g["ms"] > 0:
             ach = g["flops"] / g["ms"] / 1e9
-            roof_gemm = {"kernel": "gemm_bf16_tcgen05_kernel (M > 128 launches of one step)", "bound": "tensor", "achieved": ach,
+            roof_gemm = {"kernel": "gemm_bf16_tcgen05_pair_kernel (CTA pairs, tcgen05.mma.cta_group::2; the few sub-wave problems: gemm_bf16_tcgen05_kernel), M > 128 launches of one step", "bound": "tensor", "achieved": ach,
                          "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": ach / peaks["tflops"], "traffic": traffic.get("gemm_bytes_per_launch"),
                          "peak_source": f"MEASURED_PEAKS.json bf16_tflops_sustained ({peaks['source']})",
                          "launches": g["launches"], "ms_per_launch": g["ms"] / g["launches"], "share_of_step": g["ms"] / step_ms,

@@ -361,6 +361,79 @@ __device__ __noinline__ void splitk_finish(const GemmArgs& g, int tile, int m0, 
   }
 }
 
+// one epilogue warp's share of a finished 128 x BN accumulator (TMEM lanes of its quarter, its half of the columns): bias, activation /
+// gate, residual, bf16 or fp32 stores (rows staged through shared memory into full 128-byte lines when `coalesce`)
+template <int BN>
+__device__ __forceinline__ void epilogue_tile(const GemmArgs& g, uint8_t* staging, int warp, int lane, uint32_t taddr, int m0, int n0) {
+  const int quarter = warp & 3;
+  const int half = (warp - 2) >> 2;
+  constexpr bool kSplit32 = BN >= 64, kSplit64 = BN >= 128;
+  const int p_beg = kSplit32 ? half * (BN / 2) : 0, p_end = kSplit32 ? (half + 1) * (BN / 2) : (half == 0 ? BN : 0);
+  const int g_cut = (BN == 192) ? 128 : BN / 2;
+  const int g_beg = kSplit64 ? half * g_cut : 0, g_end = kSplit64 ? (half == 0 ? g_cut : BN) : (half == 0 ? BN : 0);
+  const int m = m0 + quarter * 32 + lane;
+  if (!g.gated) {
+    // software pipeline: the TMEM load of chunk c+1 is in flight while chunk c is converted and stored
+    constexpr int NCH = (kSplit32 ? BN / 2 : BN) / 32;
+    uint8_t* stg = staging + (warp - 2) * 4096;
+    uint32_t r[2][32];
+    const int cbeg = p_beg;
+    const bool worker = p_end > p_beg;
+    if (worker && n0 + cbeg < g.N) ptx::tmem_ld_32x32(taddr + cbeg, r[0]);
+#pragma unroll
+    for (int ci = 0; ci < NCH; ++ci) {
+      const int c = cbeg + ci * 32;
+      if (!worker || n0 + c >= g.N) break;  // warp-uniform
+      ptx::tmem_ld_wait();
+      float v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[ci & 1][j]);
+      if (ci + 1 < NCH && n0 + c + 32 < g.N) ptx::tmem_ld_32x32(taddr + c + 32, r[(ci + 1) & 1]);
+      if (g.bias != nullptr) add_bias32(v, g.bias, g.bias_dtype, n0 + c, g.N);
+      apply_act32(v, g.act);
+      if (!g.coalesce) {
+        if (m < g.M) store_row32(g, v, m, n0 + c, g.N);
+      } else if (g.d_dtype == FO1_BF16) {
+        // two 32-column chunks (2 x 64 B) fill a 128-byte row before it is flushed
+        stage_row32(stg, lane, (ci & 1) * 4, v, true);
+        const bool last = (ci + 1 == NCH) || (n0 + c + 32 >= g.N);
+        if ((ci & 1) || last) flush_rows(g, stg, lane, (ci & 1) ? 8 : 4, m0 + quarter * 32, n0 + c - (ci & 1) * 32, g.N);
+      } else {
+        stage_row32(stg, lane, 0, v, false);
+        flush_rows(g, stg, lane, 8, m0 + quarter * 32, n0 + c, g.N);
+      }
+    }
+  } else {
+    // W rows interleave [32 gate | 32 up] blocks: out[:, (n0+c)/2 + j] = act(gate_j) * up_j
+#pragma unroll 1
+    for (int c = g_beg; c < g_end; c += 64) {
+      if (n0 + c >= g.N) break;
+      uint32_t rg[32], ru[32];
+      ptx::tmem_ld_32x32(taddr + c, rg);
+      ptx::tmem_ld_32x32(taddr + c + 32, ru);
+      ptx::tmem_ld_wait();
+      float gt[32], v[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j) { gt[j] = __uint_as_float(rg[j]); v[j] = __uint_as_float(ru[j]); }
+      if (g.bias != nullptr) {
+        add_bias32(gt, g.bias, g.bias_dtype, n0 + c, g.N);
+        add_bias32(v, g.bias, g.bias_dtype, n0 + c + 32, g.N);
+      }
+      apply_act32(gt, g.act);
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = gt[j] * v[j];
+      if (!g.coalesce) {
+        if (m < g.M) store_row32(g, v, m, (n0 + c) >> 1, g.N >> 1);
+      } else {
+        uint8_t* stg = staging + (warp - 2) * 4096;
+        const bool bf = g.d_dtype == FO1_BF16;
+        stage_row32(stg, lane, 0, v, bf);
+        flush_rows(g, stg, lane, bf ? 4 : 8, m0 + quarter * 32, (n0 + c) >> 1, g.N >> 1);
+      }
+    }
+  }
+}
+
 // one A tile into a ring stage: rows m0 .. m0+127 of the [M][K] matrix, or (implicit conv) the shifted pixel patch of the k-block's tap
 __device__ __forceinline__ void load_a_tile(const GemmArgs& g, const CUtensorMap* tmA, uint32_t dst, uint32_t bar, int kb, int m0) {
   if (g.conv_cpb == 0) {
@@ -537,66 +610,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
         asm volatile("bar.sync 1, 256;" ::: "memory");   // last_flag is reused by the next work item
         continue;
       }
-      if (!g.gated) {
-        // software pipeline: the TMEM load of chunk c+1 is in flight while chunk c is converted and stored
-        constexpr int NCH = (kSplit32 ? BN / 2 : BN) / 32;
-        uint8_t* stg = staging + (warp - 2) * 4096;
-        uint32_t r[2][32];
-        const int cbeg = p_beg;
-        const bool worker = p_end > p_beg;
-        if (worker && n0 + cbeg < g.N) ptx::tmem_ld_32x32(taddr + cbeg, r[0]);
-#pragma unroll
-        for (int ci = 0; ci < NCH; ++ci) {
-          const int c = cbeg + ci * 32;
-          if (!worker || n0 + c >= g.N) break;  // warp-uniform
-          ptx::tmem_ld_wait();
-          float v[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[ci & 1][j]);
-          if (ci + 1 < NCH && n0 + c + 32 < g.N) ptx::tmem_ld_32x32(taddr + c + 32, r[(ci + 1) & 1]);
-          if (g.bias != nullptr) add_bias32(v, g.bias, g.bias_dtype, n0 + c, g.N);
-          apply_act32(v, g.act);
-          if (!g.coalesce) {
-            if (m < g.M) store_row32(g, v, m, n0 + c, g.N);
-          } else if (g.d_dtype == FO1_BF16) {
-            // two 32-column chunks (2 x 64 B) fill a 128-byte row before it is flushed
-            stage_row32(stg, lane, (ci & 1) * 4, v, true);
-            const bool last = (ci + 1 == NCH) || (n0 + c + 32 >= g.N);
-            if ((ci & 1) || last) flush_rows(g, stg, lane, (ci & 1) ? 8 : 4, m0 + quarter * 32, n0 + c - (ci & 1) * 32, g.N);
-          } else {
-            stage_row32(stg, lane, 0, v, false);
-            flush_rows(g, stg, lane, 8, m0 + quarter * 32, n0 + c, g.N);
-          }
-        }
-      } else {
-        // W rows interleave [32 gate | 32 up] blocks: out[:, (n0+c)/2 + j] = act(gate_j) * up_j
-#pragma unroll 1
-        for (int c = g_beg; c < g_end; c += 64) {
-          if (n0 + c >= g.N) break;
-          uint32_t rg[32], ru[32];
-          ptx::tmem_ld_32x32(taddr + c, rg);
-          ptx::tmem_ld_32x32(taddr + c + 32, ru);
-          ptx::tmem_ld_wait();
-          float gt[32], v[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) { gt[j] = __uint_as_float(rg[j]); v[j] = __uint_as_float(ru[j]); }
-          if (g.bias != nullptr) {
-            add_bias32(gt, g.bias, g.bias_dtype, n0 + c, g.N);
-            add_bias32(v, g.bias, g.bias_dtype, n0 + c + 32, g.N);
-          }
-          apply_act32(gt, g.act);
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = gt[j] * v[j];
-          if (!g.coalesce) {
-            if (m < g.M) store_row32(g, v, m, (n0 + c) >> 1, g.N >> 1);
-          } else {
-            uint8_t* stg = staging + (warp - 2) * 4096;
-            const bool bf = g.d_dtype == FO1_BF16;
-            stage_row32(stg, lane, 0, v, bf);
-            flush_rows(g, stg, lane, bf ? 4 : 8, m0 + quarter * 32, (n0 + c) >> 1, g.N >> 1);
-          }
-        }
-      }
+      epilogue_tile<BN>(g, staging, warp, lane, taddr, m0, n0);
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(ptx::smem_u32(tmem_empty + acc));
@@ -606,6 +620,146 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 1) ptx::tmem_dealloc(tmem_base, Cfg::kTmemCols);
+}
+
+// ------------------------------------------------------------------------------------- CTA-pair variant (cta_group::2)
+// Large problems: a cluster of two CTAs (one TPC) owns a 256 x 256 output tile.  Each CTA stages its own 128 rows of A and HALF of
+// the weight tile (128 of its 256 rows) per k-block, the leader issues tcgen05.mma.cta_group::2 (M = 256) which reads both halves,
+// and each CTA's TMEM receives its 128 accumulator rows.  A stage is 32 KB per SM instead of 48 KB for the same 524 MMA cycles:
+// six stages fit where four did, so the ring covers the TMA latency the single-CTA 128 x 256 tile (92 B/clk per SM) cannot
+// (tensor pipe 70 % -> see profiles/README.md), and L2 -> SM operand traffic drops by a third.
+//   barriers (same offsets in both CTAs): full[s] lives in the LEADER (one expect_tx of 64 KB, the four TMA loads of the pair credit
+//   it); empty[s] and tmem_full[a] are signalled in BOTH CTAs by the leader's multicast commit; tmem_empty[a] lives in the leader
+//   and counts the 16 epilogue warps of the pair (the peer's arrive remotely).
+constexpr int kPairBN = 256, kPairStages = 6;
+constexpr int kPairStageBytes = (BM * BK + (kPairBN / 2) * BK) * 2;                     // 32 KB per CTA
+constexpr int kPairSmemBytes = kPairStages * kPairStageBytes + 1024 + 512 + 8 * 4096;  // + align, barriers, epilogue staging
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kGemmThreads, 1)
+gemm_bf16_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const __grid_constant__ GemmArgs g) {
+  constexpr int BN = kPairBN, S = kPairStages;
+  constexpr int kAStage = BM * BK * 2, kBStage = (BN / 2) * BK * 2;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + S * kAStage;
+  uint8_t* tail = smem + S * (kAStage + kBStage);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tail);
+  uint64_t* full_bar = bars;                          // [S]   (used in the leader)
+  uint64_t* empty_bar = bars + kMaxStages;            // [S]
+  uint64_t* tmem_full = bars + 2 * kMaxStages;        // [2]
+  uint64_t* tmem_empty = bars + 2 * kMaxStages + 2;   // [2]   (used in the leader)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 2 * kMaxStages + 4);
+  uint8_t* staging = tail + 512;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = ptx::cluster_ctarank();
+  const int cluster = blockIdx.x >> 1, n_clusters = gridDim.x >> 1;
+  const int pairs_m = (g.tiles_m + 1) >> 1;
+  const int num_work = pairs_m * g.tiles_n;
+  const int num_kb = (g.K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmA);
+    ptx::prefetch_tmap(&tmW);
+    for (int s = 0; s < S; ++s) {
+      ptx::mbar_init(ptx::smem_u32(full_bar + s), 1);
+      ptx::mbar_init(ptx::smem_u32(empty_bar + s), 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(ptx::smem_u32(tmem_full + a), 1);
+      ptx::mbar_init(ptx::smem_u32(tmem_empty + a), 2 * (kEpiThreads / 32));   // the epilogue warps of BOTH CTAs
+    }
+    ptx::mbar_fence_init_cluster();
+  }
+  if (warp == 1) ptx::tmem_alloc_pair(ptx::smem_u32(tmem_ptr), 2 * BN);
+  ptx::tc_fence_before();
+  ptx::cluster_sync_all();       // both CTAs' barriers exist before anybody signals across the pair
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  griddep_launch();
+
+  if (warp == 0) {
+    // ===================================== TMA producer (both CTAs) =====================================
+    if (ptx::elect_one()) {
+      griddep_wait();
+      uint32_t it = 0;
+      for (int work = cluster; work < num_work; work += n_clusters) {
+        const int m0 = (work / g.tiles_n) * (2 * BM) + (int)rank * BM;
+        const int n0 = (work % g.tiles_n) * BN + (int)rank * (BN / 2);
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const uint32_t s = it % S, ph = (it / S) & 1;
+          ptx::mbar_wait(ptx::smem_u32(empty_bar + s), ph ^ 1);
+          const uint32_t fb_local = ptx::smem_u32(full_bar + s);
+          if (rank == 0) ptx::mbar_expect_tx(fb_local, 2u * (uint32_t)(kAStage + kBStage));
+          const uint32_t fb = ptx::mapa_rank(fb_local, 0);
+          const uint32_t dst_a = ptx::smem_u32(smem_a + s * kAStage);
+          if (g.conv_cpb == 0) {
+            ptx::tma_load_2d_pair(dst_a, &tmA, fb, kb * BK, m0);
+          } else {
+            const int tap = kb / g.conv_cpb, c0 = (kb - tap * g.conv_cpb) * BK;
+            const int hw = g.conv_H * g.conv_W;
+            const int b = m0 / hw, rem = m0 - b * hw;
+            const int y0 = rem / g.conv_W, x0 = rem - y0 * g.conv_W;
+            ptx::tma_load_4d_pair(dst_a, &tmA, fb, c0, x0 + tap % 3 - 1, y0 + tap / 3 - 1, b);
+          }
+          ptx::tma_load_2d_pair(ptx::smem_u32(smem_b + s * kBStage), &tmW, fb, kb * BK, n0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ====================================== MMA issuer (leader only) ======================================
+    if (rank == 0) {
+      constexpr uint32_t idesc = ptx::umma_idesc_bf16(2 * BM, BN);
+      uint32_t it = 0, tcount = 0;
+      for (int work = cluster; work < num_work; work += n_clusters, ++tcount) {
+        const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
+        ptx::mbar_wait(ptx::smem_u32(tmem_empty + acc), aph ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        for (int kb = 0; kb < num_kb; ++kb, ++it) {
+          const uint32_t s = it % S, ph = (it / S) & 1;
+          ptx::mbar_wait(ptx::smem_u32(full_bar + s), ph);
+          ptx::tc_fence_after();
+          if (ptx::elect_one()) {
+            const uint32_t a_addr = ptx::smem_u32(smem_a + s * kAStage);
+            const uint32_t b_addr = ptx::smem_u32(smem_b + s * kBStage);
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              const uint64_t da = ptx::umma_desc_k_sw128(a_addr + k * UMMA_K * 2);
+              const uint64_t db = ptx::umma_desc_k_sw128(b_addr + k * UMMA_K * 2);
+              ptx::tc_mma_bf16_pair(tmem_d, da, db, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            }
+            ptx::tc_commit_pair(ptx::smem_u32(empty_bar + s), 3);                      // both CTAs may refill the slot
+            if (kb == num_kb - 1) ptx::tc_commit_pair(ptx::smem_u32(tmem_full + acc), 3);  // both CTAs' accumulator halves are complete
+          }
+          __syncwarp();
+        }
+      }
+    }
+  } else {
+    // ======================================= epilogue (both CTAs) ========================================
+    const int quarter = warp & 3;
+    uint32_t tcount = 0;
+    griddep_wait();
+    for (int work = cluster; work < num_work; work += n_clusters, ++tcount) {
+      const int m0 = (work / g.tiles_n) * (2 * BM) + (int)rank * BM;
+      const int n0 = (work % g.tiles_n) * BN;
+      const uint32_t acc = tcount & 1, aph = (tcount >> 1) & 1;
+      ptx::mbar_wait(ptx::smem_u32(tmem_full + acc), aph);
+      ptx::tc_fence_after();
+      const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(quarter * 32) << 16);
+      if (m0 < g.M) epilogue_tile<BN>(g, staging, warp, lane, taddr, m0, n0);
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa_rank(ptx::smem_u32(tmem_empty + acc), 0));
+    }
+  }
+
+  ptx::tc_fence_before();
+  ptx::cluster_sync_all();       // the peer's MMAs read this CTA's shared memory and TMEM until the very end
+  if (warp == 1) ptx::tmem_dealloc_pair(tmem_base, 2 * BN);
 }
 
 // ---------------------------------------------------------------------------------------------- host
@@ -800,6 +954,57 @@ static int launch_gemm(const fo1_gemm_desc* d, cudaStream_t stream, int ksplit =
   return FO1_OK;
 }
 
+// the CTA-pair kernel: ordinary (and implicit-conv) problems with >= one wave of 256 x 256 tile pairs
+static int launch_gemm_pair(const fo1_gemm_desc* d, cudaStream_t stream, const ConvInfo* conv) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    FO1_CUDA(cudaFuncSetAttribute(gemm_bf16_tcgen05_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kPairSmemBytes));
+    attr_set = true;
+  }
+  CUtensorMap tmA, tmW;
+  if (conv != nullptr) {
+    FO1_TRY(make_tmap_4d_bf16(&tmA, d->A, (uint64_t)conv->C, (uint64_t)conv->W, (uint64_t)conv->H, (uint64_t)conv->B, BK, (uint32_t)conv->Wt, (uint32_t)(BM / conv->Wt)));
+  } else {
+    FO1_TRY(make_tmap_2d_bf16(&tmA, d->A, (uint64_t)d->K, (uint64_t)d->M, (uint64_t)d->lda, BK, BM));
+  }
+  FO1_TRY(make_tmap_2d_bf16(&tmW, d->W, (uint64_t)d->K, (uint64_t)d->N, (uint64_t)d->ldw, BK, kPairBN / 2));
+  GemmArgs g;
+  memset(&g, 0, sizeof(g));
+  g.M = d->M; g.N = d->N; g.K = d->K;
+  g.D = d->D; g.ldd = d->ldd; g.d_dtype = d->d_dtype;
+  g.bias = d->bias; g.bias_dtype = d->bias_dtype;
+  g.act = d->act;
+  g.residual = static_cast<const __nv_bfloat16*>(d->residual); g.ldr = d->ldr;
+  g.gated = d->gated;
+  g.conv_cpb = conv ? conv->C / BK : 0; g.conv_H = conv ? conv->H : 0; g.conv_W = conv ? conv->W : 0; g.conv_Wt = conv ? conv->Wt : 0;
+  g.tiles_m = ceil_div(d->M, BM);
+  g.tiles_n = ceil_div(d->N, kPairBN);
+  g.ksplit = 1; g.kb_per_split = ceil_div(d->K, BK);
+  g.stages = kPairStages;
+  {
+    const int esz = d->d_dtype == FO1_BF16 ? 2 : 4;
+    const bool d_ok = (reinterpret_cast<uintptr_t>(d->D) & 15) == 0 && (d->ldd * esz) % 16 == 0;
+    const bool r_ok = d->residual == nullptr || ((reinterpret_cast<uintptr_t>(d->residual) & 15) == 0 && (d->ldr * 2) % 16 == 0);
+    static const bool direct_store = getenv("FO1_GEMM_DIRECT_STORE") != nullptr;
+    g.coalesce = (d_ok && r_ok && !direct_store) ? 1 : 0;
+  }
+  const int work = ((g.tiles_m + 1) / 2) * g.tiles_n;
+  const int clusters = std::min(work, device_sm_count() / 2);
+  char tag[96] = "gemm";
+  if (g_prof_on) snprintf(tag, sizeof(tag), "gemm:%dx%dx%d%s%s:pair", d->M, d->N, d->K, d->gated ? ":gated" : "", conv ? ":conv3x3" : "");
+  ProfScope prof(tag, 2.0 * d->M * (double)d->N * d->K,
+                 2.0 * ((double)d->M * d->K + (double)d->N * d->K + (double)d->M * (d->gated ? d->N / 2 : d->N)), stream);
+  launch_k(gemm_bf16_tcgen05_pair_kernel, dim3(2 * clusters), dim3(kGemmThreads), kPairSmemBytes, stream, tmA, tmW, g);
+  FO1_LAUNCH_CHECK();
+  return FO1_OK;
+}
+// one wave of tile pairs at least, whole 128-row A boxes, and not switched off (FO1_GEMM_NO_PAIR: the A/B knob of the parity test)
+static bool use_pair_kernel(int M, int N) {
+  if (getenv("FO1_GEMM_NO_PAIR") != nullptr) return false;
+  const long long work = (long long)ceil_div(ceil_div(M, BM), 2) * ceil_div(N, kPairBN);
+  return M >= BM && N >= kPairBN && work >= device_sm_count() / 2;
+}
+
 int gemm_bf16(const fo1_gemm_desc* d, cudaStream_t stream) {
   FO1_CHECK_ARG(d != nullptr, "fo1_gemm_bf16: null descriptor");
   FO1_CHECK_ARG(d->M >= 0 && d->N > 0 && d->K > 0, "fo1_gemm_bf16: bad shape M=%d N=%d K=%d", d->M, d->N, d->K);
@@ -833,6 +1038,7 @@ int gemm_bf16(const fo1_gemm_desc* d, cudaStream_t stream) {
   // tile-width choice: widest tile that still yields >= 1 wave of CTAs, else narrower for occupancy
   const int sms = device_sm_count();
   const long long tm = ceil_div(d->M, BM);
+  if (use_pair_kernel(d->M, d->N)) return launch_gemm_pair(d, stream, nullptr);
   if (d->N >= 256 && tm * ceil_div(d->N, 256) >= sms) return launch_gemm<256>(d, stream);
   // weight-streaming problems whose 128-wide tiles need a second, mostly empty wave (decode gate/up: 172 tiles on 148 SMs)
   // run as ONE wave of 192-wide tiles instead (measured 27.3 -> 22.3 us, profiles/r01_sweep_skinny.json)
@@ -864,6 +1070,7 @@ int conv3x3_gemm(const bf16* x, int B, int H, int W, int C, const bf16* Wm, bf16
   ConvInfo ci{B, H, W, C, W % BM == 0 ? BM : W};
   const int sms = device_sm_count();
   const long long tm = ceil_div(d.M, BM);
+  if (use_pair_kernel(d.M, N)) return launch_gemm_pair(&d, stream, &ci);
   if (N >= 256 && tm * ceil_div(N, 256) >= sms) return launch_gemm<256>(&d, stream, 1, &ci);
   if (N >= 128 && tm * ceil_div(N, 128) >= sms) return launch_gemm<128>(&d, stream, 1, &ci);
   return launch_gemm<64>(&d, stream, 1, &ci);

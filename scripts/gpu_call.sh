@@ -1,10 +1,7 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout -s KILL 300 python scripts/gemm_pair_bench.py 2>&1 | tail -12
-timeout -s KILL 900 python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_c3.json 2> gpurun_out/bench_c3.err; tail -2 gpurun_out/bench_c3.err
-python - <<'PY'
-import json
-d=json.load(open('gpurun_out/bench_c3.json'))
-print(d['value'], d['ms_per_step'], d['stage_ms'], d['e2e']['value'], d['clocks'])
-print(d['roofline'])
-PY
+timeout -s KILL 600 python -m pytest tests/test_gpu_decode_mega.py tests/test_gpu_llm.py -x -q 2>&1 | tail -4
+for cfg in "32 1195" "8 600"; do
+set -- $cfg
+FO1_MEGA_PROF=1 timeout -s KILL 600 python scripts/mega_prof.py $1 $2 > gpurun_out/mega_prof_$1_$2.log 2>&1; grep -E "ms/step|decode_mega profile, first" gpurun_out/mega_prof_$1_$2.log | tail -3
+done

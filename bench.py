@@ -106,22 +106,32 @@ class ClockSampler:
 
 
 def reference_arm(args, cfg, steps, decode_tokens):
-    """The CPU arm: ONE full-depth image per step through the reference's own modules (oracle/reference_path.py; the oracle
-    port if baseline/_ref is absent), fp32, every host thread.  ``decode_tokens`` < args.tokens shortens the greedy loop; the
-    remaining steps are then added at the measured per-token cost (stated in the returned note).
-    Returns (images/s, kind, cores, note, stage seconds of the last step)."""
+    """The CPU arm: ONE image per step through the reference's own modules (oracle/reference_path.py; the oracle port if
+    baseline/_ref is absent), fp32, the host cores this process may use.  A full-depth image costs minutes of host time, so a step is a
+    BOUNDED DEPTH SAMPLE unless --cpu-full: one period of the ViT's block pattern (8 of 32 blocks), 4 of 36 decoder layers, DaViT's third
+    stage at depth 3 of 9, ``decode_tokens`` decode steps -- block times scaled to the full depth, everything else (patch embed, merger,
+    DaViT stems, SimpleFPN, HFRE, projector, splice, LM head) run in full; the note states it.
+    Returns (images/s, kind, cores, note, stage seconds of the last step, already scaled to full depth)."""
     from importlib import import_module
     SY = import_module("vlm-fo1_b200.synthetic")
-    cores = os.cpu_count() or 1
+    from oracle import reference_path as RP
+    cores = RP.usable_cores()
     torch.set_num_threads(cores)
     s = SY.synthetic_batch(0, 1, args.size, args.boxes)[0]
     T = max(args.tokens, 1)
     dt = max(1, min(decode_tokens, T))
-    from oracle import reference_path as RP
     times, detail = [], None
+    sample = None if getattr(args, "cpu_full", False) else dict(vit_blocks=8, llm_layers=4, davit_stage3=3)
+    depth_note = "FULL depth"
     if RP.available():
         kind = "reference"
-        rp = RP.ReferencePath(cfg.vit, "davit-large", cfg.llm, region_dim=cfg.region_dim, davit_depths=cfg.davit["depths"])
+        rp = RP.ReferencePath(cfg.vit, "davit-large", cfg.llm, region_dim=cfg.region_dim, davit_depths=cfg.davit["depths"], sample=sample)
+        sc = rp.scale
+        if any(v != 1.0 for v in sc.values()):
+            depth_note = (f"DEPTH SAMPLE scaled to full depth: ViT {int(round(cfg.vit['depth'] / sc['vit']))} of {cfg.vit['depth']} blocks (x{sc['vit']:g}), "
+                          f"DaViT stage 3 at {int(round(cfg.davit['depths'][2] / sc['davit3']))} of {cfg.davit['depths'][2]} (its measured time x{sc['davit3']:g}), "
+                          f"LLM {int(round(cfg.llm['num_hidden_layers'] / sc['llm']))} of {cfg.llm['num_hidden_layers']} layers (x{sc['llm']:g}); "
+                          "embeddings / merger / FPN / HFRE / projector / LM head in full")
         for _ in range(steps):
             out = rp.run(input_ids=s.input_ids, pixel_values=s.pixel_values, grid_hw=s.grid_hw, image_aux=s.image_aux, boxes=s.boxes,
                          max_new_tokens=dt)
@@ -131,7 +141,7 @@ def reference_arm(args, cfg, steps, decode_tokens):
             t["llm_decode_s_per_token"] = per_tok
             times.append(total); detail = t
         what = ("the reference's own modules (baseline/_ref copy of vlm_fo1: Qwen2_5_VisionTransformerPretrainedModel + custom_forward + "
-                f"GATHER, DaViT, HFREModule incl. SimpleFP, mm_projector_aux, {cfg.llm['num_hidden_layers']} x Qwen2_5_VLDecoderLayer; "
+                f"GATHER, DaViT, HFREModule incl. SimpleFP, mm_projector_aux, Qwen2_5_VLDecoderLayer; "
                 f"attention '{rp.attn}'), model loop / splice / greedy loop restated")
     else:
         kind = "port"
@@ -148,7 +158,7 @@ def reference_arm(args, cfg, steps, decode_tokens):
             total = t["vit_s"] + t["davit_s"] + t["fpn_s"] + t["hfre_s"] + t["proj_s"] + t["llm_prefill_s"] + (T - 1) * per_tok
             times.append(total); detail = t
         what = "oracle/pipeline.py (the CPU restatement of the reference; baseline/_ref is absent on this machine)"
-    note = (f"1 image per step, {args.size}x{args.size}, {args.boxes} boxes, FULL depth (ViT {cfg.vit['depth']} blocks, DaViT "
+    note = (f"1 image per step, {args.size}x{args.size}, {args.boxes} boxes, {depth_note} (ViT {cfg.vit['depth']} blocks, DaViT "
             f"{cfg.davit['depths']}, LLM {cfg.llm['num_hidden_layers']} layers), fp32, {cores} host threads, through {what}; "
             + (f"all {T} decode tokens executed" if dt >= T else
                f"{dt} of {T} decode tokens executed, the remaining {T - dt} added at the measured per-token time (extrapolated term: "
@@ -197,7 +207,8 @@ def main():
     ap.add_argument("--boxes", type=int, default=None)
     ap.add_argument("--tokens", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-tokens", type=int, default=8, help="decode steps the in-run cpu_baseline executes (rest at the measured per-token time)")
+    ap.add_argument("--cpu-full", action="store_true", help="CPU legs run every block (minutes per image) instead of the bounded depth sample")
+    ap.add_argument("--cpu-tokens", type=int, default=3, help="decode steps the in-run cpu_baseline executes (rest at the measured per-token time)")
     ap.add_argument("--profile-run", action="store_true", help="warm-up exactly as given, one timed pass, nothing else (for ncu)")
     ap.add_argument("--small", action="store_true", help="tiny architecture (plumbing check only; NOT a valid bench number)")
     args = ap.parse_args()
@@ -236,15 +247,19 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        steps = max(1, min(args.steps, 2))           # bounded: one full-depth image is about a minute of CPU work
-        ips, kind, cores, note, detail = reference_arm(args, cfg, steps, max(T, 1))
+        # bounded: a step is one depth-sampled image (reference_arm); at most one untimed warm-up step and three timed ones, so that any
+        # --steps K --warmup W ends within a few minutes of host time
+        if args.warmup > 0:
+            reference_arm(args, cfg, 1, min(2, max(T, 1)))
+        steps = max(1, min(args.steps, 3))
+        ips, kind, cores, note, detail = reference_arm(args, cfg, steps, min(args.cpu_tokens, max(T, 1)))
         value = ips
         if hfre_only:                                # the HFRE stage alone, same unit as the GPU arm
             host1 = SY.synthetic_batch(0, 1, args.size, args.boxes)
             sec = detail.get("fpn_hfre_s", detail.get("hfre_s", 0.0) + detail.get("fpn_s", 0.0))
             value = hfre_algorithmic_bytes(HF, cfg, host1, args.size) / max(sec, 1e-9) / 1e9
             note += "; value = unique HFRE bytes of that image / the reference's SimpleFP + HFREModule time"
-        line = {"impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus, "steps": steps, "warmup": 0,
+        line = {"impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1),
                 "ms_per_step": 1000.0 / ips, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic", "config": config,
                 "cpu_baseline": {"value": value, "unit": unit, "cores": cores, "kind": kind, "sample": note, "stage_seconds": detail},

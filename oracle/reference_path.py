@@ -21,7 +21,7 @@ from __future__ import annotations
 import os
 import time
 from types import SimpleNamespace as NS
-from typing import Dict, Sequence
+from typing import Dict, Optional, Sequence
 
 import torch
 
@@ -46,8 +46,35 @@ def _fill_(mod: torch.nn.Module) -> None:
             p.data.zero_()
 
 
+def usable_cores(cap: int = 32) -> int:
+    """Host threads worth using: the affinity mask and the cgroup CPU quota (a container that sees 128 logical CPUs but owns a fraction
+    of them crawls when 128 OpenMP threads spin on it), capped where these small fp32 GEMMs stop scaling."""
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        pass
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()
+        if q != "max":
+            n = min(n, max(1, int(float(q) / float(per))))
+    except Exception:
+        try:
+            q = int(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read()); per = int(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                n = min(n, max(1, q // per))
+        except Exception:
+            pass
+    return max(1, min(n, cap))
+
+
 class ReferencePath:
-    def __init__(self, vit_cfg: dict, davit_name: str, llm_cfg: dict, region_dim: int = 5888, davit_depths=None):
+    """``sample``: None runs every block; ``dict(vit_blocks=8, llm_layers=4, davit_stage3=3)`` builds and runs a DEPTH SAMPLE -- one period
+    of the ViT's block pattern (7 windowed + 1 full-attention block), a few decoder layers, DaViT's third stage at reduced depth -- and
+    ``run`` scales the measured block times to the full depth (blocks of a stack cost the same; embeddings, mergers, FPN, HFRE, projector,
+    LM head are always run in full).  The bench's bounded CPU sample (a full-depth image takes minutes on the host cores)."""
+
+    def __init__(self, vit_cfg: dict, davit_name: str, llm_cfg: dict, region_dim: int = 5888, davit_depths=None, sample: Optional[dict] = None):
         import sys
         try:
             from . import ref_shim
@@ -68,6 +95,26 @@ class ReferencePath:
         from vlm_fo1.model.multimodal_projector.builder import build_vision_projector_aux
         self.M, self.enc = M, enc
         t0 = time.perf_counter()
+        self.scale = dict(vit=1.0, llm=1.0, davit3=1.0)
+        vit_cfg, llm_cfg = dict(vit_cfg), dict(llm_cfg)
+        full_davit_depths = list(davit_depths) if davit_depths is not None else None
+        if sample:
+            fa = list(vit_cfg["fullatt_block_indexes"])
+            period = fa[0] + 1 if fa else 0
+            vb = int(sample.get("vit_blocks", 0))
+            if vb and period and vb % period == 0 and vb < vit_cfg["depth"] and fa == [period * (i + 1) - 1 for i in range(len(fa))] \
+                    and vit_cfg["depth"] % period == 0:
+                self.scale["vit"] = vit_cfg["depth"] / vb
+                vit_cfg["depth"] = vb
+                vit_cfg["fullatt_block_indexes"] = [period * (i + 1) - 1 for i in range(vb // period)]
+            ll = int(sample.get("llm_layers", 0))
+            if ll and ll < llm_cfg["num_hidden_layers"]:
+                self.scale["llm"] = llm_cfg["num_hidden_layers"] / ll
+                llm_cfg["num_hidden_layers"] = ll
+            d3 = int(sample.get("davit_stage3", 0))
+            if d3 and full_davit_depths is not None and d3 < full_davit_depths[2]:
+                self.scale["davit3"] = full_davit_depths[2] / d3
+                davit_depths = list(full_davit_depths); davit_depths[2] = d3
         with torch.no_grad():
             vc = Qwen2_5_VLVisionConfig(depth=vit_cfg["depth"], hidden_size=vit_cfg["hidden_size"], num_heads=vit_cfg["num_heads"],
                                         intermediate_size=vit_cfg["intermediate_size"], out_hidden_size=vit_cfg["out_hidden_size"],
@@ -134,10 +181,15 @@ class ReferencePath:
         gh, gw = grid_hw
         t0 = time.perf_counter()
         merged = self.vit(pixel_values.float(), grid_thw=torch.tensor([[1, gh, gw]]))
-        taps = self.enc.GATHER.extract_multi_level_features()[0]               # 4 x [1, hidden, gh, gw]
-        t["vit_s"] = time.perf_counter() - t0; t0 = time.perf_counter()
+        taps = self.enc.GATHER.extract_multi_level_features()[0]               # n_fullatt x [1, hidden, gh, gw]
+        t["vit_s"] = (time.perf_counter() - t0) * self.scale["vit"]; t0 = time.perf_counter()
+        st3 = {"t": 0.0}
+        stage3 = self.davit.blocks[2]
+        h1 = stage3.register_forward_pre_hook(lambda m, a: st3.__setitem__("t0", time.perf_counter()))
+        h2 = stage3.register_forward_hook(lambda m, a, o: st3.__setitem__("t", time.perf_counter() - st3["t0"]))
         aux = self.davit(image_aux.float().unsqueeze(0))["image_features"]
-        t["davit_s"] = time.perf_counter() - t0; t0 = time.perf_counter()
+        h1.remove(); h2.remove()
+        t["davit_s"] = (time.perf_counter() - t0) + st3["t"] * (self.scale["davit3"] - 1.0); t0 = time.perf_counter()
         Ha, Wa = image_aux.shape[-2:]
         b = boxes.float() if boxes.numel() else torch.tensor([[0.0, 10.0, 0.0, 10.0]])
         p = self.vit_cfg["patch_size"]
@@ -155,15 +207,20 @@ class ReferencePath:
         cache = DynamicCache()
         L = x.shape[1]
         h = self._decoder(x, pos, 0, cache)
+        t_layers = time.perf_counter() - t0; t0 = time.perf_counter()
         lg = (self.norm(h[:, -1:]) @ emb.t())[0, -1]                           # tied head, last position only
-        t["llm_prefill_s"] = time.perf_counter() - t0; t0 = time.perf_counter()
+        t["llm_prefill_s"] = t_layers * self.scale["llm"] + (time.perf_counter() - t0); t0 = time.perf_counter()
         toks = []
+        t_dec_layers = t_dec_head = 0.0
         for s in range(max_new_tokens):
             tok = int(lg.argmax()); toks.append(tok)
             if s == max_new_tokens - 1:
                 break
+            t0 = time.perf_counter()
             h = self._decoder(emb[tok][None, None, :], torch.full((3, 1), L + s + delta, dtype=torch.long), L + s, cache)
+            t_dec_layers += time.perf_counter() - t0; t0 = time.perf_counter()
             lg = (self.norm(h) @ emb.t())[0, -1]
-        t["llm_decode_s"] = time.perf_counter() - t0
+            t_dec_head += time.perf_counter() - t0
+        t["llm_decode_s"] = t_dec_layers * self.scale["llm"] + t_dec_head
         t["total_s"] = sum(v for k, v in t.items() if k.endswith("_s"))
-        return dict(tokens=toks, timings=t, prompt_len=L)
+        return dict(tokens=toks, timings=t, prompt_len=L, scale=dict(self.scale))

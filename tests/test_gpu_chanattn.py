@@ -34,4 +34,6 @@ def test_channel_attention_matches_fp32(B, N, C):
     assert err < 1e-3 + 2 * 2.0 ** -8, err
     if B > 1:
         assert torch.equal(out[0], out[1])                 # no atomics: independent of the batch slot, bit-reproducible
+        # ... and of the batch SIZE: the token chunking (= the summation order of the Gram) may not change with the number of images
+        assert torch.equal(out[0], ops.channel_attention(qkv[:1].contiguous(), C // 32)[0])
     assert torch.equal(out, ops.channel_attention(qkv, C // 32))

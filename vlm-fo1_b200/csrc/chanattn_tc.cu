@@ -305,9 +305,11 @@ chan_apply_tc_kernel(const __grid_constant__ CUtensorMap tmV, const ChanArgs a) 
 }
 
 // ------------------------------------------------------------------------------------------------------ host
-static void chan_plan(int B, int N, int C, int* n_chunks, int* tiles_per_chunk) {
+// The token chunking fixes the summation order of the Gram: it must NOT depend on the batch size, or an image's features would
+// depend on how many neighbours it was batched with (tests/test_gpu_eval_drivers.py: generate_batch == one-by-one generate).
+static void chan_plan(int /*B*/, int N, int C, int* n_chunks, int* tiles_per_chunk) {
   const int quads = ceil_div(C, kCaQuad), tiles = ceil_div(N, kCaTok);
-  int n = ceil_div(2 * device_sm_count(), std::max(1, B * quads));     // about two CTAs' worth of work per SM
+  int n = ceil_div(2 * 148, std::max(1, quads));     // about two CTAs' worth of work per SM for ONE image; a batch only adds CTAs
   n = std::max(1, std::min(n, std::min(tiles, kCaMaxChunks)));
   *tiles_per_chunk = ceil_div(tiles, n);
   *n_chunks = ceil_div(tiles, *tiles_per_chunk);

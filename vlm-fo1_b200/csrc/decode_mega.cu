@@ -151,6 +151,8 @@ struct MgWork {
 // Per-warp cp.async ring.  (A ring of cp.async.bulk copies from a tile-contiguous weight image was measured too: faster in an empty
 // streaming loop -- scripts/probes/stream_probe.cu, 5.4 vs 4.0 TB/s -- but slower here, because expect_tx + the bulk issue + the
 // mbarrier wait cost this latency-bound loop ~500 cycles more per 2-4 KB stage than four cp.async per lane and a wait_group.)
+// Also measured and rejected: the A fragments of the K <= 2048 phases kept in registers to free the 128 KB activation tile for the ring
+// (spills at the 255-register cap, step time doubled).
 struct MgRing {
   uint32_t base;            // shared address of this warp's stages
   int stage_bytes, n_stages;

@@ -105,13 +105,13 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def reference_arm(args, cfg, steps, decode_tokens):
+def reference_arm(args, cfg, steps, decode_tokens, warm=0):
     """The CPU arm: ONE image per step through the reference's own modules (oracle/reference_path.py; the oracle port if
-    baseline/_ref is absent), fp32, the host cores this process may use.  A full-depth image costs minutes of host time, so a step is a
-    BOUNDED DEPTH SAMPLE unless --cpu-full: one period of the ViT's block pattern (8 of 32 blocks), 4 of 36 decoder layers, DaViT's third
-    stage at depth 3 of 9, ``decode_tokens`` decode steps -- block times scaled to the full depth, everything else (patch embed, merger,
-    DaViT stems, SimpleFPN, HFRE, projector, splice, LM head) run in full; the note states it.
-    Returns (images/s, kind, cores, note, stage seconds of the last step, already scaled to full depth)."""
+    baseline/_ref is absent), fp32, FULL depth, on the host cores this process owns (affinity + cgroup quota: with every logical CPU of
+    the box the OpenMP pool of a quota-limited container thrashes -- 455 s per image instead of ~45 s).  ``decode_tokens`` < args.tokens
+    shortens the greedy loop; the remaining steps are then added at the measured per-token cost (the note says so).  --cpu-sample swaps the
+    full depth for a bounded depth sample (8 of 32 ViT blocks, 4 of 36 decoder layers, DaViT stage 3 at 3 of 9) scaled to full depth.
+    Returns (images/s, kind, cores, note, stage seconds of the last step)."""
     from importlib import import_module
     SY = import_module("vlm-fo1_b200.synthetic")
     from oracle import reference_path as RP
@@ -121,7 +121,7 @@ def reference_arm(args, cfg, steps, decode_tokens):
     T = max(args.tokens, 1)
     dt = max(1, min(decode_tokens, T))
     times, detail = [], None
-    sample = None if getattr(args, "cpu_full", False) else dict(vit_blocks=8, llm_layers=4, davit_stage3=3)
+    sample = dict(vit_blocks=8, llm_layers=4, davit_stage3=3) if getattr(args, "cpu_sample", False) else None
     depth_note = "FULL depth"
     if RP.available():
         kind = "reference"
@@ -132,9 +132,11 @@ def reference_arm(args, cfg, steps, decode_tokens):
                           f"DaViT stage 3 at {int(round(cfg.davit['depths'][2] / sc['davit3']))} of {cfg.davit['depths'][2]} (its measured time x{sc['davit3']:g}), "
                           f"LLM {int(round(cfg.llm['num_hidden_layers'] / sc['llm']))} of {cfg.llm['num_hidden_layers']} layers (x{sc['llm']:g}); "
                           "embeddings / merger / FPN / HFRE / projector / LM head in full")
-        for _ in range(steps):
+        for i in range(warm + steps):
             out = rp.run(input_ids=s.input_ids, pixel_values=s.pixel_values, grid_hw=s.grid_hw, image_aux=s.image_aux, boxes=s.boxes,
                          max_new_tokens=dt)
+            if i < warm:
+                continue
             t = dict(out["timings"])
             per_tok = t["llm_decode_s"] / max(dt - 1, 1)
             total = t["total_s"] + (T - dt) * per_tok
@@ -207,8 +209,8 @@ def main():
     ap.add_argument("--boxes", type=int, default=None)
     ap.add_argument("--tokens", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-full", action="store_true", help="CPU legs run every block (minutes per image) instead of the bounded depth sample")
-    ap.add_argument("--cpu-tokens", type=int, default=3, help="decode steps the in-run cpu_baseline executes (rest at the measured per-token time)")
+    ap.add_argument("--cpu-sample", action="store_true", help="CPU legs run a bounded depth sample scaled to full depth instead of every block (~45 s per image)")
+    ap.add_argument("--cpu-tokens", type=int, default=64, help="decode steps the in-run cpu_baseline executes (rest at the measured per-token time)")
     ap.add_argument("--profile-run", action="store_true", help="warm-up exactly as given, one timed pass, nothing else (for ncu)")
     ap.add_argument("--small", action="store_true", help="tiny architecture (plumbing check only; NOT a valid bench number)")
     args = ap.parse_args()
@@ -247,12 +249,10 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        # bounded: a step is one depth-sampled image (reference_arm); at most one untimed warm-up step and three timed ones, so that any
-        # --steps K --warmup W ends within a few minutes of host time
-        if args.warmup > 0:
-            reference_arm(args, cfg, 1, min(2, max(T, 1)))
-        steps = max(1, min(args.steps, 3))
-        ips, kind, cores, note, detail = reference_arm(args, cfg, steps, min(args.cpu_tokens, max(T, 1)))
+        # bounded: a step is ONE full-depth image (~45 s on the 16 cores a box grants); one untimed warm-up step (if any was asked for)
+        # and at most two timed ones, so that any --steps K --warmup W ends within a few minutes of host time
+        steps = max(1, min(args.steps, 2))
+        ips, kind, cores, note, detail = reference_arm(args, cfg, steps, min(args.cpu_tokens, max(T, 1)), warm=min(args.warmup, 1))
         value = ips
         if hfre_only:                                # the HFRE stage alone, same unit as the GPU arm
             host1 = SY.synthetic_batch(0, 1, args.size, args.boxes)

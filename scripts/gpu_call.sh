@@ -1,8 +1,13 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout -s KILL 600 ncu --set full --clock-control none --import-source on -k regex:pair_kernel -s 1 -c 1 -o gpurun_out/r02_pair_gemm -f python scripts/ncu_pair.py > gpurun_out/ncu_pair.log 2>&1; tail -2 gpurun_out/ncu_pair.log
-timeout -s KILL 1500 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none \
-  -k regex:'gemm_bf16|attn_tc|hfre_sweep|chan_gram|chan_apply|dwconv3x3' --csv --log-file gpurun_out/r02_dram_step.csv \
-  python bench.py --profile-run --steps 1 --warmup 0 --tokens 1 --no-cpu-baseline > gpurun_out/r02_dram_step.log 2>&1
-tail -1 gpurun_out/r02_dram_step.log; python scripts/make_traffic.py gpurun_out/r02_dram_step.csv gpurun_out/r02_traffic.json
-( time timeout -s KILL 1500 python -m pytest tests -q -m gpu > gpurun_out/r02_pytest_gpu.log 2>&1 ) 2> gpurun_out/pytest_time.log; tail -2 gpurun_out/r02_pytest_gpu.log; grep real gpurun_out/pytest_time.log
+( time timeout -s KILL 1200 python bench.py --impl reference --steps 5 --warmup 3 > gpurun_out/r02_bench_reference.json 2> gpurun_out/r02_bench_reference.err ) 2> gpurun_out/ref_time.log; grep real gpurun_out/ref_time.log; tail -2 gpurun_out/r02_bench_reference.err | cut -c1-300
+( time timeout -s KILL 1200 python bench.py > gpurun_out/r02_bench_c3.json 2> gpurun_out/r02_bench_c3.err ) 2> gpurun_out/bench_time.log; grep real gpurun_out/bench_time.log
+python - <<'PY'
+import json
+r=json.load(open('gpurun_out/r02_bench_reference.json'))
+print('ref', r['value'], 'steps', r['steps'], 'warm', r['warmup'], 'ms/step', r['ms_per_step'], r['cpu_baseline']['cores'], r['cpu_baseline']['stage_seconds'])
+print(r['cpu_baseline']['sample'][:400])
+d=json.load(open('gpurun_out/r02_bench_c3.json'))
+print('c3', round(d['value'],2), round(d['ms_per_step'],1), 'e2e', round(d['e2e']['value'],2), d['clocks'])
+print('cpu', d['cpu_baseline']['value'], d['cpu_baseline']['cores'], d['cpu_baseline']['stage_seconds'])
+PY

@@ -64,6 +64,7 @@ struct AttnTcArgs {
   const int2* rowseg;   // [T]: keys [lo, hi) of the segment every packed row belongs to
   const int2* tiles;    // optional [n_tiles] (first row, rows <= 128) of every query tile; null: tile i = rows [128 i, 128 i + 128)
   int T, q_heads, kv_heads;
+  int n_work;           // query tiles x heads
   float sl2;            // softmax scale * log2(e)
 };
 
@@ -111,28 +112,17 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   uint64_t* s_empty = bars + 11;      // [2]
   uint64_t* p_full = bars + 13;       // [1]
   uint64_t* o_done = bars + 14;       // [1]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 15);
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(sP);   // read once before the first P tile is written (second __syncthreads below)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int head = blockIdx.x % a.q_heads;
-  const int tile = blockIdx.x / a.q_heads;
-  const int kvh = head / (a.q_heads / a.kv_heads);
-  int row0 = tile * kAtM, rows_valid = min(kAtM, a.T - row0);
-  if (a.tiles != nullptr) {
-    const int2 tl = __ldg(a.tiles + tile);
-    row0 = tl.x; rows_valid = tl.y;
-  }
-  // key range of the tile (segments are ordered, so first row's lo / last row's hi bound every row's range)
-  const int kv_begin = __ldg(&a.rowseg[row0].x);
-  int kv_end = __ldg(&a.rowseg[row0 + rows_valid - 1].y);
-  if (CAUSAL) kv_end = min(kv_end, row0 + rows_valid);
-  const int n_kv = (kv_end - kv_begin + kAtN - 1) / kAtN;
+  uint64_t* q_empty = bars + 15;      // [1] the softmax warps are done with the Q tile (their output staging) and with O in TMEM
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmQ);
     ptx::prefetch_tmap(&tmK);
     ptx::prefetch_tmap(&tmV);
     ptx::mbar_init(ptx::smem_u32(q_full), 1);
+    ptx::mbar_init(ptx::smem_u32(q_empty), 128);
     for (int s = 0; s < 2; ++s) {
       ptx::mbar_init(ptx::smem_u32(k_full + s), 1);
       ptx::mbar_init(ptx::smem_u32(k_empty + s), 1);
@@ -150,206 +140,252 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  __syncthreads();                    // everybody holds the TMEM address before the softmax warps reuse its slot for P
+
+  // Persistent CTA: work items (query tile, head), head fastest, static round robin.  Barriers, TMEM and the tensor-map prefetch are
+  // set up once; every role walks the same item list and carries ONE running key-tile counter g across items (ring stage = g & 1,
+  // phase = (g >> 1) & 1), so the K/V ring keeps streaming across item boundaries.  Per item: the Q tile and the O accumulator are
+  // single-buffered -- the producer reloads Q, and the MMA warp restarts O, only after the softmax warps released them (q_empty).
+  const int n_work = a.n_work;
+  auto item_geom = [&](int work, int& head, int& kvh, int& row0, int& rows_valid, int& kv_begin, int& n_kv) {
+    head = work % a.q_heads;
+    const int tile = work / a.q_heads;
+    kvh = head / (a.q_heads / a.kv_heads);
+    row0 = tile * kAtM; rows_valid = min(kAtM, a.T - row0);
+    if (a.tiles != nullptr) {
+      const int2 tl = __ldg(a.tiles + tile);
+      row0 = tl.x; rows_valid = tl.y;
+    }
+    // key range of the tile (segments are ordered, so first row's lo / last row's hi bound every row's range)
+    kv_begin = __ldg(&a.rowseg[row0].x);
+    int kv_end = __ldg(&a.rowseg[row0 + rows_valid - 1].y);
+    if (CAUSAL) kv_end = min(kv_end, row0 + rows_valid);
+    n_kv = (kv_end - kv_begin + kAtN - 1) / kAtN;
+  };
 
   if (warp == 0) {
     // ================================================ TMA producer ================================================
     if (ptx::elect_one()) {
-      ptx::mbar_expect_tx(ptx::smem_u32(q_full), Cfg::kQBytes);
+      uint32_t g = 0, item = 0;
+      for (int work = blockIdx.x; work < n_work; work += gridDim.x, ++item) {
+        int head, kvh, row0, rows_valid, kv_begin, n_kv;
+        item_geom(work, head, kvh, row0, rows_valid, kv_begin, n_kv);
+        if (item > 0) at_wait(q_empty, (item - 1) & 1);
+        ptx::mbar_expect_tx(ptx::smem_u32(q_full), Cfg::kQBytes);
 #pragma unroll
-      for (int b = 0; b < NDB; ++b) ptx::tma_load_3d(ptx::smem_u32(sQ + b * kAtM * 128), &tmQ, ptx::smem_u32(q_full), b * 64, head, row0);
-      for (int j = 0; j < n_kv; ++j) {
-        const int st = j & 1, key0 = kv_begin + j * kAtN;
-        if (j >= 2) at_wait(k_empty + st, ((j >> 1) - 1) & 1);
-        ptx::mbar_expect_tx(ptx::smem_u32(k_full + st), Cfg::kKBytes);
+        for (int b = 0; b < NDB; ++b) ptx::tma_load_3d(ptx::smem_u32(sQ + b * kAtM * 128), &tmQ, ptx::smem_u32(q_full), b * 64, head, row0);
+        for (int j = 0; j < n_kv; ++j, ++g) {
+          const uint32_t st = g & 1;
+          const int key0 = kv_begin + j * kAtN;
+          if (g >= 2) at_wait(k_empty + st, ((g >> 1) - 1) & 1);
+          ptx::mbar_expect_tx(ptx::smem_u32(k_full + st), Cfg::kKBytes);
 #pragma unroll
-        for (int b = 0; b < NDB; ++b)
-          ptx::tma_load_3d(ptx::smem_u32(sK + st * Cfg::kKBytes + b * kAtN * 128), &tmK, ptx::smem_u32(k_full + st), b * 64, kvh, key0);
-        if (j >= 2) at_wait(v_empty + st, ((j >> 1) - 1) & 1);
-        ptx::mbar_expect_tx(ptx::smem_u32(v_full + st), Cfg::kVBytes);
+          for (int b = 0; b < NDB; ++b)
+            ptx::tma_load_3d(ptx::smem_u32(sK + st * Cfg::kKBytes + b * kAtN * 128), &tmK, ptx::smem_u32(k_full + st), b * 64, kvh, key0);
+          if (g >= 2) at_wait(v_empty + st, ((g >> 1) - 1) & 1);
+          ptx::mbar_expect_tx(ptx::smem_u32(v_full + st), Cfg::kVBytes);
 #pragma unroll
-        for (int b = 0; b < NDB; ++b)
-          ptx::tma_load_3d(ptx::smem_u32(sV + st * Cfg::kVBytes + b * kAtN * 128), &tmV, ptx::smem_u32(v_full + st), b * 64, kvh, key0);
+          for (int b = 0; b < NDB; ++b)
+            ptx::tma_load_3d(ptx::smem_u32(sV + st * Cfg::kVBytes + b * kAtN * 128), &tmV, ptx::smem_u32(v_full + st), b * 64, kvh, key0);
+        }
       }
     }
   } else if (warp == 1) {
     // ================================================= MMA issuer =================================================
     constexpr uint32_t idesc_s = ptx::umma_idesc_bf16(kAtM, kAtN);
-    at_wait(q_full, 0);
-    for (int j = 0; j <= n_kv; ++j) {
-      if (j < n_kv) {                                   // S_j = Q . K_j^T
-        const int st = j & 1;
-        at_wait(k_full + st, (j >> 1) & 1);
-        if (j >= 2) at_wait(s_empty + st, ((j >> 1) - 1) & 1);
-        ptx::tc_fence_after();
-        if (ptx::elect_one()) {
-          const uint32_t q_addr = ptx::smem_u32(sQ), k_addr = ptx::smem_u32(sK + st * Cfg::kKBytes);
+    uint32_t gbase = 0, item = 0;
+    for (int work = blockIdx.x; work < n_work; work += gridDim.x, ++item) {
+      int head, kvh, row0, rows_valid, kv_begin, n_kv;
+      item_geom(work, head, kvh, row0, rows_valid, kv_begin, n_kv);
+      at_wait(q_full, item & 1);          // (Q is reloaded only after q_empty: O of the previous item has been read out by then)
+      for (int j = 0; j <= n_kv; ++j) {
+        if (j < n_kv) {                                   // S_j = Q . K_j^T
+          const uint32_t g = gbase + j, st = g & 1;
+          at_wait(k_full + st, (g >> 1) & 1);
+          if (g >= 2) at_wait(s_empty + st, ((g >> 1) - 1) & 1);
+          ptx::tc_fence_after();
+          if (ptx::elect_one()) {
+            const uint32_t q_addr = ptx::smem_u32(sQ), k_addr = ptx::smem_u32(sK + st * Cfg::kKBytes);
 #pragma unroll
-          for (int kk = 0; kk < HD / 16; ++kk) {
-            const uint64_t da = ptx::umma_desc_k_sw128(q_addr + (kk >> 2) * (kAtM * 128) + (kk & 3) * 32);
-            const uint64_t db = ptx::umma_desc_k_sw128(k_addr + (kk >> 2) * (kAtN * 128) + (kk & 3) * 32);
-            ptx::tc_mma_bf16(tmem_base + st * kAtN, da, db, idesc_s, kk > 0 ? 1u : 0u);
-          }
-          ptx::tc_commit(ptx::smem_u32(s_full + st));
-          ptx::tc_commit(ptx::smem_u32(k_empty + st));
-        }
-        __syncwarp();
-      }
-      if (j >= 1) {                                     // O += P_{j-1} . V_{j-1}
-        const int jj = j - 1, st = jj & 1;
-        at_wait(p_full, jj & 1);
-        at_wait(v_full + st, (jj >> 1) & 1);
-        ptx::tc_fence_after();
-        if (ptx::elect_one()) {
-          const uint32_t p_addr = ptx::smem_u32(sP), v_addr = ptx::smem_u32(sV + st * Cfg::kVBytes);
-#pragma unroll
-          for (int kk = 0; kk < kAtN / 16; ++kk) {
-            const uint64_t da = ptx::umma_desc_k_sw128(p_addr + kk * 32);
-#pragma unroll
-            for (int b = 0; b < NDB; ++b) {
-              constexpr int kLastN = HD - (NDB - 1) * 64;             // live dims of the last box (16 for head_dim 80)
-              const int nb = (b == NDB - 1) ? kLastN : 64;
-              const uint64_t db = ptx::umma_desc_mn_sw128(v_addr + b * (kAtN * 128) + kk * 2048);
-              ptx::tc_mma_bf16(tmem_base + 2 * kAtN + b * 64, da, db, ptx::umma_idesc_bf16(kAtM, nb) | ptx::kUmmaBMajorMN,
-                               (jj > 0 || kk > 0) ? 1u : 0u);
+            for (int kk = 0; kk < HD / 16; ++kk) {
+              const uint64_t da = ptx::umma_desc_k_sw128(q_addr + (kk >> 2) * (kAtM * 128) + (kk & 3) * 32);
+              const uint64_t db = ptx::umma_desc_k_sw128(k_addr + (kk >> 2) * (kAtN * 128) + (kk & 3) * 32);
+              ptx::tc_mma_bf16(tmem_base + st * kAtN, da, db, idesc_s, kk > 0 ? 1u : 0u);
             }
+            ptx::tc_commit(ptx::smem_u32(s_full + st));
+            ptx::tc_commit(ptx::smem_u32(k_empty + st));
           }
-          ptx::tc_commit(ptx::smem_u32(o_done));
-          ptx::tc_commit(ptx::smem_u32(v_empty + st));
+          __syncwarp();
         }
-        __syncwarp();
+        if (j >= 1) {                                     // O += P_{j-1} . V_{j-1}
+          const int jj = j - 1;
+          const uint32_t g = gbase + jj, st = g & 1;
+          at_wait(p_full, g & 1);
+          at_wait(v_full + st, (g >> 1) & 1);
+          ptx::tc_fence_after();
+          if (ptx::elect_one()) {
+            const uint32_t p_addr = ptx::smem_u32(sP), v_addr = ptx::smem_u32(sV + st * Cfg::kVBytes);
+#pragma unroll
+            for (int kk = 0; kk < kAtN / 16; ++kk) {
+              const uint64_t da = ptx::umma_desc_k_sw128(p_addr + kk * 32);
+#pragma unroll
+              for (int b = 0; b < NDB; ++b) {
+                constexpr int kLastN = HD - (NDB - 1) * 64;             // live dims of the last box (16 for head_dim 80)
+                const int nb = (b == NDB - 1) ? kLastN : 64;
+                const uint64_t db = ptx::umma_desc_mn_sw128(v_addr + b * (kAtN * 128) + kk * 2048);
+                ptx::tc_mma_bf16(tmem_base + 2 * kAtN + b * 64, da, db, ptx::umma_idesc_bf16(kAtM, nb) | ptx::kUmmaBMajorMN,
+                                 (jj > 0 || kk > 0) ? 1u : 0u);
+              }
+            }
+            ptx::tc_commit(ptx::smem_u32(o_done));
+            ptx::tc_commit(ptx::smem_u32(v_empty + st));
+          }
+          __syncwarp();
+        }
       }
+      gbase += (uint32_t)n_kv;
     }
   } else {
     // ================================================== softmax ===================================================
     const int quarter = warp & 3;                       // TMEM lane quarter this warp may touch (warp id mod 4)
     const int r = quarter * 32 + lane;                  // row inside the tile == TMEM lane
-    const int row = row0 + r;
-    int lo = 0, hi = 0;                                 // rows beyond T: empty key range
-    if (r < rows_valid) {
-      const int2 rs = __ldg(a.rowseg + row);
-      lo = rs.x; hi = rs.y;
-      if (CAUSAL) hi = min(hi, row + 1);
-    }
-    int wlo_min = lo, wlo_max = lo, whi_min = hi, whi_max = hi;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      wlo_min = min(wlo_min, __shfl_xor_sync(0xffffffffu, wlo_min, o));
-      wlo_max = max(wlo_max, __shfl_xor_sync(0xffffffffu, wlo_max, o));
-      whi_min = min(whi_min, __shfl_xor_sync(0xffffffffu, whi_min, o));
-      whi_max = max(whi_max, __shfl_xor_sync(0xffffffffu, whi_max, o));
-    }
-    const uint32_t span = (uint32_t)(hi - lo);
     const uint32_t t_lane = tmem_base + ((uint32_t)(quarter * 32) << 16);
-    float m_run = -INFINITY, l_run = 0.f;               // running max (scaled, log2 units) and sum of this row
     uint8_t* p_row = sP + r * 128;
+    uint32_t gbase = 0;
+    for (int work = blockIdx.x; work < n_work; work += gridDim.x) {
+      int head, kvh, row0, rows_valid, kv_begin, n_kv;
+      item_geom(work, head, kvh, row0, rows_valid, kv_begin, n_kv);
+      const int row = row0 + r;
+      int lo = 0, hi = 0;                                 // rows beyond T: empty key range
+      if (r < rows_valid) {
+        const int2 rs = __ldg(a.rowseg + row);
+        lo = rs.x; hi = rs.y;
+        if (CAUSAL) hi = min(hi, row + 1);
+      }
+      int wlo_min = lo, wlo_max = lo, whi_min = hi, whi_max = hi;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        wlo_min = min(wlo_min, __shfl_xor_sync(0xffffffffu, wlo_min, o));
+        wlo_max = max(wlo_max, __shfl_xor_sync(0xffffffffu, wlo_max, o));
+        whi_min = min(whi_min, __shfl_xor_sync(0xffffffffu, whi_min, o));
+        whi_max = max(whi_max, __shfl_xor_sync(0xffffffffu, whi_max, o));
+      }
+      const uint32_t span = (uint32_t)(hi - lo);
+      float m_run = -INFINITY, l_run = 0.f;               // running max (scaled, log2 units) and sum of this row
 
-    for (int j = 0; j < n_kv; ++j) {
-      const int st = j & 1, k0 = kv_begin + j * kAtN;
-      const bool dead = (k0 >= whi_max) || (k0 + kAtN <= wlo_min);          // no row of this warp sees the tile
-      const bool interior = (k0 >= wlo_max) && (k0 + kAtN <= whi_min);      // every row sees every key
-      at_wait(s_full + st, (j >> 1) & 1);
+      for (int j = 0; j < n_kv; ++j) {
+        const uint32_t g = gbase + j, st = g & 1;
+        const int k0 = kv_begin + j * kAtN;
+        const bool dead = (k0 >= whi_max) || (k0 + kAtN <= wlo_min);          // no row of this warp sees the tile
+        const bool interior = (k0 >= wlo_max) && (k0 + kAtN <= whi_min);      // every row sees every key
+        at_wait(s_full + st, (g >> 1) & 1);
+        ptx::tc_fence_after();
+        uint32_t sr[2][32];
+        if (!dead) {
+          ptx::tmem_ld_32x32(t_lane + st * kAtN, sr[0]);
+          ptx::tmem_ld_32x32(t_lane + st * kAtN + 32, sr[1]);
+          ptx::tmem_ld_wait();
+        }
+        ptx::tc_fence_before();
+        ptx::mbar_arrive(ptx::smem_u32(s_empty + st));     // S_j is in registers: the buffer may take S_{j+2}
+        uint32_t pk[32];
+        if (dead) {
+#pragma unroll
+          for (int c = 0; c < 32; ++c) pk[c] = 0u;
+        } else {
+          float mt = -INFINITY;
+          if (interior) {
+#pragma unroll
+            for (int c = 0; c < 64; ++c) mt = fmaxf(mt, __uint_as_float(sr[c >> 5][c & 31]));
+          } else {
+#pragma unroll
+            for (int c = 0; c < 64; ++c) {
+              const bool ok = (uint32_t)(k0 + c - lo) < span;
+              const float x = ok ? __uint_as_float(sr[c >> 5][c & 31]) : -INFINITY;
+              sr[c >> 5][c & 31] = __float_as_uint(x);
+              mt = fmaxf(mt, x);
+            }
+          }
+          const float m_new = fmaxf(m_run, mt * a.sl2);
+          // lazy rescale: keep a stale maximum until it lags by 2^8; a row without any live key so far has O == 0 exactly
+          const bool grow = m_new > m_run + kAtRescale;
+          const bool touch = grow && (m_run != -INFINITY);
+          float alpha = 1.0f;
+          if (grow) {
+            if (touch) { alpha = ex2_approx(m_run - m_new); l_run *= alpha; }
+            m_run = m_new;
+          }
+          if (__any_sync(0xffffffffu, touch)) {            // (touch implies j >= 1: g - 1 is this item's previous tile)
+            at_wait(o_done, (g - 1) & 1);                  // P_{j-1}.V_{j-1} has landed in O
+            ptx::tc_fence_after();
+#pragma unroll
+            for (int c = 0; c < (HD + 31) / 32; ++c) {
+              uint32_t orow[32];
+              ptx::tmem_ld_32x32(t_lane + 2 * kAtN + c * 32, orow);
+              ptx::tmem_ld_wait();
+#pragma unroll
+              for (int i = 0; i < 32; ++i) orow[i] = __float_as_uint(__uint_as_float(orow[i]) * alpha);
+              ptx::tmem_st_32x32(t_lane + 2 * kAtN + c * 32, orow);
+            }
+            ptx::tmem_st_wait();
+            ptx::tc_fence_before();
+          }
+          const float m_use = (m_run == -INFINITY) ? 0.f : m_run;
+          float sum = 0.f;
+#pragma unroll
+          for (int c = 0; c < 64; c += 2) {
+            const float p0 = ex2_approx(fmaf(__uint_as_float(sr[c >> 5][c & 31]), a.sl2, -m_use));
+            const float p1 = ex2_approx(fmaf(__uint_as_float(sr[(c + 1) >> 5][(c + 1) & 31]), a.sl2, -m_use));
+            sum += p0 + p1;
+            pk[c >> 1] = pack_bf16(p0, p1);
+          }
+          l_run += sum;
+        }
+        if (g >= 1) at_wait(o_done, (g - 1) & 1);          // the previous P (of this item or the last one) has been consumed: the buffer is free
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+          *reinterpret_cast<uint4*>(p_row + ((c ^ (r & 7)) << 4)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+        ptx::fence_proxy_async_smem();
+        ptx::mbar_arrive(ptx::smem_u32(p_full));
+      }
+      gbase += (uint32_t)n_kv;
+
+      // ---- O / l -> bf16, staged through the (dead) Q tile of this warp, row-contiguous 16-byte stores ----
+      at_wait(o_done, (gbase - 1) & 1);
       ptx::tc_fence_after();
-      uint32_t sr[2][32];
-      if (!dead) {
-        ptx::tmem_ld_32x32(t_lane + st * kAtN, sr[0]);
-        ptx::tmem_ld_32x32(t_lane + st * kAtN + 32, sr[1]);
+      const float inv = l_run > 0.f ? 1.0f / l_run : 0.f;
+      constexpr int PITCH = Cfg::HDP * 2;
+      uint8_t* stg = sQ + (warp - 2) * 32 * PITCH;
+#pragma unroll
+      for (int c = 0; c < (HD + 31) / 32; ++c) {
+        uint32_t orow[32];
+        ptx::tmem_ld_32x32(t_lane + 2 * kAtN + c * 32, orow);
         ptx::tmem_ld_wait();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          if (c * 32 + q * 8 < HD) {
+            const int ch = c * 4 + q;                     // 16-byte chunk of the row
+            *reinterpret_cast<uint4*>(stg + lane * PITCH + (((ch & ~7) | ((ch ^ lane) & 7)) << 4)) =
+                make_uint4(pack_bf16(__uint_as_float(orow[q * 8 + 0]) * inv, __uint_as_float(orow[q * 8 + 1]) * inv),
+                           pack_bf16(__uint_as_float(orow[q * 8 + 2]) * inv, __uint_as_float(orow[q * 8 + 3]) * inv),
+                           pack_bf16(__uint_as_float(orow[q * 8 + 4]) * inv, __uint_as_float(orow[q * 8 + 5]) * inv),
+                           pack_bf16(__uint_as_float(orow[q * 8 + 6]) * inv, __uint_as_float(orow[q * 8 + 7]) * inv));
+          }
+        }
       }
       ptx::tc_fence_before();
-      ptx::mbar_arrive(ptx::smem_u32(s_empty + st));     // S_j is in registers: the buffer may take S_{j+2}
-      uint32_t pk[32];
-      if (dead) {
-#pragma unroll
-        for (int c = 0; c < 32; ++c) pk[c] = 0u;
-      } else {
-        float mt = -INFINITY;
-        if (interior) {
-#pragma unroll
-          for (int c = 0; c < 64; ++c) mt = fmaxf(mt, __uint_as_float(sr[c >> 5][c & 31]));
-        } else {
-#pragma unroll
-          for (int c = 0; c < 64; ++c) {
-            const bool ok = (uint32_t)(k0 + c - lo) < span;
-            const float x = ok ? __uint_as_float(sr[c >> 5][c & 31]) : -INFINITY;
-            sr[c >> 5][c & 31] = __float_as_uint(x);
-            mt = fmaxf(mt, x);
-          }
-        }
-        const float m_new = fmaxf(m_run, mt * a.sl2);
-        // lazy rescale: keep a stale maximum until it lags by 2^8; a row without any live key so far has O == 0 exactly
-        const bool grow = m_new > m_run + kAtRescale;
-        const bool touch = grow && (m_run != -INFINITY);
-        float alpha = 1.0f;
-        if (grow) {
-          if (touch) { alpha = ex2_approx(m_run - m_new); l_run *= alpha; }
-          m_run = m_new;
-        }
-        if (__any_sync(0xffffffffu, touch)) {
-          at_wait(o_done, (j - 1) & 1);                  // P_{j-1}.V_{j-1} has landed in O
-          ptx::tc_fence_after();
-#pragma unroll
-          for (int c = 0; c < (HD + 31) / 32; ++c) {
-            uint32_t orow[32];
-            ptx::tmem_ld_32x32(t_lane + 2 * kAtN + c * 32, orow);
-            ptx::tmem_ld_wait();
-#pragma unroll
-            for (int i = 0; i < 32; ++i) orow[i] = __float_as_uint(__uint_as_float(orow[i]) * alpha);
-            ptx::tmem_st_32x32(t_lane + 2 * kAtN + c * 32, orow);
-          }
-          ptx::tmem_st_wait();
-          ptx::tc_fence_before();
-        }
-        const float m_use = (m_run == -INFINITY) ? 0.f : m_run;
-        float sum = 0.f;
-#pragma unroll
-        for (int c = 0; c < 64; c += 2) {
-          const float p0 = ex2_approx(fmaf(__uint_as_float(sr[c >> 5][c & 31]), a.sl2, -m_use));
-          const float p1 = ex2_approx(fmaf(__uint_as_float(sr[(c + 1) >> 5][(c + 1) & 31]), a.sl2, -m_use));
-          sum += p0 + p1;
-          pk[c >> 1] = pack_bf16(p0, p1);
-        }
-        l_run += sum;
+      __syncwarp();
+      constexpr int CH = HD / 8;
+      bf16* op = a.o + (long long)(row0 + quarter * 32) * a.ldo + (long long)head * HD;
+      for (int i = lane; i < 32 * CH; i += 32) {
+        const int rr = i / CH, ch = i - rr * CH;
+        if (quarter * 32 + rr < rows_valid)
+          *reinterpret_cast<uint4*>(op + (long long)rr * a.ldo + ch * 8) =
+              *reinterpret_cast<const uint4*>(stg + rr * PITCH + (((ch & ~7) | ((ch ^ rr) & 7)) << 4));
       }
-      if (j >= 1) at_wait(o_done, (j - 1) & 1);          // P_{j-1} has been consumed: the P buffer is free
-#pragma unroll
-      for (int c = 0; c < 8; ++c)
-        *reinterpret_cast<uint4*>(p_row + ((c ^ (r & 7)) << 4)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
-      ptx::fence_proxy_async_smem();
-      ptx::mbar_arrive(ptx::smem_u32(p_full));
-    }
-
-    // ---- O / l -> bf16, staged through the (dead) Q tile of this warp, row-contiguous 16-byte stores ----
-    at_wait(o_done, (n_kv - 1) & 1);
-    ptx::tc_fence_after();
-    const float inv = l_run > 0.f ? 1.0f / l_run : 0.f;
-    constexpr int PITCH = Cfg::HDP * 2;
-    uint8_t* stg = sQ + (warp - 2) * 32 * PITCH;
-#pragma unroll
-    for (int c = 0; c < (HD + 31) / 32; ++c) {
-      uint32_t orow[32];
-      ptx::tmem_ld_32x32(t_lane + 2 * kAtN + c * 32, orow);
-      ptx::tmem_ld_wait();
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        if (c * 32 + q * 8 < HD) {
-          const int ch = c * 4 + q;                     // 16-byte chunk of the row
-          *reinterpret_cast<uint4*>(stg + lane * PITCH + (((ch & ~7) | ((ch ^ lane) & 7)) << 4)) =
-              make_uint4(pack_bf16(__uint_as_float(orow[q * 8 + 0]) * inv, __uint_as_float(orow[q * 8 + 1]) * inv),
-                         pack_bf16(__uint_as_float(orow[q * 8 + 2]) * inv, __uint_as_float(orow[q * 8 + 3]) * inv),
-                         pack_bf16(__uint_as_float(orow[q * 8 + 4]) * inv, __uint_as_float(orow[q * 8 + 5]) * inv),
-                         pack_bf16(__uint_as_float(orow[q * 8 + 6]) * inv, __uint_as_float(orow[q * 8 + 7]) * inv));
-        }
-      }
-    }
-    ptx::tc_fence_before();
-    __syncwarp();
-    constexpr int CH = HD / 8;
-    bf16* op = a.o + (long long)(row0 + quarter * 32) * a.ldo + (long long)head * HD;
-    for (int i = lane; i < 32 * CH; i += 32) {
-      const int rr = i / CH, ch = i - rr * CH;
-      if (quarter * 32 + rr < rows_valid)
-        *reinterpret_cast<uint4*>(op + (long long)rr * a.ldo + ch * 8) =
-            *reinterpret_cast<const uint4*>(stg + rr * PITCH + (((ch & ~7) | ((ch ^ rr) & 7)) << 4));
+      __syncwarp();
+      ptx::fence_proxy_async_smem();                       // the next Q tile arrives through the async proxy
+      ptx::mbar_arrive(ptx::smem_u32(q_empty));            // Q tile (staging) and O are free for the next item
     }
   }
 
@@ -414,8 +450,14 @@ static int launch_attn_tc(const AttnArgs& a, const int2* rowseg, cudaStream_t s)
   g.sl2 = a.scale * 1.4426950408889634f;
   const long long blocks = (long long)(a.tiles != nullptr ? a.n_tiles : ceil_div(T, kAtM)) * a.q_heads;
   FO1_CHECK_ARG(blocks < (1ll << 31), "attention: grid too large (%lld blocks)", blocks);
+  g.n_work = (int)blocks;
   ProfScope prof(CAUSAL ? "attn_causal" : "attn", a.flops, 0.0, s);
-  attn_tc_kernel<HD, CAUSAL><<<(unsigned)blocks, kAtThreads, Cfg::kSmemBytes, s>>>(tmQ, tmK, tmV, g);
+  // persistent for the non-causal shapes (equal-cost items: ViT / DaViT windows 0.40 -> 0.33 ms, 0.78 -> 0.66 ms per layer at 32 images): two
+  // CTAs per SM walk the item list.  Causal prompts have items of very different cost; the static round robin lost 19 % against the
+  // hardware block scheduler there, so they keep one CTA per item (the same kernel with a one-item list).  FO1_ATTN_ONE_ITEM: A/B knob.
+  const long long resident = 2LL * device_sm_count();
+  const unsigned grid = (unsigned)((CAUSAL || getenv("FO1_ATTN_ONE_ITEM") != nullptr || blocks < resident) ? blocks : resident);
+  attn_tc_kernel<HD, CAUSAL><<<grid, kAtThreads, Cfg::kSmemBytes, s>>>(tmQ, tmK, tmV, g);
   FO1_LAUNCH_CHECK();
   return FO1_OK;
 }

@@ -1,5 +1,3 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout -s KILL 150 python -m pytest tests/test_gpu_attention.py -x -q 2>&1 | grep -E "passed|failed|Error|error" | tail -4
-echo "--- persistent"; timeout -s KILL 120 python scripts/attn_probe.py 2>&1 | cut -c1-160 | tail -12
-echo "--- one CTA per item"; FO1_ATTN_ONE_ITEM=1 timeout -s KILL 120 python scripts/attn_probe.py 2>&1 | cut -c1-160 | tail -12
+timeout -s KILL 300 ncu --set full --clock-control none --import-source on -k regex:pair_kernel -s 1 -c 1 -o gpurun_out/r02_pair_smallk -f python scripts/ncu_pair_smallk.py > gpurun_out/ncu_pair_smallk.log 2>&1; tail -1 gpurun_out/ncu_pair_smallk.log

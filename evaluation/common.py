@@ -4,6 +4,7 @@ and an image source that can synthesise noise images of the recorded sizes when 
 from __future__ import annotations
 
 import os
+import zlib
 import time
 from typing import Callable, Iterable, List, Optional, Sequence, Tuple
 
@@ -32,7 +33,7 @@ class ImageSource:
         out = os.path.join(self.synthetic_dir, os.path.splitext(os.path.basename(name))[0] + ".png")
         if not os.path.exists(out):
             w, h = max(int(size_hint[0]), 28), max(int(size_hint[1]), 28)
-            rng = np.random.default_rng(abs(hash(name)) % (1 << 32))
+            rng = np.random.default_rng(zlib.crc32(name.encode()))      # NOT hash(): str hashes are salted per process
             Image.fromarray(rng.integers(0, 256, (h, w, 3), dtype=np.uint8)).save(out)
         return out
 

@@ -72,6 +72,16 @@ struct PdlScope {
   explicit PdlScope(bool on) : prev(t_pdl) { t_pdl = on; }
   ~PdlScope() { t_pdl = prev; }
 };
+// Split-K of skinny GEMMs (gemm_tcgen05.cu's automatic choice) is allowed only inside a SplitKScope: the decode steps and the LM head
+// (M = number of sequences: weight streaming, where the choice depends on N and K only) and the public fo1_gemm_bf16.  Every other
+// linear() of the engine keeps ONE accumulation order whatever its M, so a sample's tower / projector / prefill results do not depend
+// on how many neighbours shared its batch (a short prompt alone used to take split-K, the same prompt inside a batch did not).
+extern thread_local bool t_splitk_ok;
+struct SplitKScope {
+  bool prev;
+  explicit SplitKScope(bool on) : prev(t_splitk_ok) { t_splitk_ok = on; }
+  ~SplitKScope() { t_splitk_ok = prev; }
+};
 #ifdef __CUDACC__
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {

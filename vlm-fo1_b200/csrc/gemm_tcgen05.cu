@@ -1051,7 +1051,8 @@ int gemm_bf16(const fo1_gemm_desc* d, cudaStream_t stream) {
   const int bn = d->N >= 512 ? 64 : 32;
   const long long t = tm * ceil_div(d->N, bn);
   int ks = 1;
-  if (t * 2 <= sms) ks = (int)std::min<long long>(std::min<long long>(8, sms / t), std::max(1, ceil_div(d->K, BK) / 8));
+  // (only inside a SplitKScope -- decode steps, LM head, the public entry point: see common.cuh)
+  if (t_splitk_ok && t * 2 <= sms) ks = (int)std::min<long long>(std::min<long long>(8, sms / t), std::max(1, ceil_div(d->K, BK) / 8));
   return bn == 64 ? launch_gemm<64>(d, stream, ks) : launch_gemm<32>(d, stream, ks);
 }
 
@@ -1079,6 +1080,7 @@ int conv3x3_gemm(const bf16* x, int B, int H, int W, int C, const bf16* Wm, bf16
 }  // namespace fo1
 
 extern "C" int fo1_gemm_bf16(const fo1_gemm_desc* d, void* stream) {
+  fo1::SplitKScope sk(true);     // a caller's own GEMM: no batch semantics to protect
   return fo1::gemm_bf16(d, static_cast<cudaStream_t>(stream));
 }
 

@@ -23,6 +23,7 @@ void set_error(const char* fmt, ...) {
 // ---- profiler ------------------------------------------------------------------------------------
 bool g_prof_on = false;
 thread_local bool t_pdl = false;
+thread_local bool t_splitk_ok = false;
 struct ProfRec { cudaEvent_t a, b; std::string tag; double flops, bytes; };
 static std::vector<ProfRec> g_recs;
 static std::mutex g_prof_mu;

@@ -79,8 +79,8 @@ def test_generate_batch_equals_one_by_one(setup):
         same += int(one.shape == got.shape and torch.equal(one, got))
     # This fabricated checkpoint has ONE random-init decoder layer: its logits are nearly flat, so a last-bit difference anywhere
     # upstream flips a token (measured: whole-batch equality in about half of the runs while the noise images were still salted per
-    # process, i.e. roughly one flip per 60 tokens; they are crc32-seeded now).  Every stage's batch-size independence is asserted bit for
-    # bit where it is decidable (test_gpu_chanattn, test_gpu_hfre packed path, test_gpu_gemm_pair, test_gpu_dp_ids); the source of the
-    # remaining last-bit difference between the batched and the single call is an open item.  Asserted here: the
-    # batch call returns well-formed sequences, the first tokens agree for all but at most one sample, most sequences agree entirely.
+    # process, i.e. roughly one flip per 60 tokens; they are crc32-seeded now).  Two row-count heuristics that made a sample's numerics
+    # depend on the batch size (norm kernel choice below 593 rows, split-K by tile count) were removed AFTER the last GPU run of the
+    # round; until that is confirmed on a GPU the assertion is: well-formed sequences, first tokens agree for all
+    # but at most one sample, most sequences agree entirely.  TODO(next round): torch.equal for every sample.
     assert first_same >= len(kws) - 1 and same >= 3, (first_same, same)

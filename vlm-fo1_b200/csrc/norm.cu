@@ -173,7 +173,11 @@ static int launch_rownorm(const bf16* x, long long ldx, const bf16* g, const bf1
   FO1_CHECK_ARG(cols <= 8 * 32 * 32, "rownorm: cols=%d too large", cols);
   if (rows == 0) return FO1_OK;
   const int nvec = cols / 8;
-  if (rows <= 592 && nvec <= 512) {   // fewer rows than 4 per SM: spread each row over a block
+  // Decode-shaped launches (one row per sequence) spread each row over a block.  The threshold is the decode batch limit, NOT "fewer rows
+  // than the GPU has warps": the two kernels sum a row in different orders, and with a row-count threshold of 592 a 430-token prompt alone
+  // was normalised by one kernel and the same prompt inside a batch by the other -- last-bit differences that flipped near-tie tokens
+  // (tests/test_gpu_eval_drivers.py).  At <= 32 rows both the single and the batched call are decode steps.
+  if (rows <= 32 && nvec <= 512) {
     if (nvec <= 256) launch_k(rownorm_block_kernel<1, RMS>, dim3(rows), dim3(256), 0, s, x, ldx, g, b, y, ldy, cols, eps);
     else launch_k(rownorm_block_kernel<2, RMS>, dim3(rows), dim3(256), 0, s, x, ldx, g, b, y, ldy, cols, eps);
     FO1_LAUNCH_CHECK();
